@@ -1,0 +1,37 @@
+"""Named switches for upstream-NeMo details recalled from memory.
+
+Each constant selects between behaviours that different NeMo 1.x/2.x releases
+(or an imperfect recollection) could have.  The product path implements the
+default value of every switch; tests flip them only on the oracle side to show
+which ones change results.
+"""
+
+# features.FilterbankFeatures.forward: 2.x masks the pre-emphasised signal beyond
+# seq_len ("timemask") -- irrelevant under fixed_seq collate (all lengths equal).
+PREEMPH_TIMEMASK = True
+
+# label_models.EncDecSpeakerLabelModel.__setup_dataloader_from_config uses
+# dataset.fixed_seq_collate_fn: short segments in a batch are *tiled* (repeated)
+# up to the batch max length, and every length becomes that max.
+# "pad" would be the generic _speech_collate_fn (zero pad, true lengths).
+COLLATE = "fixed_seq"  # or "pad"
+
+# speaker_utils.get_subsegments: "classic" python loop (<= 1.2x) or the
+# torch.arange/round(decimals=2) variant that appeared in 2.x.
+SUBSEGMENT_RULE = "classic"  # or "v2"
+MIN_SUBSEGMENT_DURATION = 0.05
+
+# offline_clustering.getKneighborsConnections builds the binarized matrix in
+# half precision; the degree vector of getLaplacian is therefore rounded to fp16.
+BINARIZE_HALF = True
+
+# offline_clustering.getLaplacian: unnormalised L = D - A.
+LAPLACIAN = "unnormalized"
+
+# offline_clustering.cos_similarity eps added to the norm.
+COS_EPS = 3.5e-4
+
+# SpeakerClustering / NMESC defaults (not forwarded from YAML by perform_clustering)
+MIN_SAMPLES_FOR_NMESC = 6
+NME_MAT_SIZE = 512
+ENHANCED_COUNT_THRES = 80
