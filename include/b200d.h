@@ -1,0 +1,212 @@
+/*
+ * b200d.h -- C ABI of the B200-native diarization hot path (libb200d.so).
+ *
+ * Drop-in boundary for the path the reference reaches at
+ *   /root/reference/diarize.py:200-201 and /root/reference/nemo_process.py:31-32
+ *   (`NeuralDiarizer(cfg=create_config(dir)).to(device).diarize()` ->
+ *    NeMo `ClusteringDiarizer(cfg).diarize()`),
+ * configured by /root/reference/nemo_msdd_configs/diar_infer_*.yaml:39-56 and
+ * /root/reference/helpers.py:252-303.  The reference itself has no FFI for this
+ * path: the arithmetic lives in nemo-toolkit (PyTorch ops -> cuFFT/cuDNN/cuBLAS/
+ * cuSOLVER).  Each entry point below therefore cites the upstream NeMo function
+ * whose device work it replaces; INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    its name ends in _host; the caller (PyTorch) owns all memory;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *    hidden synchronisation, no allocation, no retained pointers;
+ *  - return 0 on success, a negative B200D_E* code on failure;
+ *    b200d_last_error() returns a thread-local message;
+ *  - sm_100a only; there is no CPU path.
+ */
+#ifndef B200D_H_
+#define B200D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200D_OK 0
+#define B200D_EINVAL (-1)   /* bad shape / alignment / null pointer          */
+#define B200D_EARCH (-2)    /* device is not sm_100                           */
+#define B200D_ELAUNCH (-3)  /* CUDA launch or driver error (see last_error)   */
+#define B200D_EWORKSPACE (-4) /* workspace too small                          */
+
+const char* b200d_version(void);
+const char* b200d_last_error(void);
+/* 0 if the current device is sm_100 and the driver entry points were resolved. */
+int b200d_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Featurizer: replaces AudioToSpeechLabelDataset slicing + fixed_seq collate (tiling) and
+ * FilterbankFeatures.forward (nemo/collections/asr/parts/preprocessing/features.py):
+ * pre-emphasis 0.97 -> STFT(n_fft 512, hann 400, hop 160, center/reflect) -> |.|^2 ->
+ * 80 slaney mels -> log(x + 2^-24) -> per-feature mean / unbiased std over the segment.
+ *
+ *  wav          float32 [n_wav]      whole recording(s), resident in HBM
+ *  seg_start    int32   [n_seg]      first sample of each segment in `wav`
+ *  seg_len      int32   [n_seg]      true sample count of each segment (>= 1)
+ *  fixed_len    samples every segment is tiled up to (batch max, fixed_seq collate);
+ *               frames T = fixed_len / 160 + 1
+ *  fb_start     int32   [80]         first FFT bin of each mel filter's support
+ *  fb_off       int32   [81]         offsets of each filter's weights in fb_w (fb_off[80] == fb_nnz)
+ *  fb_w         float32 [fb_nnz]     packed non-zero filterbank weights (librosa slaney), fb_nnz <= 1024
+ *  window       float32 [400]        hann(400, periodic=False)
+ *  out_f16      __half  [n_seg*T][ldo]  channels-last, channels 80..ldo-1 zeroed (ldo >= 80, ldo % 8 == 0)
+ *  out_f32      float32 [n_seg][T][80] or NULL (parity taps)
+ * ------------------------------------------------------------------------------------------ */
+int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, const int32_t* seg_len,
+                    int32_t n_seg, int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off,
+                    const float* fb_w, int32_t fb_nnz, const float* window,
+                    void* out_f16, int32_t ldo, float* out_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TitaNet-L building blocks (nemo/collections/asr/parts/submodules/jasper.py JasperBlock,
+ * MaskedConv1d, SqueezeExcite; modules/conv_asr.py ConvASREncoder, SpeakerDecoder;
+ * parts/submodules/tdnn_attention.py AttentivePoolLayer).  Activations are fp16,
+ * channels-last [n_seg*T][C]; every segment of a call has the same frame count T.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Depthwise 1-D conv over time (groups == C, 'same' zero padding inside each segment).
+ *  x, y __half [n_seg*T][C];  w float32 [ksize][C] (tap-major);  C % 8 == 0; ksize odd <= 15 */
+int b200d_depthwise_conv(const void* x, void* y, const float* w, int32_t n_seg, int32_t T, int32_t C,
+                         int32_t ksize, void* stream);
+
+/* Pointwise conv == GEMM on tcgen05 tensor cores, TMA-fed, TMEM accumulators:
+ *    acc[m][n] = sum_k A[m][k] * W[n][k]      A __half [M][lda], W __half [N][ldw] (both K-major)
+ * followed by one fused epilogue (fp32 math):
+ *   B200D_EPI_BIAS       out16 = acc + bias[n]
+ *   B200D_EPI_BIAS_RELU  out16 = relu(acc + bias[n])
+ *   B200D_EPI_SE_RES     out16 = relu(aux16[m][n] * rowvec[m / rows_per_seg][n] + acc + bias[n])
+ *                        (SE excitation * main branch + BN-folded residual conv, JasperBlock tail)
+ *   B200D_EPI_TDNN       out16 = tanh(scale[n] * relu(acc + rowvec[m / rows_per_seg][n]) + shift[n])
+ *   B200D_EPI_BIAS_F32   out32 = acc + bias[n]
+ *   B200D_EPI_SIGMOID_F32 out32 = 1 / (1 + exp(-acc))          (SqueezeExcite gate)
+ *   B200D_EPI_CHEB       Chebyshev / Laplacian step of the spectral solver (see b200d_cheb_step)
+ * K % 64 == 0, N % 128 == 0 (N % 256 == 0 uses 128x256 tiles), lda/ldw/ldo % 8 == 0.            */
+enum {
+  B200D_EPI_BIAS = 0,
+  B200D_EPI_BIAS_RELU = 1,
+  B200D_EPI_SE_RES = 2,
+  B200D_EPI_TDNN = 3,
+  B200D_EPI_BIAS_F32 = 4,
+  B200D_EPI_CHEB = 5,
+  B200D_EPI_SIGMOID_F32 = 6
+};
+
+typedef struct b200d_gemm_epilogue {
+  int32_t mode;
+  int32_t rows_per_seg;   /* T for SE_RES / TDNN */
+  const float* bias;      /* [N]  (BIAS*, SE_RES) */
+  const float* scale;     /* [N]  (TDNN) */
+  const float* shift;     /* [N]  (TDNN) */
+  const float* rowvec;    /* [M / rows_per_seg][N] (SE_RES: sigmoid gate; TDNN: per-segment bias) */
+  const void* aux16;      /* __half [M][ldo]  (SE_RES main branch) */
+  /* CHEB: out32 = ca * (deg[m] * x32[m][n] - acc) + cb * x32[m][n] + cc * xprev32[m][n];
+   *       and, when vt != NULL, the 3-way bf16 split [hi | mid | lo] of out32, transposed, into
+   *       vt [3*bpad][ldvt] (bpad = 32 for N == 128, 64 for N == 256): the W operand of the next step. */
+  const float* deg;       /* [M] */
+  const float* x32;       /* [M][ldx] */
+  const float* xprev32;   /* [M][ldx] or NULL */
+  float ca, cb, cc;
+  int32_t ldx;
+  void* vt;               /* __nv_bfloat16 [N][ldvt] */
+  int32_t ldvt;
+} b200d_gemm_epilogue;
+
+int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K,
+                   void* out, int32_t ldo, const b200d_gemm_epilogue* epi, void* stream);
+
+/* SqueezeExcite = b200d_time_stats(with_std=0) -> b200d_gemm_f16(fc.0, BIAS_RELU with zero bias)
+ * -> b200d_gemm_f16(fc.2, SIGMOID_F32) -> gate float32 [n_seg][C].                                 */
+
+/* y = relu(x * gate[seg]) elementwise (block without residual: B0, B4).  x,y __half [n_seg*T][C] */
+int b200d_se_apply_relu(const void* x, const float* gate, void* y, int32_t n_seg, int32_t T, int32_t C, void* stream);
+
+/* Per-segment statistics over time.  with_std == 0: mean, __half [n_seg][C] (SqueezeExcite pool).
+ * with_std != 0: [mean | std] __half [n_seg][2*C] (get_statistics_with_mask with uniform weights;
+ * input of the hoisted TDNN context term of AttentivePoolLayer).                                  */
+int b200d_time_stats(const void* x, int32_t n_seg, int32_t T, int32_t C, int32_t with_std, void* out16, void* stream);
+
+/* Attentive statistics pooling: alpha = softmax_t(e), mu = sum alpha x, sg = sqrt(clamp(sum alpha (x-mu)^2, 1e-10)).
+ *  x, e __half [n_seg*T][C];  out16 __half [n_seg][2*C] = [mu | sg]                              */
+int b200d_attn_pool(const void* x, const void* e, int32_t n_seg, int32_t T, int32_t C, void* out16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Affinity (nemo/collections/asr/parts/utils/offline_clustering.py):
+ * cos_similarity + getCosAffinityMatrix + ScalerMinMax per scale, get_argmin_mat/getRepeatedList
+ * mapping, getMultiScaleCosAffinityMatrix fusion.
+ * ------------------------------------------------------------------------------------------ */
+
+/* xn[i] = x[i] / (||x[i]|| + eps)                            x, xn float32 [n][d]           */
+int b200d_l2_normalize(const float* x, float* xn, int32_t n, int32_t d, float eps, void* stream);
+
+/* cos[i][j] = <xn_i, xn_j>, diagonal forced to 1; minmax[0] = min, minmax[1] = max over the whole
+ * matrix (minmax must be initialised by the call itself).  cos float32 [n][n].                  */
+int b200d_cos_affinity(const float* xn, int32_t n, int32_t d, float* cos, float* minmax, void* stream);
+
+/* fused[i][j] (+)= w * (cos_s[map[i]][map[j]] - min) / (max - min).  map int32 [n_base] (sorted
+ * coarse index of every base segment); accumulate == 0 overwrites.                               */
+int b200d_fuse_scale(const float* cos_s, int32_t n_s, const int32_t* map, const float* minmax, float weight,
+                     float* fused, int32_t n_base, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * NME-SC graph + spectrum (getKneighborsConnections, getAffinityGraphMat, getLaplacian,
+ * estimateNumofSpeakers, isGraphFullyConnected, SpectralClustering.getSpectralEmbeddings).
+ * ------------------------------------------------------------------------------------------ */
+
+/* rank[i][j] = position of column j in row i of mat sorted descending (ties: lower column first),
+ * on the strided view mat[i*stride][j*stride], i,j < n (n <= 2048).  rank uint16 [n][n].          */
+int b200d_row_rank(const float* mat, int64_t ld, int32_t stride, int32_t n, void* rank_u16, void* stream);
+
+/* For each p in p_list (host array, np entries): Laplacian of A_p = 0.5*(B_p + B_p^T),
+ * B_p[i][j] = rank[j][i] < p  (column-wise scatter of upstream), diagonal of A zeroed, degree
+ * rounded through fp16 as upstream's half-precision graph does.  lap float32 [np][n][n].         */
+int b200d_laplacian_from_rank(const void* rank_u16, int32_t n, const int32_t* p_list_host, int32_t np,
+                              float* lap, void* stream);
+
+/* Batched symmetric eigenvalues (values only): Householder tridiagonalisation + Sturm bisection.
+ *  a float32 [batch][n][n] (destroyed); evals float32 [batch][n_low + 1] = the n_low smallest
+ *  eigenvalues ascending followed by the largest.  ws: b200d_eigvals_workspace_bytes().           */
+size_t b200d_eigvals_workspace_bytes(int32_t batch, int32_t n);
+int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t n_low, float* evals, void* ws,
+                          size_t ws_bytes, void* stream);
+
+/* Top-p binarisation of the full matrix: a16[i][j] = 0.5*([j in top_p(row i)] + [i in top_p(row j)]),
+ * diagonal zeroed, as __half [n][lda]; deg float32 [n] = row sums (fp16-rounded as upstream).
+ * sel uint8 [n][n] scratch.                                                                       */
+int b200d_topp_binarize(const float* mat, int32_t n, int32_t p, void* a16, int32_t lda, float* deg,
+                        void* sel_u8, void* stream);
+
+/* reach[0] = number of nodes reachable from node 0 in the graph a16 != 0.  frontier/visited
+ * int32 [n] scratch.                                                                              */
+int b200d_graph_reach(const void* a16, int32_t lda, int32_t n, int32_t* visited, int32_t* reach, void* stream);
+
+/* Small dense helpers of the Chebyshev-filtered subspace iteration (bottom-k eigenvectors of L = D - A). */
+/* g[b][b] = X^T Y (double accumulate, float32 out); x,y float32 [n][ld]                          */
+int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, int32_t ld, float* g, void* stream);
+/* In-place symmetric eigendecomposition of g[b][b] (b <= 64) by cyclic Jacobi in fp64:
+ * evals ascending float32 [b], evecs float32 [b][b] (columns).  mode 1: Cholesky instead --
+ * g = R^T R, returns inv(R) in evecs (for CholQR).                                                */
+int b200d_small_eig(float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream);
+/* y[n][b] = x[n][b] * q[b][b]; optionally also writes fp16 hi/lo split transposed (vt_* may be NULL) */
+int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y,
+                    void* vt_hi, void* vt_lo, int32_t ldvt, void* stream);
+
+/* k-means of kmeans_torch / kmeans_plusplus_torch with the RNG draws supplied by the host
+ * (torch.manual_seed(0) stream: first-centre index, rand(30) per further centre, fallback randints).
+ *  x float32 [n][k_dim]; labels int32 [n].                                                        */
+int b200d_kmeans(const float* x, int32_t n, int32_t dim, int32_t n_clusters, int32_t first_center,
+                 const float* rand_vals /*[n_clusters-1][n_trials]*/, int32_t n_trials,
+                 const int32_t* fallback_idx /*[n_fallback]*/, int32_t n_fallback, int32_t iter_limit,
+                 float threshold, int32_t* labels, void* ws, size_t ws_bytes, void* stream);
+size_t b200d_kmeans_workspace_bytes(int32_t n, int32_t dim, int32_t n_clusters, int32_t n_trials);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200D_H_ */

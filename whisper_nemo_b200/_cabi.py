@@ -1,0 +1,128 @@
+"""ctypes binding of libb200d.so (include/b200d.h).  No torch types cross the boundary:
+tensors are passed as raw device pointers + sizes, the stream as a void*.
+
+There is deliberately no fallback: if the library is missing or the device is not
+sm_100, every call raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200d.so")
+
+EPI_BIAS, EPI_BIAS_RELU, EPI_SE_RES, EPI_TDNN, EPI_BIAS_F32, EPI_CHEB, EPI_SIGMOID_F32 = range(7)
+
+
+class GemmEpilogue(Structure):
+    _fields_ = [
+        ("mode", c_int32),
+        ("rows_per_seg", c_int32),
+        ("bias", c_void_p),
+        ("scale", c_void_p),
+        ("shift", c_void_p),
+        ("rowvec", c_void_p),
+        ("aux16", c_void_p),
+        ("deg", c_void_p),
+        ("x32", c_void_p),
+        ("xprev32", c_void_p),
+        ("ca", c_float),
+        ("cb", c_float),
+        ("cc", c_float),
+        ("ldx", c_int32),
+        ("vt", c_void_p),
+        ("ldvt", c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "b200d_version": (c_char_p, []),
+    "b200d_last_error": (c_char_p, []),
+    "b200d_check_device": (c_int32, []),
+    "b200d_featurize": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                  c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200d_depthwise_conv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "b200d_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                 POINTER(GemmEpilogue), c_void_p]),
+    "b200d_time_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_se_apply_relu": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "b200d_attn_pool": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
+    "b200d_cos_affinity": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_fuse_scales": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "b200d_row_rank": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_laplacian_from_rank": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200d_eigvals_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "b200d_eigvals_batched": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200d_topp_binarize": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_graph_reach": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_gram": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_small_eig": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "b200d_right_mul": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "b200d_kmeans_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "b200d_kmeans": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_float,
+                               c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen libb200d.so and declare signatures.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m whisper_nemo_b200.build` "
+            "(there is no CPU / PyTorch fallback for the diarization hot path)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = []
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    lib._b200d_missing = missing  # tests assert this is empty; calling a missing symbol raises AttributeError
+    _lib = lib
+    return lib
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return c_void_p(t)
+    return c_void_p(t.data_ptr())
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = load().b200d_last_error().decode()
+        raise RuntimeError(f"{name} failed ({rc}): {msg}")
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    check(rc, name)
+
+
+def require_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("whisper_nemo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    call("b200d_check_device")

@@ -1,0 +1,181 @@
+// Multi-scale cosine affinity (offline_clustering.cos_similarity / getCosAffinityMatrix /
+// ScalerMinMax / getMultiScaleCosAffinityMatrix of upstream NeMo), fp32 throughout so that the
+// fused matrix stays within 1e-4 absolute of the CPU path.
+//
+//  l2_normalize   xn = x / (||x|| + eps)                          one warp per row
+//  cos_affinity   cos = xn xn^T (diag := 1) + global min / max     64x64 tiles, 4x4 per thread
+//  fuse_scales    fused[i][j] = sum_s w_s (cos_s[m_s(i)][m_s(j)] - min_s) / (max_s - min_s)
+//                 one pass over the N x N output, the per-scale N x N expansions of upstream's
+//                 repeat_interleave are never materialised.
+#include "common.cuh"
+
+namespace b200d {
+
+__global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ xn, int n, int d, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + static_cast<size_t>(row) * d;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) ss = fmaf(xr[k], xr[k], ss);
+  ss = warp_sum(ss);
+  const float denom = sqrtf(ss) + eps;
+  for (int k = lane; k < d; k += 32) xn[static_cast<size_t>(row) * d + k] = xr[k] / denom;
+}
+
+__device__ __forceinline__ unsigned enc_ordered(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__global__ void minmax_init_kernel(unsigned* mm) {
+  mm[0] = 0xFFFFFFFFu;
+  mm[1] = 0u;
+}
+__global__ void minmax_decode_kernel(unsigned* mm) {
+  float* f = reinterpret_cast<float*>(mm);
+  const float mn = dec_ordered(mm[0]), mx = dec_ordered(mm[1]);
+  f[0] = mn;
+  f[1] = mx;
+}
+
+constexpr int CT = 64;  // tile edge
+constexpr int CK = 16;  // k slab
+
+__global__ void __launch_bounds__(256) cos_affinity_kernel(const float* __restrict__ xn, int n, int d, float* __restrict__ cosm,
+                                                           unsigned* __restrict__ mm) {
+  __shared__ float sa[CK][CT + 4];
+  __shared__ float sb[CK][CT + 4];
+  __shared__ float s_min[8], s_max[8];
+  const int bi = blockIdx.y * CT, bj = blockIdx.x * CT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += CK) {
+    // 64 rows x 16 k per operand, 256 threads -> 4 elements each
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + 256 * q;
+      const int r = e >> 4, k = e & 15;
+      const int gi = bi + r, gj = bj + r, gk = k0 + k;
+      sa[k][r] = (gi < n && gk < d) ? xn[static_cast<size_t>(gi) * d + gk] : 0.f;
+      sb[k][r] = (gj < n && gk < d) ? xn[static_cast<size_t>(gj) * d + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = sa[k][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = sb[k][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = bi + ty * 4 + a;
+    if (i >= n) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = bj + tx * 4 + b;
+      if (j >= n) continue;
+      const float v = (i == j) ? 1.f : acc[a][b];
+      cosm[static_cast<size_t>(i) * n + j] = v;
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_min[warp] = mn; s_max[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_min[w]); mx = fmaxf(mx, s_max[w]); }
+    if (mn <= mx) {
+      atomicMin(&mm[0], enc_ordered(mn));
+      atomicMax(&mm[1], enc_ordered(mx));
+    }
+  }
+}
+
+constexpr int kMaxScales = 8;
+struct FuseParams {
+  int S;
+  const float* cosm[kMaxScales];
+  int ns[kMaxScales];
+  const int* map[kMaxScales];
+  const float* minmax[kMaxScales];
+  float w[kMaxScales];
+  float* fused;
+  int n;
+};
+
+__global__ void __launch_bounds__(256) fuse_scales_kernel(const FuseParams p) {
+  const int i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.n) return;
+  float acc = 0.f;
+#pragma unroll 1
+  for (int s = 0; s < p.S; ++s) {
+    const float mn = __ldg(p.minmax[s]), mx = __ldg(p.minmax[s] + 1);
+    const int mi = __ldg(p.map[s] + i), mj = __ldg(p.map[s] + j);
+    const float c = __ldg(p.cosm[s] + static_cast<size_t>(mi) * p.ns[s] + mj);
+    acc += p.w[s] * ((c - mn) / (mx - mn));
+  }
+  p.fused[static_cast<size_t>(i) * p.n + j] = acc;
+}
+
+}  // namespace b200d
+
+using namespace b200d;
+
+extern "C" int b200d_l2_normalize(const float* x, float* xn, int32_t n, int32_t d, float eps, void* stream) {
+  B200D_CHECK_ARG(x && xn && n > 0 && d > 0);
+  l2_normalize_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(x, xn, n, d, eps);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_cos_affinity(const float* xn, int32_t n, int32_t d, float* cosm, float* minmax, void* stream) {
+  B200D_CHECK_ARG(xn && cosm && minmax && n > 1 && d > 0);
+  unsigned* mm = reinterpret_cast<unsigned*>(minmax);
+  minmax_init_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
+  dim3 grid((n + CT - 1) / CT, (n + CT - 1) / CT);
+  cos_affinity_kernel<<<grid, 256, 0, as_stream(stream)>>>(xn, n, d, cosm, mm);
+  minmax_decode_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_fuse_scales(int32_t n_scales, const float* const* cos_host, const int32_t* ns_host, const int32_t* const* map_host,
+                                 const float* const* minmax_host, const float* weights_host, float* fused, int32_t n_base,
+                                 void* stream) {
+  B200D_CHECK_ARG(n_scales > 0 && n_scales <= kMaxScales && cos_host && ns_host && map_host && minmax_host && weights_host && fused);
+  B200D_CHECK_ARG(n_base > 0 && n_base <= 65535 * 64);
+  FuseParams p;
+  p.S = n_scales;
+  for (int s = 0; s < n_scales; ++s) {
+    B200D_CHECK_ARG(cos_host[s] && map_host[s] && minmax_host[s] && ns_host[s] > 0);
+    p.cosm[s] = cos_host[s]; p.ns[s] = ns_host[s]; p.map[s] = map_host[s]; p.minmax[s] = minmax_host[s]; p.w[s] = weights_host[s];
+  }
+  p.fused = fused;
+  p.n = n_base;
+  B200D_CHECK_ARG(n_base <= 65535);
+  dim3 grid((n_base + 255) / 256, n_base);
+  fuse_scales_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}

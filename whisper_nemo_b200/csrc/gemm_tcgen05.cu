@@ -1,0 +1,476 @@
+// Pointwise-conv / projection GEMM on Blackwell 5th-gen tensor cores.
+//
+//   acc[m][n] = sum_k A[m][k] * W[n][k]       A [M][lda], W [N][ldw], 16-bit, both K-major
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0   TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 64-wide K slabs)
+//   warp 1   MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16 per instruction)
+//   warp 2   TMEM allocator (2 accumulator buffers -> epilogue of tile i overlaps MMA of tile i+1)
+//   warps 4-7 epilogue     (tcgen05.ld 32x32b, fused epilogue in fp32, 16-byte global stores)
+// smem ring: STAGES x (A 128x64 + W BLOCK_Nx64); mbarriers full/empty per stage, tmem_full/empty
+// per accumulator.  Replaces the cuDNN/cuBLAS 1x1 conv1d calls under JasperBlock / SpeakerDecoder
+// (nemo/collections/asr/parts/submodules/jasper.py, modules/conv_asr.py) and the A*V products of
+// the spectral solver (offline_clustering.SpectralClustering.getSpectralEmbeddings).
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+namespace b200d {
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, 64-element (128 B) rows:
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major) | SBO>>4 = 1024>>4 [32,46) |
+// version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------ kernel
+struct GemmParams {
+  int M, N, K;
+  void* out;
+  int ldo;
+  b200d_gemm_epilogue epi;
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two
+  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
+};
+
+__device__ __forceinline__ uint4 pack8_f16(const float* v) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]);
+  __half2 h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]);
+  __half2 h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+__device__ __forceinline__ void unpack8_f16(uint4 u, float* v) {
+  __half2 h0 = *reinterpret_cast<__half2*>(&u.x), h1 = *reinterpret_cast<__half2*>(&u.y);
+  __half2 h2 = *reinterpret_cast<__half2*>(&u.z), h3 = *reinterpret_cast<__half2*>(&u.w);
+  float2 f;
+  f = __half22float2(h0); v[0] = f.x; v[1] = f.y;
+  f = __half22float2(h1); v[2] = f.x; v[3] = f.y;
+  f = __half22float2(h2); v[4] = f.x; v[5] = f.y;
+  f = __half22float2(h3); v[6] = f.x; v[7] = f.y;
+}
+
+// Epilogue on 32 consecutive columns [n0, n0+32) of one row.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int n0, float* acc) {
+  const b200d_gemm_epilogue& e = p.epi;
+  if constexpr (MODE == B200D_EPI_BIAS || MODE == B200D_EPI_BIAS_RELU || MODE == B200D_EPI_BIAS_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
+      acc[j] += b.x; acc[j + 1] += b.y; acc[j + 2] += b.z; acc[j + 3] += b.w;
+    }
+    if constexpr (MODE == B200D_EPI_BIAS_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+  } else if constexpr (MODE == B200D_EPI_SE_RES) {
+    const int seg = row / e.rows_per_seg;
+    const float* gate = e.rowvec + static_cast<size_t>(seg) * p.N + n0;
+    const __half* aux = reinterpret_cast<const __half*>(e.aux16) + static_cast<size_t>(row) * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float x[8];
+      unpack8_f16(__ldg(reinterpret_cast<const uint4*>(aux + j)), x);
+      float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + j)), g1 = __ldg(reinterpret_cast<const float4*>(gate + j + 4));
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j)), b1 = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[j + q] = fmaxf(fmaf(x[q], g[q], acc[j + q] + b[q]), 0.f);
+    }
+  } else if constexpr (MODE == B200D_EPI_TDNN) {
+    const int seg = row / e.rows_per_seg;
+    const float* rb = e.rowvec + static_cast<size_t>(seg) * p.N + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float z = fmaxf(acc[j] + __ldg(rb + j), 0.f);
+      acc[j] = tanhf(fmaf(__ldg(e.scale + n0 + j), z, __ldg(e.shift + n0 + j)));
+    }
+  }
+  if constexpr (MODE == B200D_EPI_SIGMOID_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 1.f / (1.f + __expf(-acc[j]));
+  }
+  if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  } else {
+    __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(o + j) = pack8_f16(acc + j);
+  }
+}
+
+// Chebyshev epilogue: the W operand holds V^T split into three bf16 parts [hi | mid | lo], each
+// `bpad` columns wide, so acc columns (c, bpad + c, 2*bpad + c) sum to (A V)[row][c] at ~fp32 accuracy.
+__device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(h);
+  m = __float2bfloat16_rn(r);
+  r -= __bfloat162float(m);
+  l = __float2bfloat16_rn(r);
+}
+
+template <int BLOCK_N, int MODE, bool BF16>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = p.N / BLOCK_N;
+  const int total = num_m * num_n;
+  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], A_BYTES + Cfg::B_BYTES);
+          tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (1<<4), A/B format (f16 = 0, bf16 = 1) at bits 7 / 10, both K-major,
+      // N>>3 at bit 17, M>>4 at bit 24
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+                                 (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
+          const uint64_t b_desc = make_sw128_desc(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + wq * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
+      if constexpr (MODE == B200D_EPI_CHEB) {
+        const b200d_gemm_epilogue& e = p.epi;
+        const int bpad = BLOCK_N == 256 ? 64 : 32;
+        for (int c0 = 0; c0 < bpad; c0 += 32) {
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld32(t_row + c0, r0);
+          tmem_ld32(t_row + bpad + c0, r1);
+          tmem_ld32(t_row + 2 * bpad + c0, r2);
+          tmem_ld_wait();
+          if (row < p.M) {
+            const float dg = __ldg(e.deg + row);
+            const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + c0;
+            const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + c0 : nullptr;
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c0;
+            __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+              const float xv = x[j];
+              float y = e.ca * (dg * xv - av) + e.cb * xv;
+              if (xp) y += e.cc * xp[j];
+              o[j] = y;
+              if (vh) {
+                __nv_bfloat16 h, m, l;
+                split3_bf16(y, h, m, l);
+                const size_t col = c0 + j;
+                vh[(col) * e.ldvt + row] = h;
+                vh[(bpad + col) * e.ldvt + row] = m;
+                vh[(2 * bpad + col) * e.ldvt + row] = l;
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float acc_f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
+            epilogue_chunk<MODE>(p, row, n_blk * BLOCK_N + c * 32, acc_f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode;
+}
+
+// 2-D K-major map: dim0 = K (contiguous), dim1 = rows; box = 64 x box_rows, 128B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t rows, int64_t k, int64_t ld_elems, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(B200D_ELAUNCH, "%s: cuTensorMapEncodeTiled entry point not found%s", "make_map");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    static thread_local char buf[32];
+    snprintf(buf, sizeof(buf), "%d", static_cast<int>(r));
+    return set_error(B200D_ELAUNCH, "%s: cuTensorMapEncodeTiled failed with CUresult %s", "make_map", buf);
+  }
+  return B200D_OK;
+}
+
+template <int BLOCK_N, int MODE, bool BF16>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, BF16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BLOCK_N);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  switch (p.epi.mode) {
+    case B200D_EPI_BIAS: return launch<BLOCK_N, B200D_EPI_BIAS, false>(ta, tb, p, s);
+    case B200D_EPI_BIAS_RELU: return launch<BLOCK_N, B200D_EPI_BIAS_RELU, false>(ta, tb, p, s);
+    case B200D_EPI_SE_RES: return launch<BLOCK_N, B200D_EPI_SE_RES, false>(ta, tb, p, s);
+    case B200D_EPI_TDNN: return launch<BLOCK_N, B200D_EPI_TDNN, false>(ta, tb, p, s);
+    case B200D_EPI_BIAS_F32: return launch<BLOCK_N, B200D_EPI_BIAS_F32, false>(ta, tb, p, s);
+    case B200D_EPI_SIGMOID_F32: return launch<BLOCK_N, B200D_EPI_SIGMOID_F32, false>(ta, tb, p, s);
+    case B200D_EPI_CHEB: return launch<BLOCK_N, B200D_EPI_CHEB, true>(ta, tb, p, s);
+  }
+  return set_error(B200D_EINVAL, "%s: unknown epilogue mode%s", "b200d_gemm_f16");
+}
+
+}  // namespace b200d
+
+using namespace b200d;
+
+extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K, void* out,
+                              int32_t ldo, const b200d_gemm_epilogue* epi, void* stream) {
+  B200D_CHECK_ARG(A && W && out && epi);
+  B200D_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  B200D_CHECK_ARG(N % 128 == 0);
+  B200D_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0);
+  B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int mode = epi->mode;
+  if (mode == B200D_EPI_CHEB) {
+    B200D_CHECK_ARG(N == 128 || N == 256);
+    B200D_CHECK_ARG(epi->deg && epi->x32);
+    B200D_CHECK_ARG(epi->vt == nullptr || epi->ldvt >= M);
+  } else {
+    B200D_CHECK_ARG(ldo % 8 == 0 && ldo >= N);
+    if (mode == B200D_EPI_SE_RES) B200D_CHECK_ARG(epi->bias && epi->rowvec && epi->aux16 && epi->rows_per_seg > 0);
+    if (mode == B200D_EPI_TDNN) B200D_CHECK_ARG(epi->scale && epi->shift && epi->rowvec && epi->rows_per_seg > 0);
+    if (mode == B200D_EPI_BIAS || mode == B200D_EPI_BIAS_RELU || mode == B200D_EPI_BIAS_F32) B200D_CHECK_ARG(epi->bias);
+  }
+  const bool bf16 = mode == B200D_EPI_CHEB;
+  const int block_n = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&tb, W, bf16, N, K, ldw, block_n);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.epi = *epi;
+  if (block_n == 256) return dispatch_mode<256>(ta, tb, p, as_stream(stream));
+  return dispatch_mode<128>(ta, tb, p, as_stream(stream));
+}

@@ -1,0 +1,221 @@
+// CUDA-core kernels of the TitaNet-L forward (everything that is not a dense contraction):
+// masked depthwise conv over time, squeeze-excite pooling / gating, time statistics and attentive
+// statistics pooling.  Activations are fp16 channels-last [n_seg*T][C]; all segments of a call
+// share the frame count T (fixed_seq collate), so "masking beyond the sequence length" of upstream
+// MaskedConv1d reduces to zero padding at the segment edges.
+// Upstream: nemo/collections/asr/parts/submodules/jasper.py (MaskedConv1d, SqueezeExcite),
+//           nemo/collections/asr/parts/submodules/tdnn_attention.py (AttentivePoolLayer).
+#include "common.cuh"
+
+namespace b200d {
+
+__device__ __forceinline__ void load4h(const __half* p, float (&v)[4]) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4h(__half* p, const float (&v)[4]) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------ depthwise
+// Thread = 4 channels x TT consecutive output frames of one segment; the k x 4 filter taps live in
+// registers, each input vector is loaded once and feeds up to k outputs.
+constexpr int kDwTT = 8;
+
+template <int KS>
+__global__ void __launch_bounds__(256) depthwise_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                        const float* __restrict__ w, int n_seg, int T, int C, int strips) {
+  constexpr int PAD = KS / 2;
+  const int cg = blockIdx.y * blockDim.x + threadIdx.x;  // channel group of 4
+  if (cg * 4 >= C) return;
+  const int strip = blockIdx.x;
+  const int seg = strip / strips;
+  const int t0 = (strip - seg * strips) * kDwTT;
+  const int c = cg * 4;
+  float wt[KS][4];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(j) * C + c));
+    wt[j][0] = f.x; wt[j][1] = f.y; wt[j][2] = f.z; wt[j][3] = f.w;
+  }
+  float acc[kDwTT][4];
+#pragma unroll
+  for (int i = 0; i < kDwTT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const __half* xs = x + (static_cast<size_t>(seg) * T) * C + c;
+#pragma unroll
+  for (int r = 0; r < kDwTT + KS - 1; ++r) {
+    const int t = t0 + r - PAD;
+    if (t >= 0 && t < T) {
+      float v[4];
+      load4h(xs + static_cast<size_t>(t) * C, v);
+#pragma unroll
+      for (int tt = 0; tt < kDwTT; ++tt) {
+        const int j = r - tt;  // tap index: input t = (t0 + tt) + j - PAD
+        if (j >= 0 && j < KS) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[tt][q] = fmaf(wt[j][q], v[q], acc[tt][q]);
+        }
+      }
+    }
+  }
+  __half* ys = y + (static_cast<size_t>(seg) * T) * C + c;
+#pragma unroll
+  for (int tt = 0; tt < kDwTT; ++tt)
+    if (t0 + tt < T) store4h(ys + static_cast<size_t>(t0 + tt) * C, acc[tt]);
+}
+
+// ------------------------------------------------------------------------------------ time statistics
+// One block per segment, thread = 4 channels.  WITH_STD == false: mean only (SqueezeExcite pool).
+// WITH_STD == true: [mean | sqrt(clamp(mean((x-mean)^2), 1e-10))] (AttentivePoolLayer context).
+template <bool WITH_STD>
+__global__ void time_stats_kernel(const __half* __restrict__ x, int T, int C, __half* __restrict__ out16) {
+  const int seg = blockIdx.x;
+  const int c = threadIdx.x * 4;
+  if (c >= C) return;
+  const __half* xs = x + static_cast<size_t>(seg) * T * C + c;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < T; ++t) {
+    float v[4];
+    load4h(xs + static_cast<size_t>(t) * C, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] += v[q];
+  }
+  const float inv = 1.f / static_cast<float>(T);
+  float mean[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) mean[q] = s[q] * inv;
+  const int ld = WITH_STD ? 2 * C : C;
+  store4h(out16 + static_cast<size_t>(seg) * ld + c, mean);
+  if constexpr (WITH_STD) {
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < T; ++t) {
+      float v[4];
+      load4h(xs + static_cast<size_t>(t) * C, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float d = v[q] - mean[q];
+        ss[q] = fmaf(d, d, ss[q]);
+      }
+    }
+    float sd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sd[q] = sqrtf(fmaxf(ss[q] * inv, 1e-10f));
+    store4h(out16 + static_cast<size_t>(seg) * ld + C + c, sd);
+  }
+}
+
+// ------------------------------------------------------------------------------------ SE apply
+__global__ void se_apply_relu_kernel(const __half* __restrict__ x, const float* __restrict__ gate, __half* __restrict__ y,
+                                     size_t total4, int T, int C) {
+  const int c4 = C / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = i / c4;
+    const int c = static_cast<int>(i - row * c4) * 4;
+    const size_t seg = row / T;
+    float v[4];
+    load4h(x + row * C + c, v);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gate + seg * C + c));
+    v[0] = fmaxf(v[0] * g.x, 0.f); v[1] = fmaxf(v[1] * g.y, 0.f);
+    v[2] = fmaxf(v[2] * g.z, 0.f); v[3] = fmaxf(v[3] * g.w, 0.f);
+    store4h(y + row * C + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------ attentive pooling
+// alpha = softmax over time of e (per channel); mu = sum alpha x; sg = sqrt(clamp(sum alpha (x - mu)^2, 1e-10)).
+// Single pass with an online (running-max) softmax; the second moment is accumulated around the
+// running mean-free form and combined at the end in fp32.
+__global__ void attn_pool_kernel(const __half* __restrict__ x, const __half* __restrict__ e, int T, int C, __half* __restrict__ out16) {
+  const int seg = blockIdx.x;
+  const int c = threadIdx.x * 4;
+  if (c >= C) return;
+  const __half* xs = x + static_cast<size_t>(seg) * T * C + c;
+  const __half* es = e + static_cast<size_t>(seg) * T * C + c;
+  float m[4], z[4], s1[4], s2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; z[q] = 0.f; s1[q] = 0.f; s2[q] = 0.f; }
+  for (int t = 0; t < T; ++t) {
+    float xv[4], ev[4];
+    load4h(xs + static_cast<size_t>(t) * C, xv);
+    load4h(es + static_cast<size_t>(t) * C, ev);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float mn = fmaxf(m[q], ev[q]);
+      const float r = __expf(m[q] - mn);  // exp(-inf) = 0 on the first frame
+      const float wgt = __expf(ev[q] - mn);
+      z[q] = z[q] * r + wgt;
+      s1[q] = s1[q] * r + wgt * xv[q];
+      s2[q] = s2[q] * r + wgt * xv[q] * xv[q];
+      m[q] = mn;
+    }
+  }
+  float mu[4], sg[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float iz = 1.f / z[q];
+    mu[q] = s1[q] * iz;
+    sg[q] = sqrtf(fmaxf(s2[q] * iz - mu[q] * mu[q], 1e-10f));
+  }
+  store4h(out16 + static_cast<size_t>(seg) * 2 * C + c, mu);
+  store4h(out16 + static_cast<size_t>(seg) * 2 * C + C + c, sg);
+}
+
+}  // namespace b200d
+
+using namespace b200d;
+
+extern "C" int b200d_depthwise_conv(const void* x, void* y, const float* w, int32_t n_seg, int32_t T, int32_t C, int32_t ksize,
+                                    void* stream) {
+  B200D_CHECK_ARG(x && y && w && x != y);
+  B200D_CHECK_ARG(n_seg > 0 && T > 0 && C > 0 && C % 4 == 0);
+  const int strips = (T + kDwTT - 1) / kDwTT;
+  const int threads = (C / 4) < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
+  B200D_CHECK_ARG(static_cast<long long>(n_seg) * strips < 2147483647LL);
+  dim3 grid(static_cast<unsigned>(n_seg) * strips, (C / 4 + threads - 1) / threads);
+  const __half* xi = reinterpret_cast<const __half*>(x);
+  __half* yo = reinterpret_cast<__half*>(y);
+  switch (ksize) {
+    case 3: depthwise_kernel<3><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
+    case 7: depthwise_kernel<7><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
+    case 11: depthwise_kernel<11><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
+    case 15: depthwise_kernel<15><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
+    default: return b200d::set_error(B200D_EINVAL, "%s: unsupported kernel size (3, 7, 11, 15)%s", "b200d_depthwise_conv");
+  }
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_time_stats(const void* x, int32_t n_seg, int32_t T, int32_t C, int32_t with_std, void* out16, void* stream) {
+  B200D_CHECK_ARG(x && out16 && n_seg > 0 && T > 0 && C % 4 == 0 && C / 4 <= 1024);
+  const int threads = ((C / 4 + 31) / 32) * 32;
+  if (with_std)
+    time_stats_kernel<true><<<n_seg, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
+  else
+    time_stats_kernel<false><<<n_seg, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_se_apply_relu(const void* x, const float* gate, void* y, int32_t n_seg, int32_t T, int32_t C, void* stream) {
+  B200D_CHECK_ARG(x && gate && y && n_seg > 0 && T > 0 && C % 4 == 0);
+  const size_t total4 = static_cast<size_t>(n_seg) * T * (C / 4);
+  const int blocks = static_cast<int>(total4 / 256 + 1 < static_cast<size_t>(kNumSMs) * 16 ? total4 / 256 + 1 : kNumSMs * 16);
+  se_apply_relu_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), gate, reinterpret_cast<__half*>(y), total4, T, C);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_attn_pool(const void* x, const void* e, int32_t n_seg, int32_t T, int32_t C, void* out16, void* stream) {
+  B200D_CHECK_ARG(x && e && out16 && n_seg > 0 && T > 0 && C % 4 == 0 && C / 4 <= 1024);
+  const int threads = ((C / 4 + 31) / 32) * 32;
+  attn_pool_kernel<<<n_seg, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(e), T, C,
+                                                            reinterpret_cast<__half*>(out16));
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}

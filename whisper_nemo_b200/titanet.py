@@ -1,0 +1,340 @@
+"""TitaNet-L speaker-embedding forward on B200: host orchestration over libb200d.so.
+
+Mirrors the operator interface of upstream NeMo's `EncDecSpeakerLabelModel.forward`
+(nemo/collections/asr/models/label_models.py: preprocessor -> ConvASREncoder ->
+SpeakerDecoder, reached from the reference through helpers.py:281,290
+`speaker_embeddings.model_path = "titanet_large"`), but takes segment descriptors
+instead of padded audio batches: the waveform stays resident in HBM and the
+featurizer kernel gathers / tiles each segment itself.
+
+Weight packing (one-time): BatchNorm folded into the fp16 pointwise weights, the
+k=1 depthwise of the last block folded into its pointwise, the TDNN context term
+[mean | std] hoisted out of the per-frame GEMM, embedding BN folded into the
+final 6144->192 projection, logits layer dropped (inference discards it).
+"""
+from ctypes import byref
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import GemmEpilogue, ptr
+
+FEAT = 80
+FEAT_PAD = 128
+EMB = 192
+EMB_PAD = 256
+HOP = 160
+WIN = 400
+NFFT = 512
+
+
+# ------------------------------------------------------------------------------------------ tables
+def slaney_mel_filterbank(sr: int = 16000, n_fft: int = NFFT, n_mels: int = FEAT) -> np.ndarray:
+    """Slaney-scale, slaney-normalised triangular filterbank (what librosa.filters.mel returns with
+    its defaults, which is what NeMo's FilterbankFeatures uses).  float32 [n_mels, n_fft//2+1]."""
+    f_sp, brk = 200.0 / 3.0, 1000.0
+    brk_mel, step = brk / f_sp, np.log(6.4) / 27.0
+
+    def to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        return np.where(f >= brk, brk_mel + np.log(np.maximum(f, 1e-12) / brk) / step, f / f_sp)
+
+    def to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        return np.where(m >= brk_mel, brk * np.exp(step * (m - brk_mel)), f_sp * m)
+
+    edges = to_hz(np.linspace(to_mel(0.0), to_mel(sr / 2.0), n_mels + 2))
+    bins = np.linspace(0.0, sr / 2.0, n_fft // 2 + 1)
+    up = (bins[None, :] - edges[:-2, None]) / (edges[1:-1] - edges[:-2])[:, None]
+    down = (edges[2:, None] - bins[None, :]) / (edges[2:] - edges[1:-1])[:, None]
+    fb = np.clip(np.minimum(up, down), 0.0, None)
+    fb *= (2.0 / (edges[2:] - edges[:-2]))[:, None]
+    return fb.astype(np.float32)
+
+
+def pack_filterbank(fb: np.ndarray):
+    """Sparse (start bin, offset, packed weights) form consumed by b200d_featurize."""
+    starts, offs, weights = [], [0], []
+    for m in range(fb.shape[0]):
+        nz = np.nonzero(fb[m])[0]
+        if len(nz) == 0:
+            starts.append(0)
+            offs.append(offs[-1])
+            continue
+        a, b = int(nz[0]), int(nz[-1]) + 1
+        starts.append(a)
+        weights.extend(fb[m, a:b].tolist())
+        offs.append(offs[-1] + (b - a))
+    return np.asarray(starts, np.int32), np.asarray(offs, np.int32), np.asarray(weights, np.float32)
+
+
+# ------------------------------------------------------------------------------------------ weights
+@dataclass
+class SubBlock:
+    ksize: int
+    dw: Optional[torch.Tensor]  # float32 [k][Cin_pad] or None (k == 1 folded)
+    w: torch.Tensor  # fp16 [Cout][Cin_pad]
+    bias: torch.Tensor  # float32 [Cout]
+
+
+@dataclass
+class Block:
+    subs: List[SubBlock]
+    se_w1: torch.Tensor  # fp16 [C/8][C]
+    se_w2: torch.Tensor  # fp16 [C][C/8]
+    res_w: Optional[torch.Tensor]  # fp16 [Cout][Cin]
+    res_bias: Optional[torch.Tensor]
+    cout: int
+
+
+@dataclass
+class PackedTitaNet:
+    blocks: List[Block] = field(default_factory=list)
+    tdnn_wx: torch.Tensor = None  # fp16 [128][3072]
+    tdnn_wctx: torch.Tensor = None  # fp16 [128][6144]
+    tdnn_b: torch.Tensor = None  # float32 [128]
+    tdnn_scale: torch.Tensor = None
+    tdnn_shift: torch.Tensor = None
+    attn_w2: torch.Tensor = None  # fp16 [3072][128]
+    attn_b2: torch.Tensor = None
+    emb_w: torch.Tensor = None  # fp16 [256][6144] (rows >= 192 zero)
+    emb_b: torch.Tensor = None  # float32 [256]
+    zeros: torch.Tensor = None  # float32 [3072] zero bias
+    fb_start: torch.Tensor = None
+    fb_off: torch.Tensor = None
+    fb_w: torch.Tensor = None
+    window: torch.Tensor = None
+
+
+def _bn_fold(sd, prefix, eps):
+    g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
+    m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
+    s = g / torch.sqrt(v + eps)
+    return s, b - m * s
+
+
+def pack_weights(state_dict: Dict[str, torch.Tensor], device="cuda") -> PackedTitaNet:
+    """state_dict with upstream NeMo's TitaNet-L key layout (`encoder.encoder.{i}.mconv.{j}...`,
+    `encoder.encoder.{i}.res.0.{0,1}...`, `decoder._pooling.attention_layer...`,
+    `decoder.emb_layers.0.{0,1}...`).  Sub-module indices are discovered from the keys, so both
+    NeMo's [conv, conv, bn, act, dropout] and a dropout-free layout load."""
+    sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+    pk = PackedTitaNet()
+    n_blocks = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder.encoder."))
+    f16 = lambda t: t.to(torch.float16).contiguous().to(device)
+    f32 = lambda t: t.to(torch.float32).contiguous().to(device)
+    for i in range(n_blocks):
+        pre = f"encoder.encoder.{i}.mconv."
+        idx = sorted({int(k[len(pre):].split(".")[0]) for k in sd if k.startswith(pre)})
+        convs = [j for j in idx if f"{pre}{j}.conv.weight" in sd]
+        bns = [j for j in idx if f"{pre}{j}.running_mean" in sd]
+        ses = [j for j in idx if f"{pre}{j}.fc.0.weight" in sd]
+        assert len(convs) == 2 * len(bns) and len(ses) == 1, f"unexpected layout in block {i}"
+        subs = []
+        for r, bn_j in enumerate(bns):
+            dw_w = sd[f"{pre}{convs[2 * r]}.conv.weight"].double()  # [Cin,1,k]
+            pw_w = sd[f"{pre}{convs[2 * r + 1]}.conv.weight"].double()[:, :, 0]  # [Cout,Cin]
+            s, t = _bn_fold(sd, f"{pre}{bn_j}", 1e-3)
+            cin, k = dw_w.shape[0], dw_w.shape[2]
+            cin_pad = FEAT_PAD if cin == FEAT else cin
+            w = pw_w * s[:, None]
+            dw = None
+            if k == 1:
+                w = w * dw_w[:, 0, 0][None, :]
+            else:
+                dwp = torch.zeros(k, cin_pad, dtype=torch.float64)
+                dwp[:, :cin] = dw_w[:, 0, :].t()
+                dw = f32(dwp)
+            wp = torch.zeros(w.shape[0], cin_pad, dtype=torch.float64)
+            wp[:, :cin] = w
+            subs.append(SubBlock(ksize=k, dw=dw, w=f16(wp), bias=f32(t)))
+        se_pre = f"{pre}{ses[0]}.fc."
+        res_w = res_b = None
+        rpre = f"encoder.encoder.{i}.res.0."
+        if f"{rpre}0.conv.weight" in sd:
+            rw = sd[f"{rpre}0.conv.weight"].double()[:, :, 0]
+            s, t = _bn_fold(sd, f"{rpre}1", 1e-3)
+            res_w, res_b = f16(rw * s[:, None]), f32(t)
+        pk.blocks.append(
+            Block(subs=subs, se_w1=f16(sd[se_pre + "0.weight"]), se_w2=f16(sd[se_pre + "2.weight"]), res_w=res_w, res_bias=res_b,
+                  cout=subs[-1].w.shape[0])
+        )
+    c_enc = pk.blocks[-1].cout
+    ap = "decoder._pooling.attention_layer."
+    tw = sd[ap + "0.conv_layer.weight"].double()[:, :, 0]  # [128, 3*C]
+    pk.tdnn_wx = f16(tw[:, :c_enc])
+    pk.tdnn_wctx = f16(tw[:, c_enc:])
+    pk.tdnn_b = f32(sd[ap + "0.conv_layer.bias"])
+    s, t = _bn_fold(sd, ap + "0.bn", 1e-5)
+    pk.tdnn_scale, pk.tdnn_shift = f32(s), f32(t)
+    pk.attn_w2 = f16(sd[ap + "2.weight"][:, :, 0])
+    pk.attn_b2 = f32(sd[ap + "2.bias"])
+    s, t = _bn_fold(sd, "decoder.emb_layers.0.0", 1e-5)
+    ew = sd["decoder.emb_layers.0.1.weight"].double()[:, :, 0]  # [192, 6144]
+    eb = sd["decoder.emb_layers.0.1.bias"].double() + ew @ t
+    ewp = torch.zeros(EMB_PAD, ew.shape[1], dtype=torch.float64)
+    ewp[: ew.shape[0]] = ew * s[None, :]
+    ebp = torch.zeros(EMB_PAD, dtype=torch.float64)
+    ebp[: eb.shape[0]] = eb
+    pk.emb_w, pk.emb_b = f16(ewp), f32(ebp)
+    pk.zeros = torch.zeros(4096, dtype=torch.float32, device=device)
+    fs, fo, fw = pack_filterbank(slaney_mel_filterbank())
+    pk.fb_start = torch.from_numpy(fs).to(device)
+    pk.fb_off = torch.from_numpy(fo).to(device)
+    pk.fb_w = torch.from_numpy(fw).to(device)
+    pk.window = torch.hann_window(WIN, periodic=False, dtype=torch.float64).float().to(device)
+    return pk
+
+
+# ------------------------------------------------------------------------------------------ kernels
+def gemm(A, W, out, mode, M=None, bias=None, scale=None, shift=None, rowvec=None, aux16=None, rows_per_seg=0):
+    """out = epilogue(A[M,K] @ W[N,K]^T) through b200d_gemm_f16."""
+    M = A.shape[0] if M is None else M
+    N, K = W.shape
+    epi = GemmEpilogue()
+    epi.mode = mode
+    epi.rows_per_seg = rows_per_seg
+    epi.bias = bias.data_ptr() if bias is not None else None
+    epi.scale = scale.data_ptr() if scale is not None else None
+    epi.shift = shift.data_ptr() if shift is not None else None
+    epi.rowvec = rowvec.data_ptr() if rowvec is not None else None
+    epi.aux16 = aux16.data_ptr() if aux16 is not None else None
+    _cabi.call("b200d_gemm_f16", ptr(A), A.stride(0), ptr(W), W.stride(0), M, N, K, ptr(out), out.stride(0), byref(epi), _cabi._stream())
+    return out
+
+
+def featurize(pk: PackedTitaNet, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int,
+              out16: torch.Tensor = None, want_f32: bool = False):
+    """wav float32 [n] on device; seg_start / seg_len int32 [n_seg] on device.  Returns
+    (fp16 [n_seg*T, 128], optional float32 [n_seg, T, 80])."""
+    n_seg = seg_start.numel()
+    T = fixed_len // HOP + 1
+    if out16 is None:
+        out16 = torch.empty(n_seg * T, FEAT_PAD, dtype=torch.float16, device=wav.device)
+    out32 = torch.empty(n_seg, T, FEAT, dtype=torch.float32, device=wav.device) if want_f32 else None
+    _cabi.call("b200d_featurize", ptr(wav), wav.numel(), ptr(seg_start), ptr(seg_len), n_seg, fixed_len, ptr(pk.fb_start), ptr(pk.fb_off),
+               ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), ptr(out16), out16.stride(0), ptr(out32), _cabi._stream())
+    return out16, out32
+
+
+class Workspace:
+    """Activation buffers for up to `max_frames` frames / `max_segs` segments, allocated once."""
+
+    def __init__(self, max_frames: int, max_segs: int, device):
+        h = lambda r, c: torch.empty(r, c, dtype=torch.float16, device=device)
+        self.max_frames, self.max_segs = max_frames, max_segs
+        self.x0 = h(max_frames, FEAT_PAD)
+        self.a = h(max_frames, 1024)
+        self.b = h(max_frames, 1024)
+        self.y = h(max_frames, 1024)
+        self.d = h(max_frames, 1024)
+        self.x = h(max_frames, 3072)
+        self.e = h(max_frames, 3072)
+        self.hid = h(max_frames, 128)
+        self.mean16 = h(max_segs, 3072)
+        self.sehid = h(max_segs, 384)
+        self.gate = torch.empty(max_segs, 3072, dtype=torch.float32, device=device)
+        self.stats16 = h(max_segs, 6144)
+        self.segbias = torch.empty(max_segs, 128, dtype=torch.float32, device=device)
+        self.pool16 = h(max_segs, 6144)
+        self.emb = torch.empty(max_segs, EMB_PAD, dtype=torch.float32, device=device)
+
+
+def _flat(buf, rows, cols):
+    """Contiguous [rows, cols] view on the front of a larger scratch buffer."""
+    return buf.view(-1)[: rows * cols].view(rows, cols)
+
+
+def _se_gate(pk, ws, blk: Block, y, n_seg, T, C):
+    mean16 = _flat(ws.mean16, n_seg, C)
+    hid = _flat(ws.sehid, n_seg, C // 8)
+    gate = _flat(ws.gate, n_seg, C)
+    _cabi.call("b200d_time_stats", ptr(y), n_seg, T, C, 0, ptr(mean16), _cabi._stream())
+    gemm(mean16, blk.se_w1, hid, _cabi.EPI_BIAS_RELU, bias=pk.zeros)
+    gemm(hid, blk.se_w2, gate, _cabi.EPI_SIGMOID_F32)
+    return gate
+
+
+def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: dict = None) -> torch.Tensor:
+    """Encoder + decoder over ws.x0[: n_seg*T] (already featurized).  Returns emb float32 [n_seg, 192] (a view)."""
+    M = n_seg * T
+    s = _cabi._stream()
+    dwc = lambda x, y, w, C, k: _cabi.call("b200d_depthwise_conv", ptr(x), ptr(y), ptr(w), n_seg, T, C, k, s)
+    # ---- block 0: dw3 -> pw 80->1024 -> BN -> SE -> ReLU
+    b0 = pk.blocks[0]
+    d0v = _flat(ws.d, M, FEAT_PAD)
+    dwc(ws.x0, d0v, b0.subs[0].dw, FEAT_PAD, b0.subs[0].ksize)
+    gemm(d0v, b0.subs[0].w, ws.y, _cabi.EPI_BIAS, M=M, bias=b0.subs[0].bias)
+    gate = _se_gate(pk, ws, b0, ws.y, n_seg, T, 1024)
+    _cabi.call("b200d_se_apply_relu", ptr(ws.y), ptr(gate), ptr(ws.a), n_seg, T, 1024, s)
+    cur, nxt = ws.a, ws.b
+    if taps is not None:
+        taps["block0"] = cur[:M].clone()
+    # ---- blocks 1..3: 3 x (dw -> pw -> BN [-> ReLU]) -> SE ; + BN(conv1x1(in)) ; ReLU
+    for bi in (1, 2, 3):
+        blk = pk.blocks[bi]
+        src = cur
+        for r, sb in enumerate(blk.subs):
+            dwc(src, ws.d, sb.dw, 1024, sb.ksize)
+            last = r == len(blk.subs) - 1
+            gemm(ws.d, sb.w, ws.y, _cabi.EPI_BIAS if last else _cabi.EPI_BIAS_RELU, M=M, bias=sb.bias)
+            src = ws.y  # next depthwise reads y and writes d; its GEMM then overwrites y
+        gate = _se_gate(pk, ws, blk, ws.y, n_seg, T, 1024)
+        gemm(cur, blk.res_w, nxt, _cabi.EPI_SE_RES, M=M, bias=blk.res_bias, rowvec=gate, aux16=ws.y, rows_per_seg=T)
+        cur, nxt = nxt, cur
+        if taps is not None:
+            taps[f"block{bi}"] = cur[:M].clone()
+    # ---- block 4: (dw k=1 folded) pw 1024->3072 -> BN -> SE -> ReLU
+    b4 = pk.blocks[4]
+    gemm(cur, b4.subs[0].w, ws.e, _cabi.EPI_BIAS, M=M, bias=b4.subs[0].bias)
+    gate = _se_gate(pk, ws, b4, ws.e, n_seg, T, 3072)
+    _cabi.call("b200d_se_apply_relu", ptr(ws.e), ptr(gate), ptr(ws.x), n_seg, T, 3072, s)
+    if taps is not None:
+        taps["encoder"] = ws.x[:M].clone()
+    # ---- decoder: attentive statistics pooling + embedding projection
+    stats16 = ws.stats16[:n_seg]
+    _cabi.call("b200d_time_stats", ptr(ws.x), n_seg, T, 3072, 1, ptr(stats16), s)
+    segbias = ws.segbias[:n_seg]
+    gemm(stats16, pk.tdnn_wctx, segbias, _cabi.EPI_BIAS_F32, bias=pk.tdnn_b)
+    gemm(ws.x, pk.tdnn_wx, ws.hid, _cabi.EPI_TDNN, M=M, scale=pk.tdnn_scale, shift=pk.tdnn_shift, rowvec=segbias, rows_per_seg=T)
+    gemm(ws.hid, pk.attn_w2, ws.e, _cabi.EPI_BIAS, M=M, bias=pk.attn_b2)
+    pool16 = ws.pool16[:n_seg]
+    _cabi.call("b200d_attn_pool", ptr(ws.x), ptr(ws.e), n_seg, T, 3072, ptr(pool16), s)
+    emb = ws.emb[:n_seg]
+    gemm(pool16, pk.emb_w, emb, _cabi.EPI_BIAS_F32, bias=pk.emb_b)
+    return emb[:, :EMB]
+
+
+class TitaNetB200:
+    """Speaker-embedding extractor: `embed_segments` is the device-side replacement of the
+    `_extract_embeddings` dataloader loop of upstream ClusteringDiarizer."""
+
+    def __init__(self, state_dict, device="cuda", max_frames: int = 49152):
+        _cabi.require_device()
+        self.device = torch.device(device)
+        self.pk = pack_weights(state_dict, self.device)
+        self.max_frames = max_frames
+        self._ws = None
+
+    def _workspace(self, T):
+        max_segs = max(1, self.max_frames // T)
+        if self._ws is None or self._ws.max_segs < max_segs:
+            self._ws = Workspace(self.max_frames, max(max_segs, 1024), self.device)
+        return self._ws
+
+    @torch.no_grad()
+    def embed_segments(self, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int, taps: dict = None):
+        """All segments share `fixed_len` (batch max under fixed_seq collate).  Returns float32 [n_seg, 192]."""
+        n_seg = seg_start.numel()
+        T = fixed_len // HOP + 1
+        ws = self._workspace(T)
+        segs_per_chunk = max(1, self.max_frames // T)
+        out = torch.empty(n_seg, EMB, dtype=torch.float32, device=self.device)
+        for c0 in range(0, n_seg, segs_per_chunk):
+            c1 = min(n_seg, c0 + segs_per_chunk)
+            featurize(self.pk, wav, seg_start[c0:c1], seg_len[c0:c1], fixed_len, out16=ws.x0)
+            out[c0:c1] = forward_frames(self.pk, ws, c1 - c0, T, taps)
+        return out
