@@ -86,8 +86,8 @@ int b200d_depthwise_conv(const void* x, void* y, const float* w, int32_t n_seg, 
  *   B200D_EPI_TDNN       out16 = tanh(scale[n] * relu(acc + rowvec[m / rows_per_seg][n]) + shift[n])
  *   B200D_EPI_BIAS_F32   out32 = acc + bias[n]
  *   B200D_EPI_SIGMOID_F32 out32 = 1 / (1 + exp(-acc))          (SqueezeExcite gate)
- *   B200D_EPI_CHEB       Chebyshev / Laplacian step of the spectral solver (see b200d_cheb_step)
- * K % 64 == 0, N % 128 == 0 (N % 256 == 0 uses 128x256 tiles), lda/ldw/ldo % 8 == 0.            */
+ *   B200D_EPI_CHEB       Chebyshev / Laplacian step of the spectral solver (bf16 operands; see the struct below)
+ * N % 128 == 0 (N % 256 == 0 uses 128x256 tiles), lda/ldw/ldo % 8 == 0; K tails are zero-filled by TMA. */
 enum {
   B200D_EPI_BIAS = 0,
   B200D_EPI_BIAS_RELU = 1,
@@ -149,57 +149,80 @@ int b200d_l2_normalize(const float* x, float* xn, int32_t n, int32_t d, float ep
  * matrix (minmax must be initialised by the call itself).  cos float32 [n][n].                  */
 int b200d_cos_affinity(const float* xn, int32_t n, int32_t d, float* cos, float* minmax, void* stream);
 
-/* fused[i][j] (+)= w * (cos_s[map[i]][map[j]] - min) / (max - min).  map int32 [n_base] (sorted
- * coarse index of every base segment); accumulate == 0 overwrites.                               */
-int b200d_fuse_scale(const float* cos_s, int32_t n_s, const int32_t* map, const float* minmax, float weight,
-                     float* fused, int32_t n_base, int32_t accumulate, void* stream);
+/* fused[i][j] = sum_s w_s * (cos_s[map_s[i]][map_s[j]] - min_s) / (max_s - min_s), all scales in one pass
+ * over the N x N output (upstream materialises two repeat_interleave copies per scale).
+ *  n_scales <= 8; the *_host arrays are HOST arrays of n_scales entries holding DEVICE pointers / sizes:
+ *  cos_host[s] float32 [ns][ns], map_host[s] int32 [n_base] (non-decreasing coarse index of every base
+ *  segment, get_argmin_mat + getRepeatedList), minmax_host[s] float32 [2] as written by b200d_cos_affinity. */
+int b200d_fuse_scales(int32_t n_scales, const float* const* cos_host, const int32_t* ns_host, const int32_t* const* map_host,
+                      const float* const* minmax_host, const float* weights_host, float* fused, int32_t n_base, void* stream);
+
+/* Long-form path (longform_clustering.LongFormSpeakerClustering, offline_clustering.get_scale_interpolated_embs,
+ * online_clustering.run_reducer / get_closest_embeddings):
+ *  interp_scales  out[i] = sum_s w_s * emb_s[map_s[i]]      out float32 [n_base][d]; *_host arrays as in fuse_scales
+ *  masked_rowsum  out[j] = sum_i [labels[i] == labels[j]] * mat[j][i]   (within-cluster affinity mass, all clusters at once) */
+int b200d_interp_scales(int32_t n_scales, const float* const* emb_host, const int32_t* const* map_host, const float* weights_host,
+                        float* out, int32_t n_base, int32_t d, void* stream);
+int b200d_masked_rowsum(const float* mat, int32_t n, const int32_t* labels, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * NME-SC graph + spectrum (getKneighborsConnections, getAffinityGraphMat, getLaplacian,
  * estimateNumofSpeakers, isGraphFullyConnected, SpectralClustering.getSpectralEmbeddings).
  * ------------------------------------------------------------------------------------------ */
 
-/* rank[i][j] = position of column j in row i of mat sorted descending (ties: lower column first),
- * on the strided view mat[i*stride][j*stride], i,j < n (n <= 2048).  rank uint16 [n][n].          */
-int b200d_row_rank(const float* mat, int64_t ld, int32_t stride, int32_t n, void* rank_u16, void* stream);
+/* rank[i][j] = position of column j in row i of mat sorted descending (ties: lower column first, the
+ * order of torch.argsort(descending=True) on CPU), on the strided view mat[i*stride][j*stride], i,j < n
+ * (n <= 1024: NMESC.subsampleAffinityMat keeps the sweep matrix below 2*nme_mat_size).
+ * rank, rankT uint16 [n][n]; rankT is the transpose of rank.                                      */
+int b200d_row_rank(const float* mat, int64_t ld, int32_t stride, int32_t n, void* rank_u16, void* rankT_u16, void* stream);
 
-/* For each p in p_list (host array, np entries): Laplacian of A_p = 0.5*(B_p + B_p^T),
+/* For each p in p_list (host array, np <= 64 entries): Laplacian L = D - A of A_p = 0.5*(B_p + B_p^T),
  * B_p[i][j] = rank[j][i] < p  (column-wise scatter of upstream), diagonal of A zeroed, degree
  * rounded through fp16 as upstream's half-precision graph does.  lap float32 [np][n][n].         */
-int b200d_laplacian_from_rank(const void* rank_u16, int32_t n, const int32_t* p_list_host, int32_t np,
+int b200d_laplacian_from_rank(const void* rank_u16, const void* rankT_u16, int32_t n, const int32_t* p_list_host, int32_t np,
                               float* lap, void* stream);
 
-/* Batched symmetric eigenvalues (values only): Householder tridiagonalisation + Sturm bisection.
- *  a float32 [batch][n][n] (destroyed); evals float32 [batch][n_low + 1] = the n_low smallest
- *  eigenvalues ascending followed by the largest.  ws: b200d_eigvals_workspace_bytes().           */
+/* reach[b] = number of nodes reachable from node 0 in the p_list[b]-neighbour graph given by the rank
+ * matrices (isGraphFullyConnected / getTheLargestComponent; the whole list of getMinimumConnection in
+ * one launch): frontier expansion, one CTA per p.  p_list_host: HOST array, np <= 64; reach int32 [np]. */
+int b200d_graph_reach_rank(const void* rank_u16, const void* rankT_u16, int32_t n, const int32_t* p_list_host, int32_t np,
+                           int32_t* reach, void* stream);
+
+/* Batched symmetric eigenvalues (values only): chip-wide cooperative Householder tridiagonalisation
+ * followed by Sturm multisection in fp64.
+ *  a float32 [batch][n][n] (destroyed), batch <= 148, n <= 2048; evals float32 [batch][n_low + 1] = the
+ *  n_low smallest eigenvalues ascending followed by the largest.  ws: b200d_eigvals_workspace_bytes(). */
 size_t b200d_eigvals_workspace_bytes(int32_t batch, int32_t n);
-int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t n_low, float* evals, void* ws,
-                          size_t ws_bytes, void* stream);
+int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t n_low, float* evals, void* ws, size_t ws_bytes,
+                          void* stream);
 
-/* Top-p binarisation of the full matrix: a16[i][j] = 0.5*([j in top_p(row i)] + [i in top_p(row j)]),
- * diagonal zeroed, as __half [n][lda]; deg float32 [n] = row sums (fp16-rounded as upstream).
- * sel uint8 [n][n] scratch.                                                                       */
-int b200d_topp_binarize(const float* mat, int32_t n, int32_t p, void* a16, int32_t lda, float* deg,
-                        void* sel_u8, void* stream);
+/* Top-p binarisation of the full matrix (getAffinityGraphMat on the N x N fused affinity):
+ * a[i][j] = 0.5*([j in top_p(row i)] + [i in top_p(row j)]), diagonal zeroed, as __nv_bfloat16 [n][lda]
+ * (exact: entries are 0, 0.5, 1; columns n..lda-1 zeroed); deg float32 [n] = row sums, fp16-rounded as
+ * upstream.  Radix select per row (no sort); sel uint8 [n][n] scratch.                             */
+int b200d_topp_binarize(const float* mat, int32_t n, int32_t p, void* a_bf16, int32_t lda, float* deg, void* sel_u8,
+                        void* stream);
 
-/* reach[0] = number of nodes reachable from node 0 in the graph a16 != 0.  frontier/visited
- * int32 [n] scratch.                                                                              */
-int b200d_graph_reach(const void* a16, int32_t lda, int32_t n, int32_t* visited, int32_t* reach, void* stream);
-
-/* Small dense helpers of the Chebyshev-filtered subspace iteration (bottom-k eigenvectors of L = D - A). */
-/* g[b][b] = X^T Y (double accumulate, float32 out); x,y float32 [n][ld]                          */
-int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, int32_t ld, float* g, void* stream);
-/* In-place symmetric eigendecomposition of g[b][b] (b <= 64) by cyclic Jacobi in fp64:
- * evals ascending float32 [b], evecs float32 [b][b] (columns).  mode 1: Cholesky instead --
- * g = R^T R, returns inv(R) in evecs (for CholQR).                                                */
-int b200d_small_eig(float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream);
-/* y[n][b] = x[n][b] * q[b][b]; optionally also writes fp16 hi/lo split transposed (vt_* may be NULL) */
-int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y,
-                    void* vt_hi, void* vt_lo, int32_t ldvt, void* stream);
+/* One step of the Chebyshev-filtered subspace iteration for the bottom eigenvectors of L = D - A is
+ * b200d_gemm_f16(A, vt, ..., B200D_EPI_CHEB).  The small dense helpers around it:                  */
+/* g[b][b] = X^T Y (fp32 block partials, fixed-order fp64 combine); x,y float32 [n][ld]; b in {32, 64} */
+size_t b200d_gram_workspace_bytes(int32_t n, int32_t b);
+int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, int32_t ld, float* g, void* ws, size_t ws_bytes, void* stream);
+/* Symmetric eigendecomposition of g[b][b] (b even, <= 96) by parallel cyclic Jacobi in fp64:
+ * evals ascending float32 [b], evecs float32 [b][b] (columns).  mode 1: scaled Cholesky instead --
+ * returns Q = S R^-1 in evecs with (Y Q)^T (Y Q) = I for g = Y^T Y (CholQR).                       */
+int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream);
+/* y[n][b] = x[n][b] * q[b][b] (q NULL: y = x; y may alias x or be NULL); when vt_bf16 != NULL also the
+ * 3-way bf16 split [hi | mid | lo] of y^T into vt_bf16 [3*b][ldvt]: the W operand of the next CHEB GEMM. */
+int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y, void* vt_bf16, int32_t ldvt,
+                    void* stream);
+/* out[j] = sum_r (w[r][j] - theta[j] * x[r][j])^2 : squared residual norms of the Ritz pairs.       */
+int b200d_resid_norms(const float* w, const float* x, const float* theta, int32_t n, int32_t b, int32_t ld, float* out,
+                      void* stream);
 
 /* k-means of kmeans_torch / kmeans_plusplus_torch with the RNG draws supplied by the host
  * (torch.manual_seed(0) stream: first-centre index, rand(30) per further centre, fallback randints).
- *  x float32 [n][k_dim]; labels int32 [n].                                                        */
+ *  x float32 [n][dim] (dim, n_clusters <= 128; n_trials <= 32); labels int32 [n].                  */
 int b200d_kmeans(const float* x, int32_t n, int32_t dim, int32_t n_clusters, int32_t first_center,
                  const float* rand_vals /*[n_clusters-1][n_trials]*/, int32_t n_trials,
                  const int32_t* fallback_idx /*[n_fallback]*/, int32_t n_fallback, int32_t iter_limit,

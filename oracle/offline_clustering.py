@@ -88,7 +88,7 @@ def getKneighborsConnections(affinity_mat: torch.Tensor, p_value: int) -> torch.
     if switches.BINARIZE_HALF:
         binarized = binarized.half()
     p_value = int(p_value)
-    sorted_matrix = torch.argsort(affinity_mat, dim=1, descending=True)[:, :p_value]
+    sorted_matrix = torch.argsort(affinity_mat, dim=1, descending=True, stable=switches.ARGSORT_STABLE)[:, :p_value]
     binarized[sorted_matrix.T, torch.arange(affinity_mat.shape[0])] = 1
     indices_row = sorted_matrix[:, :p_value].flatten()
     indices_col = torch.arange(dim[1]).repeat(p_value, 1).T.flatten()

@@ -35,3 +35,10 @@ COS_EPS = 3.5e-4
 MIN_SAMPLES_FOR_NMESC = 6
 NME_MAT_SIZE = 512
 ENHANCED_COUNT_THRES = 80
+
+# offline_clustering.getKneighborsConnections calls torch.argsort(descending=True) WITHOUT stable=True.
+# On CPU that sort is not stable (tie order is an implementation detail of the torch build: it differs
+# between CPU and CUDA and between releases), so upstream's choice among exactly equal affinities at the
+# p-th position is unspecified.  The restatement pins it to the stable order (lower column first), which
+# is also what the CUDA path implements; set False to get torch's native (unspecified) tie order.
+ARGSORT_STABLE = True

@@ -1,0 +1,269 @@
+"""Kernel-level parity on the B200: every C-ABI entry point of the clustering stage against torch fp64 /
+the CPU oracle on seeded inputs.  Run with `pytest -m gpu`."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lap_batch(n, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    mats = []
+    for b in range(batch):
+        a = (torch.rand(n, n, generator=g) < (0.02 + 0.03 * b / max(batch - 1, 1))).float()
+        a = 0.5 * (a + a.t())
+        a.fill_diagonal_(0)
+        mats.append(torch.diag(a.sum(1)) - a)
+    return torch.stack(mats)
+
+
+@pytest.mark.parametrize("n,batch,n_low", [(2, 1, 1), (7, 3, 6), (100, 5, 9), (515, 30, 9), (600, 30, 9), (110, 10, 81), (1000, 12, 51)])
+def test_eigvals_batched(dev, n, batch, n_low):
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200._cabi import ptr
+
+    n_low = min(n_low, n)
+    lap = _lap_batch(n, batch, seed=n)
+    ref = torch.linalg.eigvalsh(lap.double())
+    a = lap.to(dev).contiguous()
+    ws_bytes = _cabi.load().b200d_eigvals_workspace_bytes(batch, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ev = torch.empty(batch, n_low + 1, dtype=torch.float32, device=dev)
+    _cabi.call("b200d_eigvals_batched", ptr(a), batch, n, n_low, ptr(ev), ptr(ws), ws_bytes, _cabi._stream())
+    torch.cuda.synchronize()
+    ev = ev.cpu().double()
+    scale = ref.abs().max().item()
+    err_low = (ev[:, :n_low] - ref[:, :n_low]).abs().max().item()
+    err_max = (ev[:, n_low] - ref[:, -1]).abs().max().item()
+    print(f"eigvals n={n} batch={batch}: low err {err_low:.3e} max err {err_max:.3e} (scale {scale:.1f})")
+    assert err_low <= 2e-5 * scale + 1e-5 and err_max <= 2e-5 * scale + 1e-5
+
+
+def _rank(mat, stride, dev):
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200._cabi import ptr
+
+    n = len(range(0, mat.shape[0], stride))
+    rank = torch.empty(n, n, dtype=torch.int16, device=dev)
+    rankT = torch.empty(n, n, dtype=torch.int16, device=dev)
+    _cabi.call("b200d_row_rank", ptr(mat), mat.stride(0), stride, n, ptr(rank), ptr(rankT), _cabi._stream())
+    return rank, rankT, n
+
+
+@pytest.mark.parametrize("N,stride", [(300, 1), (1023, 1), (2399, 4), (3000, 5)])
+def test_rank_laplacian_reach(dev, N, stride):
+    from oracle import offline_clustering as oc
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200._cabi import ptr
+
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(N, 16, generator=g)
+    x[: N // 2] += 2.0
+    mat = oc.getCosAffinityMatrix(x)
+    mat[5, 7] = mat[5, 9]  # an exact tie inside a row
+    sub = mat[::stride, ::stride].contiguous()
+    md = mat.to(dev)
+    rank, rankT, n = _rank(md, stride, dev)
+    torch.cuda.synchronize()
+    order = torch.argsort(sub, dim=1, descending=True, stable=True)
+    want = torch.empty_like(order)
+    want.scatter_(1, order, torch.arange(n).repeat(n, 1))
+    assert torch.equal(rank.cpu().long(), want)
+    assert torch.equal(rankT.cpu().long(), want.t())
+    p_list = [1, 2, max(2, n // 40), max(3, n // 8)]
+    lap = torch.empty(len(p_list), n, n, dtype=torch.float32, device=dev)
+    arr = (ctypes.c_int32 * len(p_list))(*p_list)
+    _cabi.call("b200d_laplacian_from_rank", ptr(rank), ptr(rankT), n, arr, len(p_list), ptr(lap), _cabi._stream())
+    reach = torch.empty(len(p_list), dtype=torch.int32, device=dev)
+    _cabi.call("b200d_graph_reach_rank", ptr(rank), ptr(rankT), n, arr, len(p_list), ptr(reach), _cabi._stream())
+    torch.cuda.synchronize()
+    for b, p in enumerate(p_list):
+        aff = oc.getAffinityGraphMat(sub.clone(), p)
+        comp = int(oc.getTheLargestComponent(aff, 0).sum())
+        want_lap = oc.getLaplacian(aff.clone()).float()
+        assert torch.equal(lap[b].cpu(), want_lap), f"laplacian mismatch at p={p}"
+        assert int(reach[b]) == comp, f"reach mismatch at p={p}: {int(reach[b])} vs {comp}"
+
+
+@pytest.mark.parametrize("N,p", [(200, 3), (2399, 40), (5000, 1300)])
+def test_topp_binarize(dev, N, p):
+    from oracle import offline_clustering as oc
+    from whisper_nemo_b200 import clustering as cl
+
+    g = torch.Generator().manual_seed(N + p)
+    x = torch.randn(N, 24, generator=g)
+    mat = oc.getCosAffinityMatrix(x)
+    mat[3, 10] = mat[3, 20]
+    a16, deg = cl.getAffinityGraphMat(mat.to(dev), p)
+    torch.cuda.synchronize()
+    aff = oc.getAffinityGraphMat(mat.clone(), p)
+    want = aff.clone().float()
+    want.fill_diagonal_(0)
+    assert torch.equal(a16[:, :N].float().cpu(), want)
+    assert a16[:, N:].abs().sum().item() == 0
+    lap = oc.getLaplacian(aff.clone()).float()
+    assert torch.equal(deg.cpu(), torch.diagonal(lap))
+
+
+@pytest.mark.parametrize("n,b", [(500, 32), (5000, 64), (14399, 32)])
+def test_gram_smalleig_rightmul_resid(dev, n, b):
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200._cabi import ptr
+
+    g = torch.Generator().manual_seed(n + b)
+    x = torch.randn(n, b, generator=g).to(dev)
+    y = torch.randn(n, b, generator=g).to(dev)
+    G = torch.empty(b, b, dtype=torch.float32, device=dev)
+    wsb = _cabi.load().b200d_gram_workspace_bytes(n, b)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    _cabi.call("b200d_gram", ptr(x), ptr(y), n, b, b, ptr(G), ptr(ws), wsb, _cabi._stream())
+    ref = (x.double().t() @ y.double())
+    assert (G.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-4
+    # CholQR: Q from X^T X makes X Q orthonormal
+    _cabi.call("b200d_gram", ptr(x), ptr(x), n, b, b, ptr(G), ptr(ws), wsb, _cabi._stream())
+    Q = torch.empty(b, b, dtype=torch.float32, device=dev)
+    _cabi.call("b200d_small_eig", ptr(G), b, None, ptr(Q), 1, _cabi._stream())
+    xo = torch.empty_like(x)
+    ldvt = (n + 7) // 8 * 8
+    vt = torch.zeros(4 * b, ldvt, dtype=torch.bfloat16, device=dev)
+    _cabi.call("b200d_right_mul", ptr(x), n, b, b, ptr(Q), ptr(xo), ptr(vt), ldvt, _cabi._stream())
+    torch.cuda.synchronize()
+    eye = xo.double().t() @ xo.double()
+    assert (eye - torch.eye(b, device=dev, dtype=torch.float64)).abs().max().item() < 5e-5
+    assert (xo.double() - x.double() @ Q.double()).abs().max().item() < 1e-5
+    rec = (vt[:b, :n].float() + vt[b : 2 * b, :n].float() + vt[2 * b : 3 * b, :n].float()).t()
+    assert (rec - xo).abs().max().item() <= 1e-7 * xo.abs().max().item() + 1e-9
+    # symmetric eigen-decomposition
+    S = torch.randn(b, b, generator=g)
+    S = (S + S.t()).to(dev).contiguous()
+    ev = torch.empty(b, dtype=torch.float32, device=dev)
+    V = torch.empty(b, b, dtype=torch.float32, device=dev)
+    _cabi.call("b200d_small_eig", ptr(S), b, ptr(ev), ptr(V), 0, _cabi._stream())
+    torch.cuda.synchronize()
+    ref_ev = torch.linalg.eigvalsh(S.double())
+    assert (ev.double() - ref_ev).abs().max().item() < 1e-5
+    assert (S.double() @ V.double() - V.double() * ev.double()[None, :]).abs().max().item() < 2e-5
+    # residual norms
+    theta = torch.rand(b, device=dev)
+    out = torch.empty(b, dtype=torch.float32, device=dev)
+    _cabi.call("b200d_resid_norms", ptr(y), ptr(x), ptr(theta), n, b, b, ptr(out), _cabi._stream())
+    ref_r = ((y.double() - x.double() * theta.double()[None, :]) ** 2).sum(0)
+    assert ((out.double() - ref_r).abs() / ref_r).max().item() < 1e-4
+
+
+@pytest.mark.parametrize("n,b", [(300, 32), (2399, 32), (5000, 64)])
+def test_cheb_gemm_step(dev, n, b):
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200 import clustering as cl
+    from whisper_nemo_b200._cabi import ptr
+
+    g = torch.Generator().manual_seed(n)
+    lda = (n + 7) // 8 * 8
+    a = (torch.rand(n, n, generator=g) < 0.05).float()
+    a = 0.5 * (a + a.t())
+    a.fill_diagonal_(0)
+    a16 = torch.zeros(n, lda, dtype=torch.bfloat16, device=dev)
+    a16[:, :n] = a.to(dev).bfloat16()
+    deg = a.sum(1).to(dev)
+    x = torch.randn(n, b, generator=g).to(dev)
+    xp = torch.randn(n, b, generator=g).to(dev)
+    ldvt = lda
+    vt_in = torch.zeros(4 * b, ldvt, dtype=torch.bfloat16, device=dev)
+    vt_out = torch.zeros(4 * b, ldvt, dtype=torch.bfloat16, device=dev)
+    _cabi.call("b200d_right_mul", ptr(x), n, b, b, None, None, ptr(vt_in), ldvt, _cabi._stream())
+    out = torch.empty(n, b, dtype=torch.float32, device=dev)
+    ca, cb, cc = 0.37, -1.2, 0.6
+    cl._gemm_cheb(a16, lda, vt_in, ldvt, n, 4 * b, out, deg, x, xp, ca, cb, cc, vt_out)
+    torch.cuda.synchronize()
+    ad = a.to(dev).double()
+    want = ca * (deg.double()[:, None] * x.double() - ad @ x.double()) + cb * x.double() + cc * xp.double()
+    err = (out.double() - want).abs().max().item()
+    print(f"cheb step n={n} b={b}: max err {err:.3e} (max |want| {want.abs().max().item():.2f})")
+    assert err <= 2e-5 * want.abs().max().item()
+    rec = (vt_out[:b, :n].float() + vt_out[b : 2 * b, :n].float() + vt_out[2 * b : 3 * b, :n].float()).t()
+    assert (rec - out).abs().max().item() <= 1e-6 * out.abs().max().item()
+
+
+def _clustered_graph(n, k, p, seed):
+    from oracle import offline_clustering as oc
+
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.randn(k, 32, generator=g) * 3
+    lab = torch.randint(0, k, (n,), generator=g)
+    x = centers[lab] + torch.randn(n, 32, generator=g)
+    return oc.getCosAffinityMatrix(x), lab
+
+
+@pytest.mark.parametrize("n,k,p", [(40, 3, 6), (64, 2, 8), (150, 3, 12), (2399, 4, 60), (6000, 8, 200), (4000, 50, 80)])
+def test_spectral_embedding_subspace(dev, n, k, p):
+    """The k lowest eigenvectors span the same subspace as torch.linalg.eigh's (principal angles ~ 0)."""
+    from oracle import offline_clustering as oc
+    from whisper_nemo_b200 import clustering as cl
+
+    mat, _ = _clustered_graph(n, k, p, seed=n + k)
+    graph = cl.getAffinityGraphMat(mat.to(dev), p)
+    emb = cl.SpectralClustering(n_clusters=k).getSpectralEmbeddings(graph)
+    torch.cuda.synchronize()
+    st = cl.last_spectral_stats
+    aff = oc.getAffinityGraphMat(mat.clone(), p)
+    lap = oc.getLaplacian(aff).double()
+    lam, vec = torch.linalg.eigh(lap)
+    ref = vec[:, :k]
+    q, _ = torch.linalg.qr(emb.cpu().double())
+    sv = torch.linalg.svdvals(ref.t() @ q)
+    gap = (lam[k] - lam[k - 1]).item()
+    print(f"spectral n={n} k={k}: method {st.method} outer {st.outer} gemms {st.gemms} resid {st.max_resid:.2e} "
+          f"min cos(angle) {sv.min().item():.8f} gap {gap:.3e} lam_max {lam[-1].item():.1f}")
+    assert st.converged
+    assert sv.min().item() > 1 - 1e-4
+
+
+@pytest.mark.parametrize("n,dim,k", [(50, 2, 2), (500, 4, 4), (2399, 3, 3), (14399, 8, 8), (10000, 50, 50)])
+def test_kmeans_matches_oracle(dev, n, dim, k):
+    from oracle import offline_clustering as oc
+    from whisper_nemo_b200 import clustering as cl
+
+    g = torch.Generator().manual_seed(n + dim)
+    centers = torch.randn(k, dim, generator=g) * 4
+    lab = torch.randint(0, k, (n,), generator=g)
+    x = (centers[lab] + torch.randn(n, dim, generator=g)) / math.sqrt(n)
+    state = torch.get_rng_state()
+    want = oc.kmeans_torch(x.clone(), k)
+    torch.set_rng_state(state)
+    got = cl.kmeans_torch(x.to(dev), k).cpu()
+    agree = (got == want).float().mean().item()
+    print(f"kmeans n={n} dim={dim} k={k}: label agreement {agree:.6f}")
+    assert agree == 1.0
+
+
+def test_multiscale_affinity_matches_oracle(dev):
+    from oracle import offline_clustering as oc
+    from whisper_nemo_b200 import clustering as cl
+
+    g = torch.Generator().manual_seed(3)
+    dur = 400.0
+    scales = [(1.5, 0.75), (1.0, 0.5), (0.5, 0.25)]
+    embs, stamps = [], []
+    for w, s in scales:
+        n = int(math.ceil((dur - w) / s)) + 1
+        t0 = torch.arange(n, dtype=torch.float64) * s
+        ts = torch.stack([t0, torch.clamp(t0 + w, max=dur)], 1)
+        spk = ((t0 + w / 2) // 20).long() % 3
+        e = torch.randn(3, 192, generator=g)[spk] * 2 + torch.randn(n, 192, generator=g)
+        embs.append(e)
+        stamps.append(ts.float())
+    weights = torch.tensor([[1.0, 1.0, 1.0]])
+    want = oc.getMultiScaleCosAffinityMatrix(weights, embs, stamps)
+    got = cl.getMultiScaleCosAffinityMatrix(weights, [e.to(dev) for e in embs], stamps)
+    torch.cuda.synchronize()
+    want_map = oc.get_argmin_mat(stamps)
+    got_map = cl.get_argmin_mat(stamps)
+    for a, b in zip(want_map, got_map):
+        assert np.array_equal(a.numpy(), b)
+    err = (got.cpu() - want).abs().max().item()
+    print(f"fused affinity [0, {weights.sum().item():.0f}] range: max abs err {err:.3e}")
+    assert err <= 1e-4  # BASELINE.json: fused affinity within 1e-4 absolute (range [0, sum w] = [0, 3])

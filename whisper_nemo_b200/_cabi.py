@@ -52,15 +52,19 @@ _SIGNATURES = {
     "b200d_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "b200d_cos_affinity": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200d_fuse_scales": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
-    "b200d_row_rank": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
-    "b200d_laplacian_from_rank": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200d_interp_scales": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "b200d_masked_rowsum": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_row_rank": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_laplacian_from_rank": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200d_graph_reach_rank": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_eigvals_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "b200d_eigvals_batched": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200d_topp_binarize": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
-    "b200d_graph_reach": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
-    "b200d_gram": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_gram_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "b200d_gram": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200d_small_eig": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "b200d_right_mul": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "b200d_resid_norms": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_kmeans_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "b200d_kmeans": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_float,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -116,9 +120,50 @@ def check(rc, name):
         raise RuntimeError(f"{name} failed ({rc}): {msg}")
 
 
+# kernels launched per C-ABI call (bench.py's gpu_launches claim is the sum over the timed region)
+KERNELS_PER_CALL = {
+    "b200d_featurize": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_apply_relu": 1,
+    "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
+    "b200d_masked_rowsum": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
+    "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
+    "b200d_resid_norms": 1, "b200d_kmeans": 1,
+}
+launch_count = 0
+_profile = None  # {name: [(event0, event1, work)]} while a profiled step runs
+
+
+def start_profile():
+    """Record a CUDA-event pair around every C-ABI call (bench.py's per-kernel roofline leg; adds event overhead,
+    so it is never active during the timed steps)."""
+    global _profile
+    _profile = {}
+
+
+def stop_profile():
+    """-> {name: {"calls": n, "ms": total device ms, "work": sum of 2*M*N*K for GEMM calls}}"""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, spans in (prof or {}).items():
+        out[name] = {"calls": len(spans), "ms": sum(e0.elapsed_time(e1) for e0, e1, _ in spans), "work": sum(w for _, _, w in spans)}
+    return out
+
+
 def call(name, *args):
+    global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = getattr(lib, name)
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        work = 2.0 * args[4] * args[5] * args[6] if name == "b200d_gemm_f16" else 0.0
+        _profile.setdefault(name, []).append((e0, e1, work))
+    else:
+        rc = fn(*args)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 

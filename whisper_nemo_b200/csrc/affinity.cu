@@ -124,18 +124,57 @@ struct FuseParams {
 };
 
 __global__ void __launch_bounds__(256) fuse_scales_kernel(const FuseParams p) {
-  const int i = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.n) return;
-  float acc = 0.f;
+  for (int i = blockIdx.y; i < p.n; i += gridDim.y) {
+    float acc = 0.f;
 #pragma unroll 1
-  for (int s = 0; s < p.S; ++s) {
-    const float mn = __ldg(p.minmax[s]), mx = __ldg(p.minmax[s] + 1);
-    const int mi = __ldg(p.map[s] + i), mj = __ldg(p.map[s] + j);
-    const float c = __ldg(p.cosm[s] + static_cast<size_t>(mi) * p.ns[s] + mj);
-    acc += p.w[s] * ((c - mn) / (mx - mn));
+    for (int s = 0; s < p.S; ++s) {
+      const float mn = __ldg(p.minmax[s]), mx = __ldg(p.minmax[s] + 1);
+      const int mi = __ldg(p.map[s] + i), mj = __ldg(p.map[s] + j);
+      const float c = __ldg(p.cosm[s] + static_cast<size_t>(mi) * p.ns[s] + mj);
+      acc += p.w[s] * ((c - mn) / (mx - mn));
+    }
+    p.fused[static_cast<size_t>(i) * p.n + j] = acc;
   }
-  p.fused[static_cast<size_t>(i) * p.n + j] = acc;
+}
+
+
+// Scale-interpolated embeddings of the long-form path (offline_clustering.get_scale_interpolated_embs):
+// out[i] = sum_s w_s * emb_s[map_s[i]]
+struct InterpParams {
+  int S;
+  const float* emb[kMaxScales];
+  const int* map[kMaxScales];
+  float w[kMaxScales];
+  float* out;
+  int n, d;
+};
+
+__global__ void __launch_bounds__(256) interp_scales_kernel(const InterpParams p) {
+  const size_t total = static_cast<size_t>(p.n) * p.d;
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(e / p.d), c = static_cast<int>(e - static_cast<size_t>(i) * p.d);
+    float acc = 0.f;
+#pragma unroll 1
+    for (int s = 0; s < p.S; ++s) acc += p.w[s] * __ldg(p.emb[s] + static_cast<size_t>(__ldg(p.map[s] + i)) * p.d + c);
+    p.out[e] = acc;
+  }
+}
+
+// out[j] = sum_i [labels[i] == labels[j]] mat[j][i]: the within-cluster affinity mass of every point, which ranks
+// the merge candidates of online_clustering.run_reducer / get_closest_embeddings for all clusters in one pass.
+__global__ void __launch_bounds__(256) masked_rowsum_kernel(const float* __restrict__ mat, int n, const int* __restrict__ labels,
+                                                            float* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int lab = __ldg(labels + row);
+  const float* r = mat + static_cast<size_t>(row) * n;
+  float acc = 0.f;
+  for (int i = lane; i < n; i += 32)
+    if (__ldg(labels + i) == lab) acc += __ldg(r + i);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
 }
 
 }  // namespace b200d
@@ -164,7 +203,7 @@ extern "C" int b200d_fuse_scales(int32_t n_scales, const float* const* cos_host,
                                  const float* const* minmax_host, const float* weights_host, float* fused, int32_t n_base,
                                  void* stream) {
   B200D_CHECK_ARG(n_scales > 0 && n_scales <= kMaxScales && cos_host && ns_host && map_host && minmax_host && weights_host && fused);
-  B200D_CHECK_ARG(n_base > 0 && n_base <= 65535 * 64);
+  B200D_CHECK_ARG(n_base > 0);
   FuseParams p;
   p.S = n_scales;
   for (int s = 0; s < n_scales; ++s) {
@@ -173,9 +212,32 @@ extern "C" int b200d_fuse_scales(int32_t n_scales, const float* const* cos_host,
   }
   p.fused = fused;
   p.n = n_base;
-  B200D_CHECK_ARG(n_base <= 65535);
-  dim3 grid((n_base + 255) / 256, n_base);
+  dim3 grid((n_base + 255) / 256, n_base < 65535 ? n_base : 65535);
   fuse_scales_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_interp_scales(int32_t n_scales, const float* const* emb_host, const int32_t* const* map_host,
+                                   const float* weights_host, float* out, int32_t n_base, int32_t d, void* stream) {
+  B200D_CHECK_ARG(n_scales > 0 && n_scales <= kMaxScales && emb_host && map_host && weights_host && out && n_base > 0 && d > 0);
+  InterpParams p;
+  p.S = n_scales;
+  for (int s = 0; s < n_scales; ++s) {
+    B200D_CHECK_ARG(emb_host[s] && map_host[s]);
+    p.emb[s] = emb_host[s]; p.map[s] = map_host[s]; p.w[s] = weights_host[s];
+  }
+  p.out = out; p.n = n_base; p.d = d;
+  const size_t total = static_cast<size_t>(n_base) * d;
+  const int blocks = static_cast<int>((total + 255) / 256 < static_cast<size_t>(kNumSMs) * 8 ? (total + 255) / 256 : kNumSMs * 8);
+  interp_scales_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_masked_rowsum(const float* mat, int32_t n, const int32_t* labels, float* out, void* stream) {
+  B200D_CHECK_ARG(mat && labels && out && n > 0);
+  masked_rowsum_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(mat, n, labels, out);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }

@@ -83,11 +83,13 @@ __global__ void __launch_bounds__(256) laplacian_from_rank_kernel(const uint16_t
 }
 
 // ------------------------------------------------------------------------------------ connectivity on the rank form
+// One CTA per p of the list: nodes reachable from node 0 in the p-neighbour graph (frontier expansion).
 __global__ void __launch_bounds__(1024) graph_reach_rank_kernel(const uint16_t* __restrict__ rank, const uint16_t* __restrict__ rankT,
-                                                                 int n, int p, int* __restrict__ reach) {
+                                                                 int n, const PList pl, int* __restrict__ reach) {
   __shared__ unsigned char visited[1024], frontier[1024], nxt[1024];
   __shared__ int changed, count;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = pl.p[blockIdx.x];
   visited[tid] = (tid == 0);
   frontier[tid] = (tid == 0);
   nxt[tid] = 0;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(1024) graph_reach_rank_kernel(const uint16_t* 
   }
   if (tid < n && visited[tid]) atomicAdd(&count, 1);
   __syncthreads();
-  if (tid == 0) reach[0] = count;
+  if (tid == 0) reach[blockIdx.x] = count;
 }
 
 // ------------------------------------------------------------------------------------ full-matrix top-p select
@@ -232,10 +234,14 @@ extern "C" int b200d_laplacian_from_rank(const void* rank_u16, const void* rankT
   return B200D_OK;
 }
 
-extern "C" int b200d_graph_reach_rank(const void* rank_u16, const void* rankT_u16, int32_t n, int32_t p, int32_t* reach, void* stream) {
-  B200D_CHECK_ARG(rank_u16 && rankT_u16 && reach && n > 0 && n <= 1024 && p >= 0);
-  graph_reach_rank_kernel<<<1, 1024, 0, as_stream(stream)>>>(reinterpret_cast<const uint16_t*>(rank_u16),
-                                                             reinterpret_cast<const uint16_t*>(rankT_u16), n, p, reach);
+extern "C" int b200d_graph_reach_rank(const void* rank_u16, const void* rankT_u16, int32_t n, const int32_t* p_list_host, int32_t np,
+                                      int32_t* reach, void* stream) {
+  B200D_CHECK_ARG(rank_u16 && rankT_u16 && reach && p_list_host && n > 0 && n <= 1024 && np > 0 && np <= 64);
+  PList pl;
+  pl.np = np;
+  for (int b = 0; b < np; ++b) pl.p[b] = p_list_host[b];
+  graph_reach_rank_kernel<<<np, 1024, 0, as_stream(stream)>>>(reinterpret_cast<const uint16_t*>(rank_u16),
+                                                              reinterpret_cast<const uint16_t*>(rankT_u16), n, pl, reach);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }

@@ -1,0 +1,303 @@
+"""`ClusteringDiarizer`: the drop-in for the NeMo class the reference runs.
+
+The reference calls `NeuralDiarizer(cfg=create_config(dir)).to(device).diarize()`
+(diarize.py:200-201, nemo_process.py:31-32); NeMo's NeuralDiarizer builds a
+`ClusteringDiarizer(cfg, speaker_model)` and runs its `diarize()` before the MSDD decoder.
+This class keeps that constructor / `.to()` / `.diarize(paths2audio_files=None, batch_size=0)`
+surface, the unchanged `diar_infer_*.yaml` schema (nemo_msdd_configs/*.yaml:7-56 after the
+overrides of helpers.py:282-301) and the manifest-in / RTTM-out contract, and replaces
+everything in between with the B200 path:
+
+  WAV once -> HBM  ->  featurize + TitaNet-L over every window of every scale (titanet.py)
+               ->  multi-scale affinity + NME-SC + spectral clustering (clustering.py / longform.py)
+               ->  labels -> out_dir/pred_rttms/<stem>.rttm (+ the speaker_outputs/ files MSDD reads)
+
+MarbleNet VAD is outside this path: speech regions come from `oracle_vad: True`
+(+ `rttm_filepath` in the manifest) or `vad.external_vad_manifest`.  There is no CPU fallback.
+"""
+import json
+import os
+import pickle as pkl
+import shutil
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import speaker_utils as su
+from .config import as_config
+from .titanet import HOP, TitaNetB200
+
+
+def _get(cfg, dotted, default=None):
+    cur = cfg
+    for k in dotted.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(k, None) if hasattr(cur, "get") else getattr(cur, k, None)
+    return default if cur is None else cur
+
+
+class DeviceTimer:
+    """Per-stage device time from CUDA events on the launching stream (no host sync until read)."""
+
+    def __init__(self, enabled: bool = True):
+        self.enabled = enabled
+        self.spans = []
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.spans.append((name, e0, e1))
+        return e1
+
+    @staticmethod
+    def stop(handle):
+        if handle is not None:
+            handle.record()
+
+    def totals_ms(self) -> Dict[str, float]:
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        for name, e0, e1 in self.spans:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+class ClusteringDiarizer:
+    def __init__(self, cfg, speaker_model=None):
+        """cfg: DiarConfig / dict / OmegaConf DictConfig with the diar_infer_*.yaml schema.
+        speaker_model: a TitaNetB200, a TitaNet-L state_dict, or None (-> `speaker_embeddings.model_path`:
+        a checkpoint path, or the name `titanet_large`, which resolves to the fixed-seed random-init
+        TitaNet-L of checkpoint.py -- there is no network for the NGC download)."""
+        _cabi.require_device()
+        self.cfg = as_config(cfg)
+        self._cfg = self.cfg
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.sample_rate = int(_get(self.cfg, "sample_rate", 16000))
+        if self.sample_rate != 16000:
+            raise ValueError("TitaNet-L features are defined at 16 kHz")
+        self.batch_size = int(_get(self.cfg, "batch_size", 64))
+        self.verbose = bool(_get(self.cfg, "verbose", False))
+        p = _get(self.cfg, "diarizer.speaker_embeddings.parameters")
+        self.multiscale_args_dict = su.parse_scale_configs(_get(p, "window_length_in_sec"), _get(p, "shift_length_in_sec"),
+                                                           _get(p, "multiscale_weights"))
+        self._cluster_params = _get(self.cfg, "diarizer.clustering.parameters")
+        self._speaker_model = self._init_speaker_model(speaker_model)
+        self.stage_ms: Dict[str, float] = {}
+        self.results: Dict[str, dict] = {}
+        self.embs_and_timestamps: Dict[str, dict] = {}
+
+    # NeMo's `.to(device)` idiom (diarize.py:200): accepted; the path only exists on CUDA.
+    def to(self, device):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("whisper_nemo_b200.ClusteringDiarizer runs on a B200 only (no CPU path)")
+        return self
+
+    def _init_speaker_model(self, speaker_model):
+        if isinstance(speaker_model, TitaNetB200):
+            return speaker_model
+        if isinstance(speaker_model, dict):
+            return TitaNetB200(speaker_model, self.device)
+        if speaker_model is not None and hasattr(speaker_model, "state_dict"):
+            return TitaNetB200(speaker_model.state_dict(), self.device)
+        model_path = _get(self.cfg, "diarizer.speaker_embeddings.model_path")
+        from . import checkpoint
+
+        return TitaNetB200(checkpoint.resolve(model_path, self.device), self.device)
+
+    # ------------------------------------------------------------------ untimed preparation
+    def _prepare(self, paths2audio_files=None):
+        cfg = self.cfg
+        out_dir = _get(cfg, "diarizer.out_dir")
+        if out_dir is None:
+            raise ValueError("diarizer.out_dir is required")
+        self._out_dir = out_dir
+        self._speaker_dir = os.path.join(out_dir, "speaker_outputs")
+        if os.path.exists(self._speaker_dir):
+            shutil.rmtree(self._speaker_dir, ignore_errors=True)
+        os.makedirs(self._speaker_dir)
+        os.makedirs(os.path.join(out_dir, "pred_rttms"), exist_ok=True)
+        manifest = _get(cfg, "diarizer.manifest_filepath")
+        if paths2audio_files:
+            manifest = os.path.join(out_dir, "paths2audio_filepath.json")
+            with open(manifest, "w") as f:
+                for path in paths2audio_files:
+                    json.dump({"audio_filepath": path, "offset": 0, "duration": None, "label": "infer", "text": "-"}, f)
+                    f.write("\n")
+        if manifest is None:
+            raise ValueError("diarizer.manifest_filepath is required")
+        self.AUDIO_RTTM_MAP = su.audio_rttm_map(manifest)
+        # every recording is decoded ONCE into one pinned host buffer (upstream re-opens the WAV per segment)
+        wavs = {u: su.read_wav(m["audio_filepath"], self.sample_rate) for u, m in self.AUDIO_RTTM_MAP.items()}
+        self._wav_offset, total = {}, 0
+        for u, w in wavs.items():
+            self._wav_offset[u] = (total, len(w))
+            total += len(w)
+        if total >= 2 ** 31:
+            raise ValueError("more than 2^31 samples in one manifest; split the batch")
+        self._wav_host = torch.empty(total, dtype=torch.float32).pin_memory()
+        for u, w in wavs.items():
+            o, n = self._wav_offset[u]
+            self._wav_host[o : o + n] = torch.from_numpy(w)
+        durations = {u: n / self.sample_rate for u, (o, n) in self._wav_offset.items()}
+        ext = _get(cfg, "diarizer.vad.external_vad_manifest")
+        if _get(cfg, "diarizer.oracle_vad", False):
+            speech_manifest = su.write_rttm2manifest(self.AUDIO_RTTM_MAP, os.path.join(self._speaker_dir, "oracle_vad_manifest.json"), durations)
+        elif ext:
+            speech_manifest = ext
+        else:
+            raise NotImplementedError(
+                "MarbleNet VAD is outside the B200 hot path (embed + NME-SC): set diarizer.oracle_vad=True with rttm_filepath "
+                "in the manifest, or diarizer.vad.external_vad_manifest")
+        self._scales = {}
+        for scale_idx, (window, shift) in self.multiscale_args_dict["scale_dict"].items():
+            path = os.path.join(self._speaker_dir, f"subsegments_scale{scale_idx}.json")
+            entries = su.segments_manifest_to_subsegments_manifest(speech_manifest, path, window, shift)
+            self._scales[scale_idx] = self._plan_scale(entries)
+
+    def _plan_scale(self, entries: List[dict]) -> dict:
+        """Window descriptors of one scale: sample ranges in the concatenated waveform, and the frame
+        count each window is tiled up to (the max length inside its dataloader batch of `batch_size`,
+        label_models' fixed_seq collate)."""
+        sr = self.sample_rate
+        uniq, start, length, t0, t1 = [], [], [], [], []
+        for dic in entries:
+            u = dic.get("uniq_id") or su.get_uniqname_from_filepath(dic["audio_filepath"])
+            off, n_total = self._wav_offset[u]
+            s = int(dic["offset"] * sr)
+            n = min(int(dic["duration"] * sr), n_total - s)
+            if n < 1:
+                raise ValueError(f"empty window at {dic['offset']} s in {u}")
+            uniq.append(u)
+            start.append(off + s)
+            length.append(n)
+            t0.append(dic["offset"])
+            t1.append(dic["offset"] + dic["duration"])
+        length_np = np.asarray(length, dtype=np.int64)
+        fixed = np.empty_like(length_np)
+        for b0 in range(0, len(length_np), self.batch_size):
+            fixed[b0 : b0 + self.batch_size] = length_np[b0 : b0 + self.batch_size].max() if len(length_np) else 0
+        return {"uniq": uniq, "start": np.asarray(start, dtype=np.int64), "len": length_np, "fixed": fixed, "t0": t0, "t1": t1}
+
+    # ------------------------------------------------------------------ device work
+    def _extract_embeddings(self, plan: dict, wav_dev: torch.Tensor) -> torch.Tensor:
+        """All windows of one scale -> float32 [n, 192] on device (manifest order)."""
+        n = len(plan["uniq"])
+        out = torch.empty(n, 192, dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        fixed = plan["fixed"]
+        for fl in np.unique(fixed):
+            idx = np.nonzero(fixed == fl)[0]
+            idx_t = torch.from_numpy(idx).to(self.device)
+            st = torch.from_numpy(plan["start"][idx].astype(np.int32)).to(self.device)
+            ln = torch.from_numpy(plan["len"][idx].astype(np.int32)).to(self.device)
+            emb = self._speaker_model.embed_segments(wav_dev, st, ln, int(fl))
+            out.index_copy_(0, idx_t, emb)
+        return out
+
+    def _cluster_one(self, uniq_id: str, e: dict):
+        from .longform import LongFormSpeakerClustering
+
+        clus = self._cluster_params
+        if _get(clus, "oracle_num_speakers", False):
+            num_speakers = self.AUDIO_RTTM_MAP[uniq_id].get("num_speakers", None)
+            if num_speakers is None:
+                raise ValueError("Provided option as oracle num of speakers but num_speakers in manifest is null")
+        else:
+            num_speakers = -1
+        sc = LongFormSpeakerClustering()
+        labels = sc.forward_infer(
+            embeddings_in_scales=e["embeddings"],
+            timestamps_in_scales=e["timestamps"],
+            multiscale_segment_counts=e["multiscale_segment_counts"],
+            multiscale_weights=e["multiscale_weights"],
+            oracle_num_speakers=int(num_speakers),
+            max_num_speakers=int(_get(clus, "max_num_speakers", 8)),
+            max_rp_threshold=float(_get(clus, "max_rp_threshold", 0.25)),
+            sparse_search_volume=int(_get(clus, "sparse_search_volume", 30)),
+            chunk_cluster_count=_get(clus, "chunk_cluster_count", None),
+            embeddings_per_chunk=_get(clus, "embeddings_per_chunk", None),
+        )
+        return labels, sc
+
+    def run_device(self, wav_dev: Optional[torch.Tensor] = None, timers: bool = True) -> Dict[str, np.ndarray]:
+        """The timed region of the benchmark: waveform (host or already on device) -> labels on host."""
+        timer = DeviceTimer(timers)
+        h = timer.start("h2d")
+        if wav_dev is None:
+            wav_dev = self._wav_host.to(self.device, non_blocking=True)
+        timer.stop(h)
+        h = timer.start("embed")
+        per_scale = {}
+        for scale_idx, plan in self._scales.items():
+            embs = self._extract_embeddings(plan, wav_dev)
+            e_by, t_by = {}, {}
+            uniq_arr = np.asarray(plan["uniq"])
+            for u in self.AUDIO_RTTM_MAP.keys():
+                sel = np.nonzero(uniq_arr == u)[0]
+                if len(sel) == 0:
+                    continue
+                e_by[u] = embs[int(sel[0]) : int(sel[-1]) + 1] if (np.diff(sel) == 1).all() else embs[torch.from_numpy(sel).to(self.device)]
+                t_by[u] = [[plan["t0"][i], plan["t1"][i]] for i in sel]
+            per_scale[scale_idx] = (e_by, t_by)
+        timer.stop(h)
+        self.multiscale_embeddings_and_timestamps = per_scale
+        self.embs_and_timestamps = su.get_embs_and_timestamps(per_scale, self.multiscale_args_dict)
+        h = timer.start("cluster")
+        pending = {}
+        for uniq_id in self.AUDIO_RTTM_MAP.keys():
+            if uniq_id not in self.embs_and_timestamps:
+                continue
+            labels, sc = self._cluster_one(uniq_id, self.embs_and_timestamps[uniq_id])
+            pending[uniq_id] = (labels, sc)
+        timer.stop(h)
+        labels_host = {}
+        self.results = {}
+        for uniq_id, (labels, sc) in pending.items():
+            lab = labels.cpu().numpy()
+            labels_host[uniq_id] = lab
+            base_scale_idx = int(self.embs_and_timestamps[uniq_id]["multiscale_segment_counts"].shape[0]) - 1
+            self.results[uniq_id] = {"labels": lab, "timestamps": sc.timestamps_in_scales[base_scale_idx], "base_scale_idx": base_scale_idx,
+                                     "debug": dict(sc.speaker_clustering.debug), "fused_affinity": sc.speaker_clustering.fused_affinity}
+        if timers:
+            self.stage_ms = timer.totals_ms()
+        return labels_host
+
+    # ------------------------------------------------------------------ outputs
+    def _write_outputs(self):
+        out_rttm_dir = os.path.join(self._out_dir, "pred_rttms")
+        lines_cluster_labels, base_scale_idx = [], 0
+        for uniq_id, r in self.results.items():
+            turns, lines = su.generate_cluster_labels(r["timestamps"], r["labels"])
+            su.labels_to_rttmfile(turns, uniq_id, out_rttm_dir)
+            lines_cluster_labels.extend(f"{uniq_id} {line}\n" for line in lines)
+            base_scale_idx = r["base_scale_idx"]
+            r["rttm_labels"] = turns
+        su.write_cluster_labels(base_scale_idx, lines_cluster_labels, out_rttm_dir)
+        if _get(self.cfg, "diarizer.speaker_embeddings.parameters.save_embeddings", False):
+            emb_dir = os.path.join(self._speaker_dir, "embeddings")
+            os.makedirs(emb_dir, exist_ok=True)
+            for scale_idx, (e_by, _) in self.multiscale_embeddings_and_timestamps.items():
+                with open(os.path.join(emb_dir, f"subsegments_scale{scale_idx}_embeddings.pkl"), "wb") as f:
+                    pkl.dump({u: e.cpu() for u, e in e_by.items()}, f)
+
+    def diarize(self, paths2audio_files: List[str] = None, batch_size: int = 0):
+        """Diarize every recording of the manifest; writes `<out_dir>/pred_rttms/<stem>.rttm`.
+        Returns None (upstream returns DER scores only when reference RTTMs are being scored)."""
+        if batch_size:
+            self.batch_size = int(batch_size)
+        t0 = time.perf_counter()
+        self._prepare(paths2audio_files)
+        t1 = time.perf_counter()
+        self.run_device()
+        t2 = time.perf_counter()
+        self._write_outputs()
+        self.host_seconds = {"prepare": t1 - t0, "device_path": t2 - t1, "write": time.perf_counter() - t2}
+        return None

@@ -1,0 +1,220 @@
+"""Long-form clustering on B200: recordings with more than `embeddings_per_chunk` base-scale windows.
+
+Mirrors upstream NeMo's `nemo/collections/asr/parts/utils/longform_clustering.py`
+(`LongFormSpeakerClustering`) and the reducer helpers it borrows from
+`online_clustering.py` (`get_merge_quantity`, `calculate_removable_counts`,
+`get_closest_embeddings`, `merge_vectors`, `run_reducer`) -- the behaviour the reference
+gets from the shipped knobs `chunk_cluster_count: 50`, `embeddings_per_chunk: 10000`
+(nemo_msdd_configs/diar_infer_*.yaml:55-56) on any recording longer than ~42 min.
+
+Per chunk the O(N^2)/O(N^3) work stays on device: scale interpolation (interp_scales), the
+10 000 x 10 000 cosine affinity, NME sweep, binarisation, the 50-vector spectral embedding and
+k-means (clustering.py), and the within-cluster affinity mass that ranks merge candidates
+(masked_rowsum, one pass for all 50 clusters).  What remains on the host is integer
+bookkeeping on <= 50 cluster sizes and index lists.
+"""
+import ctypes
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import ptr
+from .clustering import SpeakerClustering, _s, get_argmin_mat, cos_affinity, _fuse, split_input_data
+
+
+def get_scale_interpolated_embs(multiscale_weights, embeddings_in_scales, timestamps_in_scales):
+    """One embedding per base-scale window: the weighted sum over scales of the embedding of the
+    nearest window of each scale.  Returns (float32 [n_base, d] on device, mapping list)."""
+    mapping = get_argmin_mat(timestamps_in_scales)
+    dev = embeddings_in_scales[0].device
+    n_base = int(timestamps_in_scales[-1].shape[0])
+    d = int(embeddings_in_scales[0].shape[1])
+    S = len(embeddings_in_scales)
+    embs = [e.float().contiguous() for e in embeddings_in_scales]
+    maps = [torch.from_numpy(np.sort(m)).to(dev) for m in mapping]
+    weights = torch.as_tensor(multiscale_weights).reshape(-1).tolist()
+    out = torch.empty(n_base, d, dtype=torch.float32, device=dev)
+    emb_p = (ctypes.c_void_p * S)(*[e.data_ptr() for e in embs])
+    map_p = (ctypes.c_void_p * S)(*[m.data_ptr() for m in maps])
+    w = (ctypes.c_float * S)(*[float(x) for x in weights])
+    _cabi.call("b200d_interp_scales", S, emb_p, map_p, w, ptr(out), n_base, d, _s())
+    return out, mapping
+
+
+def calculate_removable_counts(removable_counts_mat: torch.Tensor, remain_count: int, num_clus: int) -> torch.Tensor:
+    """Spread `remain_count` kept vectors over the clusters as evenly as their sizes allow
+    (water-filling from the largest cluster down); returns how many vectors each cluster gives up."""
+    asc = torch.sort(removable_counts_mat)[0]
+    order = torch.sort(removable_counts_mat, descending=True)[1]
+    padded = torch.cat([torch.tensor([0]), asc, torch.tensor([0])])
+    steps = (padded[1:] - padded[:-1])[:num_clus]
+    level_cost = torch.cumsum(torch.arange(num_clus, 0, -1) * steps, dim=0)
+    level = 0
+    for level, cost in enumerate(level_cost):
+        if remain_count < cost:
+            break
+    left = remain_count
+    for j in range(level):
+        removable_counts_mat[order[: num_clus - j]] -= steps[j]
+        left -= int(steps[j].item()) * (num_clus - j)
+    share, extra = divmod(left, num_clus - level)
+    removable_counts_mat[order[: num_clus - level]] -= share
+    removable_counts_mat[order[:extra]] -= 1
+    return removable_counts_mat.int()
+
+
+def get_merge_quantity(num_to_be_removed: int, pre_clus_labels: torch.Tensor, min_count_per_cluster: int) -> torch.Tensor:
+    if num_to_be_removed > pre_clus_labels.shape[0] - 1:
+        raise ValueError(f"num_to_be_removed: {num_to_be_removed} should be less than pre_clus_labels length - 1")
+    remain_count = pre_clus_labels.shape[0] - num_to_be_removed
+    spk_freq_count = torch.bincount(pre_clus_labels)
+    num_clus = len(torch.unique(pre_clus_labels))
+    if remain_count < min_count_per_cluster * num_clus:
+        raise ValueError("The remaining embedding vectors should be more than the minimum quantity")
+    floor = torch.minimum(torch.full_like(spk_freq_count, min_count_per_cluster), spk_freq_count)
+    remain_count -= int(floor.sum())
+    removable = calculate_removable_counts(spk_freq_count - floor, remain_count, num_clus)
+    if int(removable.sum()) != num_to_be_removed:
+        raise ValueError("Sum of `removable_counts_mat` is not equal to `num_to_be_removed` variable.")
+    if not torch.all(removable >= 0) or not torch.all(spk_freq_count - floor >= removable):
+        raise ValueError("removable_counts_mat out of range")
+    return removable
+
+
+class LongFormSpeakerClustering:
+    def __init__(self):
+        self.speaker_clustering = SpeakerClustering()
+        self.embeddings_in_scales: List[torch.Tensor] = []
+        self.timestamps_in_scales: List[torch.Tensor] = []
+
+    @staticmethod
+    def get_div_ceil_count(numer: int, denomin: int) -> int:
+        return int(torch.ceil(torch.tensor(numer / denomin)).item())
+
+    def check_input(self, embeddings_per_chunk, chunk_cluster_count, max_num_speakers) -> None:
+        if chunk_cluster_count is None or embeddings_per_chunk is None:
+            raise ValueError(f"chunk_cluster_count ({chunk_cluster_count}) and embeddings_per_chunk ({embeddings_per_chunk}) should be set.")
+        if chunk_cluster_count >= embeddings_per_chunk:
+            raise ValueError("chunk_cluster_count should be smaller than embeddings_per_chunk.")
+        if max_num_speakers <= 1:
+            raise ValueError("max_num_speakers should be greater than 1.")
+        if chunk_cluster_count <= max_num_speakers:
+            raise ValueError("chunk_cluster_count should be greater than max_num_speakers.")
+
+    def forward_infer(self, embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
+                      oracle_num_speakers: int = -1, max_rp_threshold: float = 0.15, max_num_speakers: int = 8,
+                      sparse_search_volume: int = 30, fixed_thres: float = -1.0, chunk_cluster_count=50,
+                      embeddings_per_chunk=10000) -> torch.Tensor:
+        if embeddings_per_chunk is not None and int(torch.max(multiscale_segment_counts)) > embeddings_per_chunk:
+            return self.long_forward_infer(embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
+                                           oracle_num_speakers, max_rp_threshold, max_num_speakers, sparse_search_volume, fixed_thres,
+                                           int(chunk_cluster_count), int(embeddings_per_chunk))
+        labels = self.speaker_clustering.forward_infer(
+            embeddings_in_scales=embeddings_in_scales, timestamps_in_scales=timestamps_in_scales,
+            multiscale_segment_counts=multiscale_segment_counts, multiscale_weights=multiscale_weights,
+            oracle_num_speakers=oracle_num_speakers, max_rp_threshold=max_rp_threshold, max_num_speakers=max_num_speakers,
+            sparse_search_volume=sparse_search_volume, fixed_thres=fixed_thres)
+        self.timestamps_in_scales = self.speaker_clustering.timestamps_in_scales
+        return labels
+
+    def _reduce_chunk(self, emb_part: torch.Tensor, mat: torch.Tensor, Y_part: torch.Tensor, class_target_vol: torch.Tensor,
+                      offset_index: int):
+        """run_reducer for every cluster of one chunk.  Returns ([merged_embs per cluster], [index mappings])."""
+        n = emb_part.shape[0]
+        y_host = Y_part.cpu()
+        mass_host = None
+        if mat is not None and int(class_target_vol.sum()) > 0:
+            mass = torch.empty(n, dtype=torch.float32, device=emb_part.device)
+            y32 = Y_part.to(torch.int32).contiguous()
+            _cabi.call("b200d_masked_rowsum", ptr(mat), n, ptr(y32), ptr(mass), _s())
+            mass_host = mass.cpu()
+        merged_list, mapping_list = [], []
+        for spk_idx, merge_quantity in enumerate(class_target_vol.tolist()):
+            target = torch.where(y_host == spk_idx)[0]
+            if merge_quantity > 0:
+                if merge_quantity > target.shape[0] - 1:
+                    raise ValueError("merge_quantity is larger than the half of targeted speaker's labels")
+                order = torch.argsort(mass_host[target], descending=True)
+                selected, rest = order[: merge_quantity + 1], order[merge_quantity + 1 :]
+                rest_sorted = rest.sort()[0]
+                tgt_dev = target.to(emb_part.device)
+                avg = emb_part.index_select(0, tgt_dev[selected.to(emb_part.device)]).mean(dim=0, keepdim=True)
+                if rest_sorted.numel() > 0:
+                    keep = emb_part.index_select(0, tgt_dev[rest_sorted.to(emb_part.device)])
+                    merged = torch.cat([keep, avg], dim=0)
+                else:
+                    merged = avg
+                mapping = (target[rest_sorted] + offset_index, target[selected] + offset_index)
+                if target.shape[0] - merge_quantity != merged.shape[0]:
+                    raise ValueError("Reducer output is not matched to the target quantity")
+            else:
+                merged = emb_part.index_select(0, target.to(emb_part.device))
+                mapping = (target + offset_index, torch.arange(0))
+            merged_list.append(merged)
+            mapping_list.append(mapping)
+        return merged_list, mapping_list
+
+    def long_forward_infer(self, embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
+                           oracle_num_speakers, max_rp_threshold, max_num_speakers, sparse_search_volume, fixed_thres,
+                           chunk_cluster_count, embeddings_per_chunk) -> torch.Tensor:
+        self.check_input(embeddings_per_chunk, chunk_cluster_count, max_num_speakers)
+        self.embeddings_in_scales, self.timestamps_in_scales = split_input_data(embeddings_in_scales, timestamps_in_scales,
+                                                                                multiscale_segment_counts)
+        emb, _ = get_scale_interpolated_embs(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales)
+        n_total = emb.shape[0]
+        total_emb: List[torch.Tensor] = []
+        window_range_list: List[Tuple[int, int]] = []
+        absolute_merge_mapping = []
+        window_offset = 0
+        for win_index in range(self.get_div_ceil_count(n_total, embeddings_per_chunk)):
+            if embeddings_per_chunk * (win_index + 1) > n_total:  # last chunk is aligned to the end (overlaps the previous one)
+                offset_index = n_total - embeddings_per_chunk
+            else:
+                offset_index = embeddings_per_chunk * win_index
+            emb_part = emb[offset_index : offset_index + embeddings_per_chunk]
+            if emb_part.shape[0] == 1:
+                Y_part = torch.zeros((1,), dtype=torch.int64, device=emb.device)
+                mat = None
+            else:
+                cos, mm = cos_affinity(emb_part)
+                ident = torch.arange(emb_part.shape[0], dtype=torch.int32, device=emb.device)
+                mat = _fuse([cos], [ident], [mm], [1.0], emb_part.shape[0])
+                del cos
+                overcluster_count = min(chunk_cluster_count, mat.shape[0])
+                Y_part = self.speaker_clustering.forward_unit_infer(
+                    mat=mat, oracle_num_speakers=overcluster_count, max_rp_threshold=max_rp_threshold,
+                    max_num_speakers=chunk_cluster_count, sparse_search_volume=sparse_search_volume)
+            num_to_be_merged = int(min(embeddings_per_chunk, emb_part.shape[0]) - chunk_cluster_count)
+            y_host = Y_part.cpu()
+            min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
+            class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
+            merged_list, mapping_list = self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
+            for merged, mapping in zip(merged_list, mapping_list):
+                total_emb.append(merged)
+                absolute_merge_mapping.append(mapping)
+                window_range_list.append((window_offset, window_offset + merged.shape[0]))
+                window_offset += merged.shape[0]
+            del mat
+        reduced_embs = torch.cat(total_emb)
+        cos, mm = cos_affinity(reduced_embs)
+        ident = torch.arange(reduced_embs.shape[0], dtype=torch.int32, device=emb.device)
+        reduced_mat = _fuse([cos], [ident], [mm], [1.0], reduced_embs.shape[0])
+        Y_aggr = self.speaker_clustering.forward_unit_infer(
+            mat=reduced_mat, oracle_num_speakers=oracle_num_speakers, max_rp_threshold=max_rp_threshold,
+            max_num_speakers=max_num_speakers, sparse_search_volume=sparse_search_volume, fixed_thres=fixed_thres)
+        if reduced_embs.shape[0] != Y_aggr.shape[0]:
+            raise ValueError("The number of embeddings and labels should be same")
+        # unpack: every original window takes the label of the reduced vector it was kept as / merged into
+        y_aggr = Y_aggr.cpu()
+        Y_unpack = torch.zeros((n_total,), dtype=torch.int64)
+        for (lo, hi), (kept, merged_idx) in zip(window_range_list, absolute_merge_mapping):
+            part = y_aggr[lo:hi]
+            if len(merged_idx) > 0:
+                Y_unpack[merged_idx] = part[-1].clone()
+                if len(kept) > 0:
+                    Y_unpack[kept] = part[:-1].clone()
+            else:
+                Y_unpack[kept] = part.clone()
+        return Y_unpack.to(emb.device)

@@ -303,6 +303,8 @@ def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: d
     gemm(ws.hid, pk.attn_w2, ws.e, _cabi.EPI_BIAS, M=M, bias=pk.attn_b2)
     pool16 = ws.pool16[:n_seg]
     _cabi.call("b200d_attn_pool", ptr(ws.x), ptr(ws.e), n_seg, T, 3072, ptr(pool16), s)
+    if taps is not None:
+        taps["pool"] = pool16.clone()
     emb = ws.emb[:n_seg]
     gemm(pool16, pk.emb_w, emb, _cabi.EPI_BIAS_F32, bias=pk.emb_b)
     return emb[:, :EMB]
