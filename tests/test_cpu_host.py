@@ -1,0 +1,180 @@
+"""Host-side logic of the product (manifests, windows, RTTM text, scale mapping, long-form bookkeeping, config,
+sharding) against the oracle's restatement, on CPU.  The device kernels are exercised by the `-m gpu` tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import longform_clustering as olf
+from oracle import offline_clustering as oc
+from oracle import speaker_utils as osu
+from tests.util import synthetic_multiscale_embeddings
+from whisper_nemo_b200 import clustering as cl
+from whisper_nemo_b200 import config, longform as lf, sharding, synth
+from whisper_nemo_b200 import speaker_utils as su
+
+SCALES = [(1.5, .75), (1.25, .625), (1.0, .5), (.75, .375), (.5, .25), (3.0, 1.5), (1.9, .95), (1.2, .6)]
+
+
+def test_subsegments_equal_oracle():
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        off, dur = round(float(rng.uniform(0, 100)), 3), round(float(rng.uniform(0.01, 30)), 3)
+        w, s = SCALES[rng.integers(len(SCALES))]
+        assert osu.get_subsegments(off, w, s, dur) == su.get_subsegments(off, w, s, dur)
+
+
+@pytest.mark.parametrize("pcm16", [False, True])
+def test_manifests_and_wav_equal_oracle(tmp_path, pcm16):
+    from oracle.clustering_diarizer import read_wav
+
+    wav_path, rttm_path, wav, turns = synth.make_session(str(tmp_path), "mono_file", 45.0, 3, 3, pcm16=pcm16)
+    man = os.path.join(tmp_path, "m.json")
+    synth.write_manifest(man, [{"audio_filepath": wav_path, "rttm_filepath": rttm_path}])
+    A, B = osu.audio_rttm_map(man), su.audio_rttm_map(man)
+    assert A == B and list(A) == ["mono_file"]
+    assert np.array_equal(read_wav(wav_path), su.read_wav(wav_path))
+    osu.write_rttm2manifest(A, str(tmp_path / "o_vad.json"), {"mono_file": 45.0})
+    su.write_rttm2manifest(B, str(tmp_path / "g_vad.json"), {"mono_file": 45.0})
+    assert open(tmp_path / "o_vad.json").read() == open(tmp_path / "g_vad.json").read()
+    for w, s in SCALES[:5]:
+        osu.segments_manifest_to_subsegments_manifest(str(tmp_path / "o_vad.json"), str(tmp_path / "o_s.json"), w, s)
+        entries = su.segments_manifest_to_subsegments_manifest(str(tmp_path / "g_vad.json"), str(tmp_path / "g_s.json"), w, s)
+        assert open(tmp_path / "o_s.json").read() == open(tmp_path / "g_s.json").read()
+        assert len(entries) == sum(1 for _ in open(tmp_path / "g_s.json"))
+
+
+def test_cluster_labels_and_rttm_text_equal_oracle(tmp_path):
+    g = torch.Generator().manual_seed(1)
+    t0 = torch.cumsum(torch.rand(300, generator=g) * 0.4 + 0.05, 0)
+    ts = torch.stack([t0, t0 + 0.5], 1).float()
+    for trial in range(50):
+        lab = torch.randint(0, 4, (300,), generator=g)
+        a, b = osu.generate_cluster_labels(ts, lab), su.generate_cluster_labels(ts, lab)
+        assert a[0] == b[0] and a[1] == b[1]
+    pa = osu.labels_to_rttmfile(a[0], "x", str(tmp_path))
+    text_o = open(pa).read()
+    pb = su.labels_to_rttmfile(b[0], "x", str(tmp_path))
+    assert open(pb).read() == text_o and "SPEAKER x 1   " in text_o
+    assert [(round(s, 3), round(e, 3), k) for s, e, k in su.rttm_to_turns(pb)] == \
+           [(round(float(l.split()[0]), 3), round(float(l.split()[1]), 3), l.split()[2]) for l in osu.rttm_to_labels(pa)]
+
+
+def test_scale_mapping_equals_dense_argmin():
+    scales = [(3.0, 1.5), (2.5, 1.25), (2.0, 1.0), (1.5, .75), (1.0, .5), (.5, .25)]
+    _, stamps, counts, _ = synthetic_multiscale_embeddings(1800.0, scales, 4, 1, dim=4)
+    st = list(torch.split(stamps, counts.tolist()))
+    for a, b in zip(oc.get_argmin_mat(st), cl.get_argmin_mat(st)):
+        assert np.array_equal(a.numpy(), b)
+    # gaps between speech regions and duplicated centres
+    odd = [torch.tensor([[0.0, 1.0], [0.5, 1.5], [10.0, 11.0], [10.0, 11.0], [30.0, 30.2]]), torch.tensor([[0.0, 0.5], [0.25, 0.75], [0.5, 1.0], [5.2, 5.7], [10.2, 10.7], [20.0, 20.5], [30.0, 30.2]])]
+    for a, b in zip(oc.get_argmin_mat(odd), cl.get_argmin_mat(odd)):
+        assert np.array_equal(a.numpy(), b)
+
+
+def test_longform_bookkeeping_equals_oracle():
+    rng = np.random.default_rng(0)
+    for trial in range(400):
+        k = int(rng.integers(2, 50))
+        n = int(rng.integers(k * 3, 2000))
+        labels = torch.from_numpy(rng.integers(0, k, n))
+        labels[:k] = torch.arange(k)
+        target = int(rng.integers(k, min(n - 1, 4 * k) + 1)) if n - 1 > k else k
+        mc = int(np.ceil(target / k))
+        res = []
+        for mod in (olf, lf):
+            try:
+                res.append(mod.get_merge_quantity(n - target, labels.clone(), mc))
+            except ValueError as e:
+                res.append(str(e))
+        if isinstance(res[0], str) or isinstance(res[1], str):
+            assert res[0] == res[1]
+        else:
+            assert torch.equal(res[0], res[1])
+
+
+def test_nmesc_p_value_list_equals_oracle():
+    for n in (7, 37, 110, 515, 600, 1023):
+        for thr, vol in ((0.25, 30), (0.15, 10), (0.05, 30)):
+            o = oc.NMESC(torch.zeros(n, n), max_rp_threshold=thr, sparse_search_volume=vol)
+            want = o.getPvalueList().tolist()
+            g = cl.NMESC(torch.zeros(n, n), max_rp_threshold=thr, sparse_search_volume=vol)
+            assert g.getPvalueList(n) == want and g.max_N == int(o.max_N)
+
+
+def test_config_schema_and_create_config(tmp_path):
+    for dom, n_scales in (("telephonic", 5), ("meeting", 6), ("general", 3)):
+        cfg = config.load_config(dom)
+        p = cfg.diarizer.speaker_embeddings.parameters
+        assert len(p.window_length_in_sec) == len(p.shift_length_in_sec) == len(p.multiscale_weights) == n_scales
+        c = cfg.diarizer.clustering.parameters
+        assert c.max_num_speakers == 8 and c.chunk_cluster_count == 50 and c.embeddings_per_chunk == 10000
+        with pytest.raises(config.MissingMandatoryValue):
+            cfg.diarizer.manifest_filepath
+    cfg = config.create_config(str(tmp_path))  # helpers.py:252-303
+    meta = json.loads(open(cfg.diarizer.manifest_filepath).read())
+    assert meta["audio_filepath"].endswith("mono_file.wav") and set(meta) == {"audio_filepath", "offset", "duration", "label", "text", "rttm_filepath", "uem_filepath"}
+    assert cfg.diarizer.speaker_embeddings.model_path == "titanet_large" and cfg.diarizer.oracle_vad is False and cfg.num_workers == 0
+    sd = su.parse_scale_configs([1.5, 1.0, 0.5], [0.75, 0.5, 0.25], [1, 1, 1])
+    assert sd["scale_dict"] == {0: (1.5, 0.75), 1: (1.0, 0.5), 2: (0.5, 0.25)} and not sd["use_single_scale_clustering"]
+    with pytest.raises(ValueError):
+        su.parse_scale_configs([1.0, 1.5], [0.5, 0.75], [1, 1])
+
+
+def test_reference_yaml_matches_bundled_yaml():
+    ref = "/root/reference/nemo_msdd_configs"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present on this box")
+    import yaml
+
+    for dom in ("telephonic", "meeting", "general"):
+        a = yaml.safe_load(open(os.path.join(ref, f"diar_infer_{dom}.yaml")))
+        b = config.load_config(dom).to_dict()
+        for key in ("speaker_embeddings", "clustering"):
+            assert a["diarizer"][key]["parameters"] == b["diarizer"][key]["parameters"], (dom, key)
+        assert a["batch_size"] == b["batch_size"] and a["sample_rate"] == b["sample_rate"]
+
+
+def test_recording_assignment_and_ranges():
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 8):
+        dur = rng.uniform(30, 4000, size=37).tolist()
+        parts = sharding.assign_recordings(dur, world)
+        assert sorted(i for p in parts for i in p) == list(range(37))
+        loads = [sum(dur[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(dur)
+        for n in (0, 1, 7, 100):
+            r = [sharding.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, d = 1001, 192
+        full = torch.arange(n * d, dtype=torch.float32).view(n, d)
+        lo, hi = sharding.shard_range(n, rank, world)
+        got = sharding.all_gather_rows(full[lo:hi].clone(), n)
+        assert torch.equal(got, full)
+        # batch-of-recordings sharding: every rank labels its own recordings, results are gathered as objects
+        dur = [600.0, 120.0, 900.0, 30.0, 450.0]
+        mine = sharding.assign_recordings(dur, world)[rank]
+        out = [None] * world
+        dist.all_gather_object(out, {i: f"labels-of-{i}" for i in mine})
+        merged = {k: v for part in out for k, v in part.items()}
+        assert sorted(merged) == list(range(len(dur)))
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_window_sharding_all_gather_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_gloo_worker, args=(2, 29517, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")

@@ -69,8 +69,10 @@ class DeviceTimer:
 
 
 class ClusteringDiarizer:
-    def __init__(self, cfg, speaker_model=None):
+    def __init__(self, cfg, speaker_model=None, shard_windows: bool = False):
         """cfg: DiarConfig / dict / OmegaConf DictConfig with the diar_infer_*.yaml schema.
+        shard_windows: under torch.distributed, split the windows of every scale across the ranks and all-gather
+        the embeddings (one long recording on several GPUs); clustering then runs replicated on every rank.
         speaker_model: a TitaNetB200, a TitaNet-L state_dict, or None (-> `speaker_embeddings.model_path`:
         a checkpoint path, or the name `titanet_large`, which resolves to the fixed-seed random-init
         TitaNet-L of checkpoint.py -- there is no network for the NGC download)."""
@@ -87,6 +89,7 @@ class ClusteringDiarizer:
         self.multiscale_args_dict = su.parse_scale_configs(_get(p, "window_length_in_sec"), _get(p, "shift_length_in_sec"),
                                                            _get(p, "multiscale_weights"))
         self._cluster_params = _get(self.cfg, "diarizer.clustering.parameters")
+        self.shard_windows = bool(shard_windows)
         self._speaker_model = self._init_speaker_model(speaker_model)
         self.stage_ms: Dict[str, float] = {}
         self.results: Dict[str, dict] = {}
@@ -193,6 +196,18 @@ class ClusteringDiarizer:
         if n == 0:
             return out
         fixed = plan["fixed"]
+        if self.shard_windows:
+            from . import sharding
+
+            rank, world = sharding.rank_world()
+            lo, hi = sharding.shard_range(n, rank, world)
+            local = torch.empty(hi - lo, 192, dtype=torch.float32, device=self.device)
+            for fl in np.unique(fixed[lo:hi]):
+                idx = lo + np.nonzero(fixed[lo:hi] == fl)[0]
+                st = torch.from_numpy(plan["start"][idx].astype(np.int32)).to(self.device)
+                ln = torch.from_numpy(plan["len"][idx].astype(np.int32)).to(self.device)
+                local.index_copy_(0, torch.from_numpy(idx - lo).to(self.device), self._speaker_model.embed_segments(wav_dev, st, ln, int(fl)))
+            return sharding.all_gather_rows(local, n)
         for fl in np.unique(fixed):
             idx = np.nonzero(fixed == fl)[0]
             idx_t = torch.from_numpy(idx).to(self.device)

@@ -29,7 +29,12 @@ def _speaker_params(n_speakers: int, rng: np.random.Generator):
     f0 = f0[rng.permutation(n_speakers)] * (1.0 + 0.03 * rng.standard_normal(n_speakers))
     tract = np.linspace(0.82, 1.22, n_speakers)[rng.permutation(n_speakers)]
     tilt = 0.6 + 1.0 * rng.random(n_speakers)
-    return f0, tract, tilt
+    # speaker-specific DYNAMICS: TitaNet's per-feature normalisation removes every static spectral envelope, so what
+    # separates speakers for a (random-init) network is temporal texture -- syllable rate, vibrato, vowel pace
+    spread = lambda lo, hi: np.geomspace(lo, hi, n_speakers)[rng.permutation(n_speakers)] if n_speakers > 1 else np.array([(lo * hi) ** 0.5])
+    dyn = {"am_rate": spread(2.2, 9.0), "am_depth": 0.25 + 0.5 * rng.random(n_speakers), "vib_rate": spread(3.0, 11.0),
+           "vib_depth": spread(0.01, 0.08), "vowel_s": spread(0.06, 0.32)}
+    return f0, tract, tilt, dyn
 
 
 def make_turns(duration_s: float, n_speakers: int, rng: np.random.Generator, turn=(2.0, 10.0), gap=(0.2, 1.0)) -> List[Tuple[float, float, int]]:
@@ -63,7 +68,7 @@ def synth_recording(duration_s: float, n_speakers: int, seed: int, n_harm: int =
     """Returns (float32 waveform [duration_s * 16000], [(start_s, end_s, speaker)])."""
     rng = np.random.default_rng(seed)
     n_total = int(round(duration_s * SR))
-    f0s, tracts, tilts = _speaker_params(n_speakers, rng)
+    f0s, tracts, tilts, dyn = _speaker_params(n_speakers, rng)
     turns = make_turns(duration_s, n_speakers, rng)
     gen = torch.Generator().manual_seed(seed)
     wav = 0.0008 * torch.randn(n_total, generator=gen)
@@ -73,12 +78,13 @@ def synth_recording(duration_s: float, n_speakers: int, seed: int, n_harm: int =
         n = i1 - i0
         tt = torch.arange(n, dtype=torch.float32) / SR
         # slowly varying pitch
-        f0 = f0s[spk] * (1.0 + 0.06 * torch.sin(2 * np.pi * float(rng.uniform(0.15, 0.5)) * tt + float(rng.uniform(0, 6.28))))
+        f0 = f0s[spk] * (1.0 + 0.04 * torch.sin(2 * np.pi * float(rng.uniform(0.15, 0.5)) * tt + float(rng.uniform(0, 6.28)))
+                         + float(dyn["vib_depth"][spk]) * torch.sin(2 * np.pi * float(dyn["vib_rate"][spk]) * tt + float(rng.uniform(0, 6.28))))
         phase = 2 * np.pi * torch.cumsum(f0.double(), 0).float() / SR
         # vowel-like segments of 90-280 ms
         seg_bounds = [0]
         while seg_bounds[-1] < n:
-            seg_bounds.append(seg_bounds[-1] + int(rng.uniform(0.09, 0.28) * SR))
+            seg_bounds.append(seg_bounds[-1] + max(320, int(rng.uniform(0.7, 1.3) * float(dyn["vowel_s"][spk]) * SR)))
         n_seg = len(seg_bounds) - 1
         vowel_idx = rng.integers(len(_VOWELS), size=n_seg)
         formants = _VOWELS[vowel_idx] * tracts[spk] * (1.0 + 0.02 * rng.standard_normal((n_seg, 3)))
@@ -89,7 +95,8 @@ def synth_recording(duration_s: float, n_speakers: int, seed: int, n_harm: int =
         amp_t = torch.tensor(amp.T, dtype=torch.float32)  # [H,n_seg]
         seg_of_sample = torch.bucketize(torch.arange(n), torch.tensor(seg_bounds[1:-1], dtype=torch.long), right=True)
         sig = (amp_t[:, seg_of_sample] * torch.sin(harm * phase.unsqueeze(0))).sum(0)
-        env = 0.65 + 0.35 * torch.sin(2 * np.pi * float(rng.uniform(3.0, 5.0)) * tt + float(rng.uniform(0, 6.28)))
+        depth = float(dyn["am_depth"][spk])
+        env = (1.0 - depth) + depth * torch.sin(2 * np.pi * float(dyn["am_rate"][spk]) * float(rng.uniform(0.93, 1.07)) * tt + float(rng.uniform(0, 6.28)))
         fade = torch.clamp(torch.minimum(tt, tt.flip(0)) / 0.02, max=1.0)
         level = 0.08 * (0.8 + 0.4 * float(rng.random()))
         sig = level * sig * env * fade + 0.0025 * torch.randn(n, generator=gen)
