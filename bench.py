@@ -185,7 +185,11 @@ def run_b200(args):
         _cabi.start_profile()
         diar.run_device(wav_dev=wav_dev, timers=False)
         prof = _cabi.stop_profile()
-        g = prof.get("b200d_gemm_f16", {"calls": 0, "ms": 0.0, "work": 0.0})
+        g = {"calls": 0, "ms": 0.0, "work": 0.0}
+        for key, v in prof.items():
+            if key.startswith("b200d_gemm_f16"):
+                for f in g:
+                    g[f] += v[f]
         peaks = _peaks()
         gemm_tflops = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         roofline = {
@@ -196,7 +200,9 @@ def run_b200(args):
             "share_of_step": round(g["ms"] / (dev_ms / args.steps), 3),
             "step_titanet_tflops": round(flops / (stage_ms.get("embed", float("nan")) * 1e-3) / 1e12, 1),
         }
-        kernels = {k: {"calls": v["calls"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        kernels = {k: ({"calls": v["calls"], "ms": round(v["ms"], 3)} if not v["work"] else
+                       {"calls": v["calls"], "ms": round(v["ms"], 3), "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)})
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         hours = seconds / 3600.0
         value = world * hours * args.steps / (dev_ms * 1e-3)
         e2e_val = world * hours * args.steps / (e2e_ms * 1e-3)

@@ -106,9 +106,9 @@ typedef struct b200d_gemm_epilogue {
   const float* shift;     /* [N]  (TDNN) */
   const float* rowvec;    /* [M / rows_per_seg][N] (SE_RES: sigmoid gate; TDNN: per-segment bias) */
   const void* aux16;      /* __half [M][ldo]  (SE_RES main branch) */
-  /* CHEB: out32 = ca * (deg[m] * x32[m][n] - acc) + cb * x32[m][n] + cc * xprev32[m][n];
-   *       and, when vt != NULL, the 3-way bf16 split [hi | mid | lo] of out32, transposed, into
-   *       vt [3*bpad][ldvt] (bpad = 32 for N == 128, 64 for N == 256): the W operand of the next step. */
+  /* CHEB: out32 = ca * (deg[m] * x32[m][c] - (A V)[m][c]) + cb * x32[m][c] + cc * xprev32[m][c] for the b = N / 4
+   *       block columns c; W (and, when vt != NULL, the output vt for the next step) is the 3-way bf16 split of V^T
+   *       laid out per 32 block columns as a 128-row tile [hi | mid | lo | pad]: vt [N][ldvt], N = 128 or 256.   */
   const float* deg;       /* [M] */
   const float* x32;       /* [M][ldx] */
   const float* xprev32;   /* [M][ldx] or NULL */
@@ -213,7 +213,8 @@ int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, int32_t ld,
  * returns Q = S R^-1 in evecs with (Y Q)^T (Y Q) = I for g = Y^T Y (CholQR).                       */
 int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream);
 /* y[n][b] = x[n][b] * q[b][b] (q NULL: y = x; y may alias x or be NULL); when vt_bf16 != NULL also the
- * 3-way bf16 split [hi | mid | lo] of y^T into vt_bf16 [3*b][ldvt]: the W operand of the next CHEB GEMM. */
+ * 3-way bf16 split of y^T into vt_bf16 [4*b][ldvt] (per 32 columns a 128-row tile [hi | mid | lo | pad]):
+ * the W operand of the next CHEB GEMM.                                                                   */
 int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y, void* vt_bf16, int32_t ldvt,
                     void* stream);
 /* out[j] = sum_r (w[r][j] - theta[j] * x[r][j])^2 : squared residual norms of the Ritz pairs.       */

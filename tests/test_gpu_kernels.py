@@ -10,6 +10,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _unsplit(vt, b, n):
+    """[4b, ldvt] bf16 tiles [hi | mid | lo | pad] per 32 columns -> float32 [n, b]"""
+    cols = []
+    for t in range(b // 32):
+        base = t * 128
+        cols.append(vt[base : base + 32, :n].float() + vt[base + 32 : base + 64, :n].float() + vt[base + 64 : base + 96, :n].float())
+    return torch.cat(cols, dim=0).t()
+
+
 def _lap_batch(n, batch, seed):
     g = torch.Generator().manual_seed(seed)
     mats = []
@@ -135,7 +144,7 @@ def test_gram_smalleig_rightmul_resid(dev, n, b):
     eye = xo.double().t() @ xo.double()
     assert (eye - torch.eye(b, device=dev, dtype=torch.float64)).abs().max().item() < 5e-5
     assert (xo.double() - x.double() @ Q.double()).abs().max().item() < 1e-5
-    rec = (vt[:b, :n].float() + vt[b : 2 * b, :n].float() + vt[2 * b : 3 * b, :n].float()).t()
+    rec = _unsplit(vt, b, n)
     assert (rec - xo).abs().max().item() <= 1e-7 * xo.abs().max().item() + 1e-9
     # symmetric eigen-decomposition
     S = torch.randn(b, b, generator=g)
@@ -184,7 +193,7 @@ def test_cheb_gemm_step(dev, n, b):
     err = (out.double() - want).abs().max().item()
     print(f"cheb step n={n} b={b}: max err {err:.3e} (max |want| {want.abs().max().item():.2f})")
     assert err <= 2e-5 * want.abs().max().item()
-    rec = (vt_out[:b, :n].float() + vt_out[b : 2 * b, :n].float() + vt_out[2 * b : 3 * b, :n].float()).t()
+    rec = _unsplit(vt_out, b, n)
     assert (rec - out).abs().max().item() <= 1e-6 * out.abs().max().item()
 
 

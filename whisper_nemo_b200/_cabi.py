@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200d.so")
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_SE_RES, EPI_TDNN, EPI_BIAS_F32, EPI_CHEB, EPI_SIGMOID_F32 = range(7)
+_EPI_NAMES = ["bias", "bias_relu", "se_res", "tdnn", "bias_f32", "cheb", "sigmoid_f32"]
 
 
 class GemmEpilogue(Structure):
@@ -159,8 +160,13 @@ def call(name, *args):
         e0.record()
         rc = fn(*args)
         e1.record()
-        work = 2.0 * args[4] * args[5] * args[6] if name == "b200d_gemm_f16" else 0.0
-        _profile.setdefault(name, []).append((e0, e1, work))
+        work, key = 0.0, name
+        if name == "b200d_gemm_f16":
+            work = 2.0 * args[4] * args[5] * args[6]
+            key = f"{name}[{_EPI_NAMES[args[9]._obj.mode]}]"
+        elif name == "b200d_small_eig":
+            key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"
+        _profile.setdefault(key, []).append((e0, e1, work))
     else:
         rc = fn(*args)
     launch_count += KERNELS_PER_CALL.get(name, 1)

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(1024) bisect_kernel(const float* __restrict__ 
   for (int w = warp; w < wanted; w += nwarps) {
     const int k = (w < n_low) ? w : (n - 1);  // 0-based index of the eigenvalue, ascending
     double lo = glo, hi = ghi;                // count(lo) <= k < count(hi)
-    for (int round = 0; round < 10; ++round) {
+    for (int round = 0; round < 7; ++round) {  // 33^7 = 4e10: below fp32 resolution of the Gershgorin width
       const double step = (hi - lo) / 33.0;
       const double x = lo + step * (lane + 1);
       const int cnt = sturm_count(s_d, s_e2, n, x, tiny);

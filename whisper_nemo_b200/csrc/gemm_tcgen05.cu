@@ -15,6 +15,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace b200d {
@@ -202,8 +203,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   }
 }
 
-// Chebyshev epilogue: the W operand holds V^T split into three bf16 parts [hi | mid | lo], each
-// `bpad` columns wide, so acc columns (c, bpad + c, 2*bpad + c) sum to (A V)[row][c] at ~fp32 accuracy.
+// Chebyshev epilogue: the W operand holds V^T split into three bf16 parts, 32 block columns per 128-row tile as
+// [hi | mid | lo | pad], so acc columns (c, 32 + c, 64 + c) of tile t sum to (A V)[row][32 t + c] at ~fp32 accuracy.
 __device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
   h = __float2bfloat16_rn(v);
   float r = v - __bfloat162float(h);
@@ -311,35 +312,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
       if constexpr (MODE == B200D_EPI_CHEB) {
+        // every 128-wide N tile carries 32 columns of the block as [hi | mid | lo | pad]: a b = 64 block is two tiles,
+        // which doubles the CTAs of a launch whose M alone (N_nodes / 128 tiles) cannot fill 148 SMs
         const b200d_gemm_epilogue& e = p.epi;
-        const int bpad = BLOCK_N == 256 ? 64 : 32;
-        for (int c0 = 0; c0 < bpad; c0 += 32) {
-          uint32_t r0[32], r1[32], r2[32];
-          tmem_ld32(t_row + c0, r0);
-          tmem_ld32(t_row + bpad + c0, r1);
-          tmem_ld32(t_row + 2 * bpad + c0, r2);
-          tmem_ld_wait();
-          if (row < p.M) {
-            const float dg = __ldg(e.deg + row);
-            const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + c0;
-            const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + c0 : nullptr;
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c0;
-            __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
+        constexpr int bpad = 32;
+        const int cb = n_blk * bpad;  // first block column of this tile
+        uint32_t r0[32], r1[32], r2[32];
+        tmem_ld32(t_row, r0);
+        tmem_ld32(t_row + bpad, r1);
+        tmem_ld32(t_row + 2 * bpad, r2);
+        tmem_ld_wait();
+        if (row < p.M) {
+          const float dg = __ldg(e.deg + row);
+          const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + cb;
+          const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + cb : nullptr;
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + cb;
+          __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
-              const float xv = x[j];
-              float y = e.ca * (dg * xv - av) + e.cb * xv;
-              if (xp) y += e.cc * xp[j];
-              o[j] = y;
-              if (vh) {
-                __nv_bfloat16 h, m, l;
-                split3_bf16(y, h, m, l);
-                const size_t col = c0 + j;
-                vh[(col) * e.ldvt + row] = h;
-                vh[(bpad + col) * e.ldvt + row] = m;
-                vh[(2 * bpad + col) * e.ldvt + row] = l;
-              }
+          for (int j = 0; j < 32; ++j) {
+            const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+            const float xv = x[j];
+            float y = e.ca * (dg * xv - av) + e.cb * xv;
+            if (xp) y += e.cc * xp[j];
+            o[j] = y;
+            if (vh) {
+              __nv_bfloat16 h, m, l;
+              split3_bf16(y, h, m, l);
+              const size_t vrow = static_cast<size_t>(n_blk) * 128 + j;
+              vh[(vrow) * e.ldvt + row] = h;
+              vh[(vrow + bpad) * e.ldvt + row] = m;
+              vh[(vrow + 2 * bpad) * e.ldvt + row] = l;
             }
           }
         }
@@ -369,6 +371,186 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ 2-CTA kernel
+// CTA-pair variant (cta_group::2) for the large pointwise convs.  The 1-CTA kernel above moves 48 KB from L2 per
+// 128x256x64 MMA block and saturates the L2 -> SM path (~6.3 KB/clk chip-wide) at about half of the tensor peak.
+// Here the two CTAs of a cluster (the two SMs of a TPC) share one 256 x 256 output tile: each loads only ITS 128
+// rows of A and ITS 128 rows of W (32 KB per block instead of 48 KB), the leader issues tcgen05.mma.cta_group::2
+// with M = 256 reading both halves, and each CTA's TMEM ends up with its own 128 accumulator rows.
+//   TMA loads of both CTAs signal the LEADER's full barrier (peer bit cleared in the barrier address);
+//   tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs;
+//   the epilogue warps of both CTAs arrive on the leader's tmem-empty barrier (remote arrive for the peer).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+constexpr int B2_BYTES = 128 * BLOCK_K * 2;             // this CTA's half of the 256-row W tile
+constexpr int STAGES2 = 6;
+constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_BYTES + B2_BYTES) + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the even CTA's copy of `bar`
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES2 * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES2 * B2_BYTES);
+  uint64_t* empty = full + STAGES2;
+  uint64_t* tfull = empty + STAGES2;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 2);   // leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty[i], 1);  // multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);   // multicast tcgen05.commit
+      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (leader's copy only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_n = p.N / BN;
+  const int total = num_m * num_n;
+  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cid; tile < total; tile += ncl) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int row_a = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int row_b = n_blk * BN + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, &full[stage], kb * BLOCK_K, row_a);
+          tma_load_2d_2sm(sB + stage * B2_BYTES, &tmB, &full[stage], kb * BLOCK_K, row_b);
+          if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B2_BYTES));
+          else mbar_arrive_leader(&full[stage]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // D fp32, A/B fp16 K-major, N = 256, M = 256 (both CTAs)
+      constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((2 * BLOCK_M) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cid; tile < total; tile += ncl) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
+          const uint64_t b_desc = make_sw128_desc(smem_u32(sB + stage * B2_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cid; tile < total; tile += ncl) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float acc_f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
+          epilogue_chunk<MODE>(p, row, n_blk * BN + c * 32, acc_f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_leader(&tempty[acc]);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -425,6 +607,33 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return B200D_OK;
 }
 
+template <int MODE>
+static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_2cta_kernel<MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (p.N / 256);
+  int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  kern<<<2 * pairs, 256, SMEM2_BYTES, stream>>>(ta, tb, p);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+static int dispatch_mode_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  switch (p.epi.mode) {
+    case B200D_EPI_BIAS: return launch_2cta<B200D_EPI_BIAS>(ta, tb, p, s);
+    case B200D_EPI_BIAS_RELU: return launch_2cta<B200D_EPI_BIAS_RELU>(ta, tb, p, s);
+    case B200D_EPI_SE_RES: return launch_2cta<B200D_EPI_SE_RES>(ta, tb, p, s);
+    case B200D_EPI_TDNN: return launch_2cta<B200D_EPI_TDNN>(ta, tb, p, s);
+    case B200D_EPI_BIAS_F32: return launch_2cta<B200D_EPI_BIAS_F32>(ta, tb, p, s);
+    case B200D_EPI_SIGMOID_F32: return launch_2cta<B200D_EPI_SIGMOID_F32>(ta, tb, p, s);
+  }
+  return set_error(B200D_EINVAL, "%s: unknown epilogue mode%s", "b200d_gemm_f16");
+}
+
 template <int BLOCK_N>
 static int dispatch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
   switch (p.epi.mode) {
@@ -453,7 +662,7 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const int mode = epi->mode;
   if (mode == B200D_EPI_CHEB) {
-    B200D_CHECK_ARG(N == 128 || N == 256);
+    B200D_CHECK_ARG(N == 128 || N == 256);  // block of 32 or 64 vectors: one or two [hi | mid | lo | pad] tiles
     B200D_CHECK_ARG(epi->deg && epi->x32);
     B200D_CHECK_ARG(epi->vt == nullptr || epi->ldvt >= M);
   } else {
@@ -463,14 +672,19 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
     if (mode == B200D_EPI_BIAS || mode == B200D_EPI_BIAS_RELU || mode == B200D_EPI_BIAS_F32) B200D_CHECK_ARG(epi->bias);
   }
   const bool bf16 = mode == B200D_EPI_CHEB;
-  const int block_n = (N % 256 == 0) ? 256 : 128;
+  const int block_n = (N % 256 == 0 && mode != B200D_EPI_CHEB) ? 256 : 128;
+  // CTA-pair kernel when there is at least one 256 x 256 tile per TPC (the large pointwise convs)
+  static const bool allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
+  const bool use_2cta = allow_2cta && mode != B200D_EPI_CHEB && block_n == 256 &&
+                        static_cast<long long>((M + 255) / 256) * (N / 256) >= kNumSMs / 2;
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&tb, W, bf16, N, K, ldw, block_n);
+  rc = make_map(&tb, W, bf16, N, K, ldw, use_2cta ? 128 : block_n);
   if (rc) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.epi = *epi;
+  if (use_2cta) return dispatch_mode_2cta(ta, tb, p, as_stream(stream));
   if (block_n == 256) return dispatch_mode<256>(ta, tb, p, as_stream(stream));
   return dispatch_mode<128>(ta, tb, p, as_stream(stream));
 }

@@ -203,9 +203,9 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
         V[r * b + q] = s * vp + c * vq;
       }
       __syncthreads();
-      // rows: A <- J^T A
+      // rows: A <- J^T A  (a warp walks 32 consecutive columns of one pair: conflict-free shared-memory rows)
       for (int e = tid; e < b * half; e += nth) {
-        const int col = e / half, k = e - col * half;
+        const int k = e / b, col = e - k * b;
         const int p = s_p[k], q = s_q[k];
         const double c = s_c[k], s = s_s[k];
         const double ap = A[p * b + col], aq = A[q * b + col];
@@ -243,7 +243,8 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16&
   l = __float2bfloat16_rn(r);
 }
 
-// y[n][b] = x[n][b] q[b][b]  (y may alias x).  vt (optional): bf16 [3*b][ldvt], rows [hi | mid | lo] of y^T.
+// y[n][b] = x[n][b] q[b][b]  (y may alias x).  vt (optional): bf16 [4*b][ldvt]: per 32 columns of y a 128-row tile
+// [hi | mid | lo | pad] of y^T (the W operand layout of the CHEB GEMM).
 // q == nullptr: y = x (only the split is produced).
 template <int B>
 __global__ void __launch_bounds__(256) right_mul_kernel(const float* __restrict__ x, int n, int ld, const float* __restrict__ q,
@@ -291,9 +292,10 @@ __global__ void __launch_bounds__(256) right_mul_kernel(const float* __restrict_
       if (row0 + rr < n) {
         __nv_bfloat16 h, m, l;
         split3(so[rr][col], h, m, l);
-        vt[static_cast<size_t>(col) * ldvt + row0 + rr] = h;
-        vt[static_cast<size_t>(B + col) * ldvt + row0 + rr] = m;
-        vt[static_cast<size_t>(2 * B + col) * ldvt + row0 + rr] = l;
+        const size_t vrow = static_cast<size_t>(col >> 5) * 128 + (col & 31);  // 32 columns per [hi | mid | lo | pad] tile
+        vt[vrow * ldvt + row0 + rr] = h;
+        vt[(vrow + 32) * ldvt + row0 + rr] = m;
+        vt[(vrow + 64) * ldvt + row0 + rr] = l;
       }
     }
   }

@@ -24,89 +24,128 @@ __device__ __forceinline__ void store4h(__half* p, const float (&v)[4]) {
 }
 
 // ------------------------------------------------------------------------------------ depthwise
-// Thread = 4 channels x TT consecutive output frames of one segment; the k x 4 filter taps live in
-// registers, each input vector is loaded once and feeds up to k outputs.
-constexpr int kDwTT = 8;
+// Thread = 2 channels x a strip of kDwTT consecutive output frames of one window.  All kDwTT + k - 1 input rows of the
+// strip are requested up front (independent 4-byte loads, a warp touches 128 contiguous bytes per row), so the DRAM /
+// L2 latency is paid once per strip instead of once per row; the k x 2 filter taps and a sliding window of the last
+// k converted rows live in registers (fully unrolled: the ring index is a compile-time constant).  Every input row is
+// loaded once per strip (read amplification (TT + k - 1) / TT, the halo from L1/L2) and the output is written once.
+constexpr int kDwTT = 32;
 
 template <int KS>
-__global__ void __launch_bounds__(256) depthwise_kernel(const __half* __restrict__ x, __half* __restrict__ y,
-                                                        const float* __restrict__ w, int n_seg, int T, int C, int strips) {
+__global__ void __launch_bounds__(256, 2) depthwise_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                           const float* __restrict__ w, int n_seg, int T, int C, int strips) {
   constexpr int PAD = KS / 2;
-  const int cg = blockIdx.y * blockDim.x + threadIdx.x;  // channel group of 4
-  if (cg * 4 >= C) return;
+  constexpr int ROWS = kDwTT + KS - 1;
+  const int cp = blockIdx.y * blockDim.x + threadIdx.x;  // channel pair
+  if (cp * 2 >= C) return;
   const int strip = blockIdx.x;
   const int seg = strip / strips;
   const int t0 = (strip - seg * strips) * kDwTT;
-  const int c = cg * 4;
-  float wt[KS][4];
-#pragma unroll
-  for (int j = 0; j < KS; ++j) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(j) * C + c));
-    wt[j][0] = f.x; wt[j][1] = f.y; wt[j][2] = f.z; wt[j][3] = f.w;
-  }
-  float acc[kDwTT][4];
-#pragma unroll
-  for (int i = 0; i < kDwTT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const int c = cp * 2;
   const __half* xs = x + (static_cast<size_t>(seg) * T) * C + c;
+  __half* ys = y + (static_cast<size_t>(seg) * T) * C + c;
+  uint32_t raw[ROWS];
 #pragma unroll
-  for (int r = 0; r < kDwTT + KS - 1; ++r) {
-    const int t = t0 + r - PAD;
-    if (t >= 0 && t < T) {
-      float v[4];
-      load4h(xs + static_cast<size_t>(t) * C, v);
+  for (int r = 0; r < ROWS; ++r) {
+    const int t = t0 - PAD + r;
+    raw[r] = (t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint32_t*>(xs + static_cast<size_t>(t) * C)) : 0u;
+  }
+  float2 wt[KS];
 #pragma unroll
-      for (int tt = 0; tt < kDwTT; ++tt) {
-        const int j = r - tt;  // tap index: input t = (t0 + tt) + j - PAD
-        if (j >= 0 && j < KS) {
+  for (int j = 0; j < KS; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(j) * C + c));
+  auto cvt = [](uint32_t u) -> float2 { return __half22float2(*reinterpret_cast<const __half2*>(&u)); };
+  float2 win[KS];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[tt][q] = fmaf(wt[j][q], v[q], acc[tt][q]);
-        }
+  for (int j = 0; j < KS - 1; ++j) win[j] = cvt(raw[j]);
+#pragma unroll
+  for (int tt = 0; tt < kDwTT; ++tt) {
+    win[(tt + KS - 1) % KS] = cvt(raw[tt + KS - 1]);
+    if (t0 + tt < T) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const float2 v = win[(tt + j) % KS];
+        acc.x = fmaf(wt[j].x, v.x, acc.x);
+        acc.y = fmaf(wt[j].y, v.y, acc.y);
       }
+      *reinterpret_cast<__half2*>(ys + static_cast<size_t>(t0 + tt) * C) = __floats2half2_rn(acc.x, acc.y);
     }
   }
-  __half* ys = y + (static_cast<size_t>(seg) * T) * C + c;
-#pragma unroll
-  for (int tt = 0; tt < kDwTT; ++tt)
-    if (t0 + tt < T) store4h(ys + static_cast<size_t>(t0 + tt) * C, acc[tt]);
 }
 
 // ------------------------------------------------------------------------------------ time statistics
-// One block per segment, thread = 4 channels.  WITH_STD == false: mean only (SqueezeExcite pool).
-// WITH_STD == true: [mean | sqrt(clamp(mean((x-mean)^2), 1e-10))] (AttentivePoolLayer context).
+// Block = (window, 256-channel chunk): 64 channel groups of 4 x kTsSlices time slices; each thread reduces the rows
+// t == slice (mod kTsSlices), the slices are combined through shared memory in a fixed order.
+// WITH_STD == false: mean only (SqueezeExcite pool).
+// WITH_STD == true: [mean | sqrt(clamp(mean((x-mean)^2), 1e-10))] (AttentivePoolLayer context), exact two-pass form.
+constexpr int kTsSlices = 4;
+
 template <bool WITH_STD>
-__global__ void time_stats_kernel(const __half* __restrict__ x, int T, int C, __half* __restrict__ out16) {
+__global__ void __launch_bounds__(64 * kTsSlices) time_stats_kernel(const __half* __restrict__ x, int T, int C, __half* __restrict__ out16) {
+  __shared__ float s_part[kTsSlices][64][4];
+  __shared__ float s_mean[64][4];
   const int seg = blockIdx.x;
-  const int c = threadIdx.x * 4;
-  if (c >= C) return;
+  const int g = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = (blockIdx.y * 64 + g) * 4;
+  const bool active = c < C;
   const __half* xs = x + static_cast<size_t>(seg) * T * C + c;
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t = 0; t < T; ++t) {
-    float v[4];
-    load4h(xs + static_cast<size_t>(t) * C, v);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) s[q] += v[q];
-  }
-  const float inv = 1.f / static_cast<float>(T);
-  float mean[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) mean[q] = s[q] * inv;
-  const int ld = WITH_STD ? 2 * C : C;
-  store4h(out16 + static_cast<size_t>(seg) * ld + c, mean);
-  if constexpr (WITH_STD) {
-    float ss[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < T; ++t) {
+  if (active) {
+    for (int t = slice; t < T; t += kTsSlices) {
       float v[4];
       load4h(xs + static_cast<size_t>(t) * C, v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float d = v[q] - mean[q];
-        ss[q] = fmaf(d, d, ss[q]);
+      for (int q = 0; q < 4; ++q) s[q] += v[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s_part[slice][g][q] = s[q];
+  __syncthreads();
+  const float inv = 1.f / static_cast<float>(T);
+  const int ld = WITH_STD ? 2 * C : C;
+  if (slice == 0) {
+    float mean[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float tot = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < kTsSlices; ++sl) tot += s_part[sl][g][q];
+      mean[q] = tot * inv;
+      s_mean[g][q] = mean[q];
+    }
+    if (active) store4h(out16 + static_cast<size_t>(seg) * ld + c, mean);
+  }
+  if constexpr (WITH_STD) {
+    __syncthreads();
+    float mean[4], ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mean[q] = s_mean[g][q];
+    if (active) {
+      for (int t = slice; t < T; t += kTsSlices) {
+        float v[4];
+        load4h(xs + static_cast<size_t>(t) * C, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float d = v[q] - mean[q];
+          ss[q] = fmaf(d, d, ss[q]);
+        }
       }
     }
-    float sd[4];
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sd[q] = sqrtf(fmaxf(ss[q] * inv, 1e-10f));
-    store4h(out16 + static_cast<size_t>(seg) * ld + C + c, sd);
+    for (int q = 0; q < 4; ++q) s_part[slice][g][q] = ss[q];
+    __syncthreads();
+    if (slice == 0 && active) {
+      float sd[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float tot = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < kTsSlices; ++sl) tot += s_part[sl][g][q];
+        sd[q] = sqrtf(fmaxf(tot * inv, 1e-10f));
+      }
+      store4h(out16 + static_cast<size_t>(seg) * ld + C + c, sd);
+    }
   }
 }
 
@@ -129,41 +168,62 @@ __global__ void se_apply_relu_kernel(const __half* __restrict__ x, const float* 
 
 // ------------------------------------------------------------------------------------ attentive pooling
 // alpha = softmax over time of e (per channel); mu = sum alpha x; sg = sqrt(clamp(sum alpha (x - mu)^2, 1e-10)).
-// Single pass with an online (running-max) softmax; the second moment is accumulated around the
-// running mean-free form and combined at the end in fp32.
-__global__ void attn_pool_kernel(const __half* __restrict__ x, const __half* __restrict__ e, int T, int C, __half* __restrict__ out16) {
+// Single pass with an online (running-max) softmax per time slice; the kTsSlices partial states (max, Z, S1, S2) are
+// merged in a fixed order through shared memory.
+__global__ void __launch_bounds__(64 * kTsSlices) attn_pool_kernel(const __half* __restrict__ x, const __half* __restrict__ e, int T, int C,
+                                                                   __half* __restrict__ out16) {
+  __shared__ float s_m[kTsSlices][64][4], s_z[kTsSlices][64][4], s_1[kTsSlices][64][4], s_2[kTsSlices][64][4];
   const int seg = blockIdx.x;
-  const int c = threadIdx.x * 4;
-  if (c >= C) return;
+  const int g = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = (blockIdx.y * 64 + g) * 4;
+  const bool active = c < C;
   const __half* xs = x + static_cast<size_t>(seg) * T * C + c;
   const __half* es = e + static_cast<size_t>(seg) * T * C + c;
   float m[4], z[4], s1[4], s2[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; z[q] = 0.f; s1[q] = 0.f; s2[q] = 0.f; }
-  for (int t = 0; t < T; ++t) {
-    float xv[4], ev[4];
-    load4h(xs + static_cast<size_t>(t) * C, xv);
-    load4h(es + static_cast<size_t>(t) * C, ev);
+  if (active) {
+    for (int t = slice; t < T; t += kTsSlices) {
+      float xv[4], ev[4];
+      load4h(xs + static_cast<size_t>(t) * C, xv);
+      load4h(es + static_cast<size_t>(t) * C, ev);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float mn = fmaxf(m[q], ev[q]);
-      const float r = __expf(m[q] - mn);  // exp(-inf) = 0 on the first frame
-      const float wgt = __expf(ev[q] - mn);
-      z[q] = z[q] * r + wgt;
-      s1[q] = s1[q] * r + wgt * xv[q];
-      s2[q] = s2[q] * r + wgt * xv[q] * xv[q];
-      m[q] = mn;
+      for (int q = 0; q < 4; ++q) {
+        const float mn = fmaxf(m[q], ev[q]);
+        const float r = __expf(m[q] - mn);  // exp(-inf) = 0 on the first frame
+        const float wgt = __expf(ev[q] - mn);
+        z[q] = z[q] * r + wgt;
+        s1[q] = s1[q] * r + wgt * xv[q];
+        s2[q] = s2[q] * r + wgt * xv[q] * xv[q];
+        m[q] = mn;
+      }
     }
   }
-  float mu[4], sg[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float iz = 1.f / z[q];
-    mu[q] = s1[q] * iz;
-    sg[q] = sqrtf(fmaxf(s2[q] * iz - mu[q] * mu[q], 1e-10f));
+  for (int q = 0; q < 4; ++q) { s_m[slice][g][q] = m[q]; s_z[slice][g][q] = z[q]; s_1[slice][g][q] = s1[q]; s_2[slice][g][q] = s2[q]; }
+  __syncthreads();
+  if (slice == 0 && active) {
+    float mu[4], sg[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float mm = s_m[0][g][q];
+#pragma unroll
+      for (int sl = 1; sl < kTsSlices; ++sl) mm = fmaxf(mm, s_m[sl][g][q]);
+      float zz = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < kTsSlices; ++sl) {
+        const float r = (s_m[sl][g][q] == -INFINITY) ? 0.f : __expf(s_m[sl][g][q] - mm);
+        zz += s_z[sl][g][q] * r;
+        a1 += s_1[sl][g][q] * r;
+        a2 += s_2[sl][g][q] * r;
+      }
+      const float iz = 1.f / zz;
+      mu[q] = a1 * iz;
+      sg[q] = sqrtf(fmaxf(a2 * iz - mu[q] * mu[q], 1e-10f));
+    }
+    store4h(out16 + static_cast<size_t>(seg) * 2 * C + c, mu);
+    store4h(out16 + static_cast<size_t>(seg) * 2 * C + C + c, sg);
   }
-  store4h(out16 + static_cast<size_t>(seg) * 2 * C + c, mu);
-  store4h(out16 + static_cast<size_t>(seg) * 2 * C + C + c, sg);
 }
 
 }  // namespace b200d
@@ -175,9 +235,9 @@ extern "C" int b200d_depthwise_conv(const void* x, void* y, const float* w, int3
   B200D_CHECK_ARG(x && y && w && x != y);
   B200D_CHECK_ARG(n_seg > 0 && T > 0 && C > 0 && C % 4 == 0);
   const int strips = (T + kDwTT - 1) / kDwTT;
-  const int threads = (C / 4) < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
+  const int threads = (C / 2) < 256 ? ((C / 2 + 31) / 32) * 32 : 256;
   B200D_CHECK_ARG(static_cast<long long>(n_seg) * strips < 2147483647LL);
-  dim3 grid(static_cast<unsigned>(n_seg) * strips, (C / 4 + threads - 1) / threads);
+  dim3 grid(static_cast<unsigned>(n_seg) * strips, (C / 2 + threads - 1) / threads);
   const __half* xi = reinterpret_cast<const __half*>(x);
   __half* yo = reinterpret_cast<__half*>(y);
   switch (ksize) {
@@ -192,12 +252,13 @@ extern "C" int b200d_depthwise_conv(const void* x, void* y, const float* w, int3
 }
 
 extern "C" int b200d_time_stats(const void* x, int32_t n_seg, int32_t T, int32_t C, int32_t with_std, void* out16, void* stream) {
-  B200D_CHECK_ARG(x && out16 && n_seg > 0 && T > 0 && C % 4 == 0 && C / 4 <= 1024);
-  const int threads = ((C / 4 + 31) / 32) * 32;
+  B200D_CHECK_ARG(x && out16 && n_seg > 0 && T > 0 && C % 4 == 0);
+  const dim3 grid(n_seg, (C / 4 + 63) / 64);
+  const int threads = 64 * kTsSlices;
   if (with_std)
-    time_stats_kernel<true><<<n_seg, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
+    time_stats_kernel<true><<<grid, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
   else
-    time_stats_kernel<false><<<n_seg, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
+    time_stats_kernel<false><<<grid, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
@@ -212,9 +273,8 @@ extern "C" int b200d_se_apply_relu(const void* x, const float* gate, void* y, in
 }
 
 extern "C" int b200d_attn_pool(const void* x, const void* e, int32_t n_seg, int32_t T, int32_t C, void* out16, void* stream) {
-  B200D_CHECK_ARG(x && e && out16 && n_seg > 0 && T > 0 && C % 4 == 0 && C / 4 <= 1024);
-  const int threads = ((C / 4 + 31) / 32) * 32;
-  attn_pool_kernel<<<n_seg, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(e), T, C,
+  B200D_CHECK_ARG(x && e && out16 && n_seg > 0 && T > 0 && C % 4 == 0);
+  attn_pool_kernel<<<dim3(n_seg, (C / 4 + 63) / 64), 64 * kTsSlices, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(e), T, C,
                                                             reinterpret_cast<__half*>(out16));
   B200D_CHECK_LAUNCH();
   return B200D_OK;
