@@ -34,7 +34,7 @@ __device__ __forceinline__ float block_sum_512(float v, float* s_red) {
 }
 
 // a [batch][n][n] (destroyed), d [batch][n], e [batch][n], pbuf [batch][2][n]
-__global__ void __launch_bounds__(kTriThreads, 1) tridiag_kernel(float* __restrict__ a, int n, int cpm, float* __restrict__ d,
+__global__ void __launch_bounds__(kTriThreads, 2) tridiag_kernel(float* __restrict__ a, int n, int cpm, float* __restrict__ d,
                                                                   float* __restrict__ e, float* __restrict__ pbuf) {
   extern __shared__ float sm[];
   float* s_vp = sm;           // v' (previous step's Householder vector), indexed by absolute row
@@ -91,13 +91,25 @@ __global__ void __launch_bounds__(kTriThreads, 1) tridiag_kernel(float* __restri
     for (int i = j + 1 + slot; i < n; i += slots) {
       float* row = A + static_cast<size_t>(i) * n;
       const float vpi = s_vp[i], wpi = s_wp[i];
-      float acc = 0.f;
-      for (int k = j + 1 + lane; k < n; k += 32) {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      int k = j + 1 + lane;
+      // four independent 128-byte requests in flight per warp: the pass is L2-latency bound, not bandwidth bound
+      for (; k + 96 < n; k += 128) {
+        const float a0 = __ldcg(row + k), a1 = __ldcg(row + k + 32), a2 = __ldcg(row + k + 64), a3 = __ldcg(row + k + 96);
+        const float v0 = a0 - vpi * s_wp[k] - wpi * s_vp[k];
+        const float v1 = a1 - vpi * s_wp[k + 32] - wpi * s_vp[k + 32];
+        const float v2 = a2 - vpi * s_wp[k + 64] - wpi * s_vp[k + 64];
+        const float v3 = a3 - vpi * s_wp[k + 96] - wpi * s_vp[k + 96];
+        __stcg(row + k, v0); __stcg(row + k + 32, v1); __stcg(row + k + 64, v2); __stcg(row + k + 96, v3);
+        acc0 = fmaf(v0, s_v[k], acc0); acc1 = fmaf(v1, s_v[k + 32], acc1);
+        acc2 = fmaf(v2, s_v[k + 64], acc2); acc3 = fmaf(v3, s_v[k + 96], acc3);
+      }
+      for (; k < n; k += 32) {
         const float v = __ldcg(row + k) - vpi * s_wp[k] - wpi * s_vp[k];
         __stcg(row + k, v);
-        acc = fmaf(v, s_v[k], acc);
+        acc0 = fmaf(v, s_v[k], acc0);
       }
-      acc = warp_sum(acc);
+      const float acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
       if (lane == 0) pw[i] = beta * acc;
     }
     __threadfence();
@@ -200,8 +212,8 @@ __global__ void __launch_bounds__(1024) bisect_kernel(const float* __restrict__ 
 
 using namespace b200d;
 
-static int tridiag_cpm(int batch) {
-  int cpm = kNumSMs / batch;
+static int tridiag_cpm(int batch, int blocks_per_sm) {
+  int cpm = (kNumSMs * blocks_per_sm) / batch;  // CTAs per matrix; the whole grid must be co-resident (cooperative launch)
   if (cpm < 1) cpm = 1;
   if (cpm > 16) cpm = 16;
   return cpm;
@@ -216,13 +228,13 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
                                      void* stream) {
   B200D_CHECK_ARG(a && evals && ws);
   B200D_CHECK_ARG(batch > 0 && batch <= kNumSMs && n >= 2 && n <= kMaxEigN && n_low >= 1 && n_low <= n);
+  static int blocks_per_sm = 0;
   if (ws_bytes < b200d_eigvals_workspace_bytes(batch, n))
     return b200d::set_error(B200D_EWORKSPACE, "%s: workspace too small%s", "b200d_eigvals_batched");
   cudaStream_t s = as_stream(stream);
   float* d = reinterpret_cast<float*>(ws);
   float* e = d + static_cast<size_t>(batch) * n;
   float* pbuf = e + static_cast<size_t>(batch) * n;
-  int cpm = tridiag_cpm(batch);
   int n_arg = n;
   const size_t smem = static_cast<size_t>(4) * n * sizeof(float);
   static bool attr_set = false;
@@ -231,6 +243,12 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
     B200D_CHECK_CUDA(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxEigN * sizeof(double)));
     attr_set = true;
   }
+  if (blocks_per_sm == 0) {
+    int occ = 1;
+    B200D_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tridiag_kernel, kTriThreads, 4 * kMaxEigN * sizeof(float)));
+    blocks_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
+  }
+  int cpm = tridiag_cpm(batch, blocks_per_sm);
   void* args[] = {&a, &n_arg, &cpm, &d, &e, &pbuf};
   B200D_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tridiag_kernel), dim3(batch * cpm), dim3(kTriThreads), args, smem, s));
   const int wanted = n_low + 1;

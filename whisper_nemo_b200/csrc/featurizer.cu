@@ -20,8 +20,9 @@ constexpr int kWin = 400;
 constexpr int kWinOff = (kNFFT - kWin) / 2;  // 56: torch.stft centres the window inside n_fft
 constexpr int kMels = 80;
 constexpr int kBins = kNFFT / 2 + 1;  // 257
-constexpr int kFeatWarps = 8;
+constexpr int kFeatWarps = 32;  // the kernel is latency-bound: more resident warps per CTA, their FFT scratch in dynamic smem
 constexpr int kMaxFbNnz = 1024;
+constexpr int kWarpScratch = 512 + kBins + 3;  // floats: 256 complex spectrum + 257 power bins (+ pad)
 
 struct FeatParams {
   const float* wav;
@@ -41,13 +42,11 @@ struct FeatParams {
 };
 
 __global__ void __launch_bounds__(kFeatWarps * 32) featurize_kernel(const FeatParams p) {
-  extern __shared__ float logmel[];  // [T][80]
+  extern __shared__ float logmel[];  // [T][80] | per-warp spectrum scratch: kFeatWarps x (256 float2 + 260 float)
   __shared__ float2 s_tw[256];       // e^{-2 pi i k / 512}
   __shared__ float s_win[kWin];
   __shared__ float s_fbw[kMaxFbNnz];
   __shared__ int s_fbs[kMels], s_fbo[kMels + 1];
-  __shared__ float2 s_c[kFeatWarps][256];
-  __shared__ float s_p[kFeatWarps][kBins + 3];
   __shared__ float s_mean[kMels], s_inv[kMels];
 
   const int seg = blockIdx.x;
@@ -81,38 +80,79 @@ __global__ void __launch_bounds__(kFeatWarps * 32) featurize_kernel(const FeatPa
     return j == 0 ? x0 : x0 - 0.97f * x_at(j - 1);
   };
 
-  float2* cbuf = s_c[warp];
-  float* pbuf = s_p[warp];
+  float* scratch = logmel + ((p.T * kMels + 3) & ~3) + warp * kWarpScratch;
+  float2* cbuf = reinterpret_cast<float2*>(scratch);
+  float* pbuf = scratch + 512;
+  // 256-point complex FFT of z[n] = v[2n] + i v[2n+1] without shared-memory stages: n = lane + 32 j.
+  //   step 1  8-point DFT over j in registers                 A[k1]  = sum_j z[j] W8^(j k1)
+  //   step 2  twiddle                                          B[k1]  = A[k1] W256^(lane k1)
+  //   step 3  32-point DIF FFT across the lanes by shuffles    X[k1 + 8 k2], k2 = bitrev5(lane)
+  // lane-constant twiddles live in registers for the whole kernel.
+  float2 tw2[8];   // W256^(lane * k1)
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) {
+    float sn, cs;
+    sincospif(static_cast<float>(lane * k1) / 128.f, &sn, &cs);
+    tw2[k1] = make_float2(cs, -sn);
+  }
+  float2 tw3[5];   // stage twiddles of the cross-lane FFT: W32^((lane & (h-1)) * (16/h)), h = 16, 8, 4, 2, 1
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    const int h = 16 >> st;
+    float sn, cs;
+    sincospif(static_cast<float>((lane & (h - 1)) * (16 / h)) / 16.f, &sn, &cs);
+    tw3[st] = make_float2(cs, -sn);
+  }
+  const int k2 = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);
+  const bool tiled = len < F;
+  auto sample = [&](int j) -> float {  // pre-emphasised, reflect-padded signal at frame-relative position
+    if (!tiled) {
+      if (j < 0) j = -j;
+      if (j >= F) j = 2 * (F - 1) - j;
+      const float x0 = __ldg(src + j);
+      return j == 0 ? x0 : x0 - 0.97f * __ldg(src + j - 1);
+    }
+    return y_at(j);
+  };
   for (int t = warp; t < p.T; t += kFeatWarps) {
     const int base = t * kHop - kNFFT / 2;
-    // z[n] = v[2n] + i v[2n+1], stored bit-reversed for the in-place DIT FFT
+    float2 z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i0 = 2 * (lane + 32 * j), i1 = i0 + 1;
+      float v0 = 0.f, v1 = 0.f;
+      if (i0 >= kWinOff && i0 < kWinOff + kWin) v0 = s_win[i0 - kWinOff] * sample(base + i0);
+      if (i1 >= kWinOff && i1 < kWinOff + kWin) v1 = s_win[i1 - kWinOff] * sample(base + i1);
+      z[j] = make_float2(v0, v1);
+    }
+    // ---- step 1: 8-point DIF DFT in registers (outputs in bit-reversed order, undone by the index map below)
+    auto bf = [](float2& a, float2& b) { const float2 s = make_float2(a.x + b.x, a.y + b.y), d = make_float2(a.x - b.x, a.y - b.y); a = s; b = d; };
+    auto mul = [](float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); };
+    const float r2 = 0.70710678118654752f;
+    bf(z[0], z[4]); bf(z[1], z[5]); bf(z[2], z[6]); bf(z[3], z[7]);
+    z[5] = mul(z[5], make_float2(r2, -r2));      // W8^1
+    z[6] = make_float2(z[6].y, -z[6].x);         // W8^2 = -i
+    z[7] = mul(z[7], make_float2(-r2, -r2));     // W8^3
+    bf(z[0], z[2]); bf(z[1], z[3]); bf(z[4], z[6]); bf(z[5], z[7]);
+    z[3] = make_float2(z[3].y, -z[3].x);
+    z[7] = make_float2(z[7].y, -z[7].x);
+    bf(z[0], z[1]); bf(z[2], z[3]); bf(z[4], z[5]); bf(z[6], z[7]);
+    // z[q] now holds A[bitrev3(q)]
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int n = lane + 32 * q;
-      const int i0 = 2 * n, i1 = 2 * n + 1;
-      float v0 = 0.f, v1 = 0.f;
-      if (i0 >= kWinOff && i0 < kWinOff + kWin) v0 = s_win[i0 - kWinOff] * y_at(base + i0);
-      if (i1 >= kWinOff && i1 < kWinOff + kWin) v1 = s_win[i1 - kWinOff] * y_at(base + i1);
-      cbuf[__brev(static_cast<unsigned>(n)) >> 24] = make_float2(v0, v1);
+      const int k1 = ((q & 1) << 2) | (q & 2) | ((q >> 2) & 1);
+      float2 b = mul(z[q], tw2[k1]);
+      // ---- step 3: 32-point DIF FFT across lanes
+#pragma unroll
+      for (int st = 0; st < 5; ++st) {
+        const int h = 16 >> st;
+        const float ox = __shfl_xor_sync(0xffffffffu, b.x, h), oy = __shfl_xor_sync(0xffffffffu, b.y, h);
+        if (lane & h) b = mul(make_float2(ox - b.x, oy - b.y), tw3[st]);
+        else b = make_float2(b.x + ox, b.y + oy);
+      }
+      cbuf[k1 + 8 * k2] = b;
     }
     __syncwarp();
-#pragma unroll
-    for (int s = 1; s <= 8; ++s) {
-      const int half = 1 << (s - 1);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = lane + 32 * q;  // butterfly id 0..127
-        const int pos = j & (half - 1);
-        const int i0 = ((j >> (s - 1)) << s) + pos;
-        const int i1 = i0 + half;
-        const float2 w = s_tw[pos << (9 - s)];
-        const float2 a = cbuf[i0], b = cbuf[i1];
-        const float tr = w.x * b.x - w.y * b.y, ti = w.x * b.y + w.y * b.x;
-        cbuf[i0] = make_float2(a.x + tr, a.y + ti);
-        cbuf[i1] = make_float2(a.x - tr, a.y - ti);
-      }
-      __syncwarp();
-    }
     // real-FFT recombination: X[k] = E[k] + e^{-2 pi i k/512} O[k], power spectrum |X|^2
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
@@ -192,12 +232,12 @@ extern "C" int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* s
   p.fixed_len = fixed_len; p.T = fixed_len / kHop + 1;
   p.fb_start = fb_start; p.fb_off = fb_off; p.fb_w = fb_w; p.window = window;
   p.out16 = reinterpret_cast<__half*>(out_f16); p.ldo = ldo; p.out32 = out_f32;
-  const size_t smem = static_cast<size_t>(p.T) * kMels * sizeof(float);
-  B200D_CHECK_ARG(smem <= 180 * 1024);
+  const size_t smem = (((static_cast<size_t>(p.T) * kMels + 3) & ~static_cast<size_t>(3)) + static_cast<size_t>(kFeatWarps) * kWarpScratch) * sizeof(float);
+  B200D_CHECK_ARG(smem <= 215 * 1024);  // T <= 362 frames (3.6 s windows)
   static size_t configured = 0;
   if (smem > configured) {
-    B200D_CHECK_CUDA(cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(180 * 1024)));
-    configured = 180 * 1024;
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(215 * 1024)));
+    configured = 215 * 1024;
   }
   featurize_kernel<<<n_seg, kFeatWarps * 32, smem, as_stream(stream)>>>(p);
   B200D_CHECK_LAUNCH();

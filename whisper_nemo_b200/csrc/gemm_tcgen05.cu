@@ -213,6 +213,43 @@ __device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& h, __nv_bflo
   l = __float2bfloat16_rn(r);
 }
 
+// One 128-column accumulator tile of the Chebyshev step: W holds V^T split into three bf16 parts, 32 block columns per
+// 128-row tile as [hi | mid | lo | pad], so accumulator columns (c, 32 + c, 64 + c) of tile `vt_tile` sum to
+// (A V)[row][32 vt_tile + c] at ~fp32 accuracy.  Also emits the same split of the result for the next step.
+__device__ __forceinline__ void cheb_epilogue_tile(const GemmParams& p, int row, uint32_t t_addr, int vt_tile) {
+  const b200d_gemm_epilogue& e = p.epi;
+  constexpr int bpad = 32;
+  const int cb = vt_tile * bpad;  // first block column of this tile
+  uint32_t r0[32], r1[32], r2[32];
+  tmem_ld32(t_addr, r0);
+  tmem_ld32(t_addr + bpad, r1);
+  tmem_ld32(t_addr + 2 * bpad, r2);
+  tmem_ld_wait();
+  if (row < p.M) {
+    const float dg = __ldg(e.deg + row);
+    const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + cb;
+    const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + cb : nullptr;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + cb;
+    __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+      const float xv = x[j];
+      float y = e.ca * (dg * xv - av) + e.cb * xv;
+      if (xp) y += e.cc * xp[j];
+      o[j] = y;
+      if (vh) {
+        __nv_bfloat16 h, m, l;
+        split3_bf16(y, h, m, l);
+        const size_t vrow = static_cast<size_t>(vt_tile) * 128 + j;
+        vh[(vrow) * e.ldvt + row] = h;
+        vh[(vrow + bpad) * e.ldvt + row] = m;
+        vh[(vrow + 2 * bpad) * e.ldvt + row] = l;
+      }
+    }
+  }
+}
+
 template <int BLOCK_N, int MODE, bool BF16>
 __global__ void __launch_bounds__(256, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -312,39 +349,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
       if constexpr (MODE == B200D_EPI_CHEB) {
-        // every 128-wide N tile carries 32 columns of the block as [hi | mid | lo | pad]: a b = 64 block is two tiles,
-        // which doubles the CTAs of a launch whose M alone (N_nodes / 128 tiles) cannot fill 148 SMs
-        const b200d_gemm_epilogue& e = p.epi;
-        constexpr int bpad = 32;
-        const int cb = n_blk * bpad;  // first block column of this tile
-        uint32_t r0[32], r1[32], r2[32];
-        tmem_ld32(t_row, r0);
-        tmem_ld32(t_row + bpad, r1);
-        tmem_ld32(t_row + 2 * bpad, r2);
-        tmem_ld_wait();
-        if (row < p.M) {
-          const float dg = __ldg(e.deg + row);
-          const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + cb;
-          const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + cb : nullptr;
-          float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + cb;
-          __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
-            const float xv = x[j];
-            float y = e.ca * (dg * xv - av) + e.cb * xv;
-            if (xp) y += e.cc * xp[j];
-            o[j] = y;
-            if (vh) {
-              __nv_bfloat16 h, m, l;
-              split3_bf16(y, h, m, l);
-              const size_t vrow = static_cast<size_t>(n_blk) * 128 + j;
-              vh[(vrow) * e.ldvt + row] = h;
-              vh[(vrow + bpad) * e.ldvt + row] = m;
-              vh[(vrow + 2 * bpad) * e.ldvt + row] = l;
-            }
-          }
-        }
+#pragma unroll 1
+        for (int t = 0; t < BLOCK_N / 128; ++t) cheb_epilogue_tile(p, row, t_row + t * 128, n_blk * (BLOCK_N / 128) + t);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -421,7 +427,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
-template <int MODE>
+template <int MODE, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int BN = 256;
@@ -489,7 +495,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp == 1) {
     if (leader && lane == 0) {
       // D fp32, A/B fp16 K-major, N = 256, M = 256 (both CTAs)
-      constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((2 * BLOCK_M) >> 4) << 24);
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                 (static_cast<uint32_t>((2 * BLOCK_M) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -524,16 +532,21 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       const int row = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
+      if constexpr (MODE == B200D_EPI_CHEB) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
-        tmem_ld_wait();
-        if (row < p.M) {
-          float acc_f[32];
+        for (int t = 0; t < BN / 128; ++t) cheb_epilogue_tile(p, row, t_row + t * 128, n_blk * (BN / 128) + t);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float acc_f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
-          epilogue_chunk<MODE>(p, row, n_blk * BN + c * 32, acc_f);
+            for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
+            epilogue_chunk<MODE>(p, row, n_blk * BN + c * 32, acc_f);
+          }
         }
       }
       tc_fence_before();
@@ -607,9 +620,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return B200D_OK;
 }
 
-template <int MODE>
+template <int MODE, bool BF16 = false>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_2cta_kernel<MODE>;
+  auto kern = gemm_tcgen05_2cta_kernel<MODE, BF16>;
   static bool attr_set = false;
   if (!attr_set) {
     B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -630,6 +643,7 @@ static int dispatch_mode_2cta(const CUtensorMap& ta, const CUtensorMap& tb, cons
     case B200D_EPI_TDNN: return launch_2cta<B200D_EPI_TDNN>(ta, tb, p, s);
     case B200D_EPI_BIAS_F32: return launch_2cta<B200D_EPI_BIAS_F32>(ta, tb, p, s);
     case B200D_EPI_SIGMOID_F32: return launch_2cta<B200D_EPI_SIGMOID_F32>(ta, tb, p, s);
+    case B200D_EPI_CHEB: return launch_2cta<B200D_EPI_CHEB, true>(ta, tb, p, s);
   }
   return set_error(B200D_EINVAL, "%s: unknown epilogue mode%s", "b200d_gemm_f16");
 }
@@ -672,11 +686,12 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
     if (mode == B200D_EPI_BIAS || mode == B200D_EPI_BIAS_RELU || mode == B200D_EPI_BIAS_F32) B200D_CHECK_ARG(epi->bias);
   }
   const bool bf16 = mode == B200D_EPI_CHEB;
-  const int block_n = (N % 256 == 0 && mode != B200D_EPI_CHEB) ? 256 : 128;
-  // CTA-pair kernel when there is at least one 256 x 256 tile per TPC (the large pointwise convs)
+  const int block_n = (N % 256 == 0) ? 256 : 128;
+  // CTA-pair kernel when there is at least one 256 x 256 tile per TPC (the large pointwise convs), and for the
+  // Chebyshev products of 64-vector blocks on large graphs (L2-traffic bound: the pair halves the W bytes per SM)
   static const bool allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
-  const bool use_2cta = allow_2cta && mode != B200D_EPI_CHEB && block_n == 256 &&
-                        static_cast<long long>((M + 255) / 256) * (N / 256) >= kNumSMs / 2;
+  const long long tiles2 = static_cast<long long>((M + 255) / 256) * (N / 256);
+  const bool use_2cta = allow_2cta && block_n == 256 && (mode == B200D_EPI_CHEB ? M >= 4096 : tiles2 >= kNumSMs / 2);
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
   if (rc) return rc;
