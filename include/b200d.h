@@ -127,6 +127,11 @@ int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32
 /* y = relu(x * gate[seg]) elementwise (block without residual: B0, B4).  x,y __half [n_seg*T][C] */
 int b200d_se_apply_relu(const void* x, const float* gate, void* y, int32_t n_seg, int32_t T, int32_t C, void* stream);
 
+/* y = relu(x * gate[seg]) and, in the same pass, stats16 __half [n_seg][2*C] = [mean | std] over time of y
+ * (block 4 of the encoder feeding AttentivePoolLayer: SE scaling + get_statistics_with_mask fused).      */
+int b200d_se_apply_relu_stats(const void* x, const float* gate, void* y, int32_t n_seg, int32_t T, int32_t C, void* stats16,
+                              void* stream);
+
 /* Per-segment statistics over time.  with_std == 0: mean, __half [n_seg][C] (SqueezeExcite pool).
  * with_std != 0: [mean | std] __half [n_seg][2*C] (get_statistics_with_mask with uniform weights;
  * input of the hoisted TDNN context term of AttentivePoolLayer).                                  */

@@ -217,3 +217,94 @@ def test_ten_minute_telephonic_properties(dev, weights, tmp_path):
     assert purity >= 0.99
     diar.run_device()
     assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
+
+
+def test_one_hour_meeting_properties(dev, weights, tmp_path):
+    """BASELINE config #3 at full size (1 hour, 8 speakers, meeting YAML, default knobs -> long-form path): size-independent
+    properties -- every window labelled, 2..8 speakers, turns sorted and non-overlapping, second run identical."""
+    from whisper_nemo_b200 import ClusteringDiarizer
+    from whisper_nemo_b200 import speaker_utils as su
+
+    cfg, wav, turns = make_session_cfg(tmp_path, "meeting", 3600.0, 8, seed=100)
+    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights)
+    diar.diarize()
+    r = diar.results["mono_file"]
+    lab1 = r["labels"].copy()
+    assert len(lab1) > 10000 and r["fused_affinity"] is None  # long-form: no N x N fused matrix was built
+    k = len(set(lab1.tolist()))
+    ts = r["timestamps"].numpy()
+    mid = ts.mean(1)
+    truth = np.full(len(mid), -1)
+    for a, b, s in turns:
+        truth[(mid >= a) & (mid <= b)] = s
+    ok = truth >= 0
+    agree = best_permutation_agreement(lab1[ok], truth[ok])
+    print(f"1 h meeting: N={len(lab1)} speakers {k} agreement with the 8 true speakers {agree:.4f} stages {diar.stage_ms}")
+    assert 2 <= k <= 8
+    rttm = su.rttm_to_turns(str(tmp_path / "pred_rttms" / "mono_file.rttm"))
+    assert all(e > s for s, e, _ in rttm)
+    assert all(b[0] >= a[1] - 1e-3 for a, b in zip(rttm, rttm[1:]))
+    diar.run_device()
+    assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
+
+
+def test_multi_recording_manifest_matches_oracle(dev, oracle_model, weights, tmp_path):
+    """A manifest with several recordings (BASELINE config #4 in miniature): the dataloader batches of 64 windows run across
+    recording boundaries (fixed_seq collate), each recording is clustered on its own."""
+    from oracle.clustering_diarizer import OracleClusteringDiarizer
+    from whisper_nemo_b200 import ClusteringDiarizer, config, synth
+
+    def build(root):
+        entries = []
+        for name, dur, spk, seed in (("rec_a", 40.0, 2, 31), ("rec_b", 65.0, 3, 32), ("rec_c", 33.0, 2, 33)):
+            wav_path, rttm_path, _, _ = synth.make_session(str(root), name, dur, spk, seed)
+            entries.append({"audio_filepath": wav_path, "rttm_filepath": rttm_path})
+        cfg = config.load_config("general")
+        man = os.path.join(str(root), "manifest.json")
+        synth.write_manifest(man, entries)
+        cfg.diarizer.manifest_filepath, cfg.diarizer.out_dir, cfg.diarizer.oracle_vad = man, str(root), True
+        return cfg
+
+    state = torch.get_rng_state()
+    oracle = OracleClusteringDiarizer(build(tmp_path / "oracle"), oracle_model)
+    oracle.diarize()
+    torch.set_rng_state(state)
+    diar = ClusteringDiarizer(cfg=build(tmp_path / "b200"), speaker_model=weights)
+    diar.diarize()
+    assert list(diar.results) == list(oracle.results) == ["rec_a", "rec_b", "rec_c"]
+    for u in oracle.results:
+        eo = oracle.embs_and_timestamps[u]["embeddings"]
+        eg = diar.embs_and_timestamps[u]["embeddings"].cpu()
+        cos = torch.nn.functional.cosine_similarity(eo, eg, dim=1)
+        assert (1 - cos).max().item() <= 1e-3
+        assert torch.equal(oracle.embs_and_timestamps[u]["timestamps"], diar.embs_and_timestamps[u]["timestamps"])
+        agree = best_permutation_agreement(diar.results[u]["labels"], oracle.results[u]["labels"])
+        print(f"{u}: N={len(oracle.results[u]['labels'])} k oracle {oracle.results[u]['debug']['n_clusters']} b200 {diar.results[u]['debug']['n_clusters']} agreement {agree:.4f}")
+        assert os.path.exists(tmp_path / "b200" / "pred_rttms" / f"{u}.rttm")
+
+
+def test_boundary_errors(dev, weights, tmp_path):
+    from whisper_nemo_b200 import ClusteringDiarizer
+
+    cfg, _, _ = make_session_cfg(tmp_path, "telephonic", 20.0, 2, seed=3)
+    cfg.diarizer.oracle_vad = False  # MarbleNet VAD is outside the accelerated path
+    with pytest.raises(NotImplementedError, match="VAD"):
+        ClusteringDiarizer(cfg=cfg, speaker_model=weights).diarize()
+    cfg.diarizer.oracle_vad = True
+    cfg.diarizer.clustering.parameters.oracle_num_speakers = True  # manifest has no num_speakers
+    with pytest.raises(ValueError, match="num_speakers"):
+        ClusteringDiarizer(cfg=cfg, speaker_model=weights).diarize()
+    with pytest.raises(RuntimeError, match="B200"):
+        ClusteringDiarizer(cfg=cfg, speaker_model=weights).to("cpu")
+    # external VAD manifest (vad.external_vad_manifest) instead of oracle VAD: same speech regions, same labels
+    import shutil
+
+    cfg2, _, _ = make_session_cfg(tmp_path / "second", "telephonic", 20.0, 2, seed=3)
+    d2 = ClusteringDiarizer(cfg=cfg2, speaker_model=weights)
+    d2.diarize()
+    shutil.copy(tmp_path / "second" / "speaker_outputs" / "oracle_vad_manifest.json", tmp_path / "ext_vad.json")
+    cfg2.diarizer.oracle_vad = False
+    cfg2.diarizer.vad.external_vad_manifest = str(tmp_path / "ext_vad.json")
+    d3 = ClusteringDiarizer(cfg=cfg2, speaker_model=weights)
+    d3.diarize()
+    assert np.array_equal(d3.results["mono_file"]["labels"], d2.results["mono_file"]["labels"])

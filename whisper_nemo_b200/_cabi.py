@@ -49,6 +49,7 @@ _SIGNATURES = {
                                  POINTER(GemmEpilogue), c_void_p]),
     "b200d_time_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_se_apply_relu": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "b200d_se_apply_relu_stats": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_attn_pool": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_l2_normalize": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "b200d_cos_affinity": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
@@ -123,7 +124,7 @@ def check(rc, name):
 
 # kernels launched per C-ABI call (bench.py's gpu_launches claim is the sum over the timed region)
 KERNELS_PER_CALL = {
-    "b200d_featurize": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_apply_relu": 1,
+    "b200d_featurize": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_apply_relu": 1, "b200d_se_apply_relu_stats": 1,
     "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
     "b200d_masked_rowsum": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
     "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,

@@ -166,6 +166,52 @@ __global__ void se_apply_relu_kernel(const __half* __restrict__ x, const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------ SE apply + statistics
+// Last encoder block: y = relu(x * gate[window]) AND, in the same pass over the 3072-channel activation, the per-window
+// [mean | std] of y that AttentivePoolLayer's TDNN context needs (moments of the fp16-rounded y, accumulated in fp32;
+// T <= 362 values per channel, so the one-pass variance is exact to ~1e-6).  Saves two full reads of y.
+__global__ void __launch_bounds__(64 * kTsSlices) se_apply_stats_kernel(const __half* __restrict__ x, const float* __restrict__ gate,
+                                                                        __half* __restrict__ y, int T, int C, __half* __restrict__ stats16) {
+  __shared__ float s_1[kTsSlices][64][4], s_2[kTsSlices][64][4];
+  const int seg = blockIdx.x;
+  const int g = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c = (blockIdx.y * 64 + g) * 4;
+  const bool active = c < C;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    const __half* xs = x + static_cast<size_t>(seg) * T * C + c;
+    __half* ys = y + static_cast<size_t>(seg) * T * C + c;
+    const float4 gt = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(seg) * C + c));
+    const float gv[4] = {gt.x, gt.y, gt.z, gt.w};
+    for (int t = slice; t < T; t += kTsSlices) {
+      float v[4];
+      load4h(xs + static_cast<size_t>(t) * C, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = __half2float(__float2half_rn(fmaxf(v[q] * gv[q], 0.f)));
+      store4h(ys + static_cast<size_t>(t) * C, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { s1[q] += v[q]; s2[q] = fmaf(v[q], v[q], s2[q]); }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { s_1[slice][g][q] = s1[q]; s_2[slice][g][q] = s2[q]; }
+  __syncthreads();
+  if (slice == 0 && active) {
+    const float inv = 1.f / static_cast<float>(T);
+    float mean[4], sd[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < kTsSlices; ++sl) { a += s_1[sl][g][q]; b += s_2[sl][g][q]; }
+      mean[q] = a * inv;
+      sd[q] = sqrtf(fmaxf(b * inv - mean[q] * mean[q], 1e-10f));
+    }
+    store4h(stats16 + static_cast<size_t>(seg) * 2 * C + c, mean);
+    store4h(stats16 + static_cast<size_t>(seg) * 2 * C + C + c, sd);
+  }
+}
+
 // ------------------------------------------------------------------------------------ attentive pooling
 // alpha = softmax over time of e (per channel); mu = sum alpha x; sg = sqrt(clamp(sum alpha (x - mu)^2, 1e-10)).
 // Single pass with an online (running-max) softmax per time slice; the kTsSlices partial states (max, Z, S1, S2) are
@@ -276,6 +322,15 @@ extern "C" int b200d_attn_pool(const void* x, const void* e, int32_t n_seg, int3
   B200D_CHECK_ARG(x && e && out16 && n_seg > 0 && T > 0 && C % 4 == 0);
   attn_pool_kernel<<<dim3(n_seg, (C / 4 + 63) / 64), 64 * kTsSlices, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(e), T, C,
                                                             reinterpret_cast<__half*>(out16));
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_se_apply_relu_stats(const void* x, const float* gate, void* y, int32_t n_seg, int32_t T, int32_t C, void* stats16,
+                                         void* stream) {
+  B200D_CHECK_ARG(x && gate && y && stats16 && n_seg > 0 && T > 0 && C % 4 == 0);
+  se_apply_stats_kernel<<<dim3(n_seg, (C / 4 + 63) / 64), 64 * kTsSlices, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(x), gate, reinterpret_cast<__half*>(y), T, C, reinterpret_cast<__half*>(stats16));
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }

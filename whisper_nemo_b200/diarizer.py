@@ -227,7 +227,7 @@ class ClusteringDiarizer:
                 raise ValueError("Provided option as oracle num of speakers but num_speakers in manifest is null")
         else:
             num_speakers = -1
-        sc = LongFormSpeakerClustering()
+        sc = LongFormSpeakerClustering(shard_chunks=self.shard_windows)
         labels = sc.forward_infer(
             embeddings_in_scales=e["embeddings"],
             timestamps_in_scales=e["timestamps"],

@@ -84,7 +84,10 @@ def get_merge_quantity(num_to_be_removed: int, pre_clus_labels: torch.Tensor, mi
 
 
 class LongFormSpeakerClustering:
-    def __init__(self):
+    def __init__(self, shard_chunks: bool = False):
+        """shard_chunks: under torch.distributed, deal the (independent) chunks of the long-form path to the ranks and
+        gather their reduced embeddings; everything else runs replicated and gives the same labels on every rank."""
+        self.shard_chunks = bool(shard_chunks)
         self.speaker_clustering = SpeakerClustering()
         self.embeddings_in_scales: List[torch.Tensor] = []
         self.timestamps_in_scales: List[torch.Tensor] = []
@@ -168,7 +171,16 @@ class LongFormSpeakerClustering:
         window_range_list: List[Tuple[int, int]] = []
         absolute_merge_mapping = []
         window_offset = 0
-        for win_index in range(self.get_div_ceil_count(n_total, embeddings_per_chunk)):
+        n_chunks = self.get_div_ceil_count(n_total, embeddings_per_chunk)
+        rank, world = (0, 1)
+        if self.shard_chunks:
+            from . import sharding
+
+            rank, world = sharding.rank_world()
+        per_chunk = {}
+        for win_index in range(n_chunks):
+            if win_index % world != rank:
+                continue
             if embeddings_per_chunk * (win_index + 1) > n_total:  # last chunk is aligned to the end (overlaps the previous one)
                 offset_index = n_total - embeddings_per_chunk
             else:
@@ -190,13 +202,20 @@ class LongFormSpeakerClustering:
             y_host = Y_part.cpu()
             min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
             class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
-            merged_list, mapping_list = self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
+            per_chunk[win_index] = self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
+            del mat
+        if world > 1:  # tiny payload: <= chunk_cluster_count x 192 floats + the index lists of one chunk per entry
+            payload = {w: ([m.cpu() for m in ml], mp) for w, (ml, mp) in per_chunk.items()}
+            gathered = [None] * world
+            torch.distributed.all_gather_object(gathered, payload)
+            per_chunk = {w: ([m.to(emb.device) for m in ml], mp) for part in gathered for w, (ml, mp) in part.items()}
+        for win_index in range(n_chunks):
+            merged_list, mapping_list = per_chunk[win_index]
             for merged, mapping in zip(merged_list, mapping_list):
                 total_emb.append(merged)
                 absolute_merge_mapping.append(mapping)
                 window_range_list.append((window_offset, window_offset + merged.shape[0]))
                 window_offset += merged.shape[0]
-            del mat
         reduced_embs = torch.cat(total_emb)
         cos, mm = cos_affinity(reduced_embs)
         ident = torch.arange(reduced_embs.shape[0], dtype=torch.int32, device=emb.device)

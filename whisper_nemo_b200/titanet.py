@@ -12,6 +12,7 @@ k=1 depthwise of the last block folded into its pointwise, the TDNN context term
 [mean | std] hoisted out of the per-frame GEMM, embedding BN folded into the
 final 6144->192 projection, logits layer dropped (inference discards it).
 """
+import os
 from ctypes import byref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -291,12 +292,11 @@ def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: d
     b4 = pk.blocks[4]
     gemm(cur, b4.subs[0].w, ws.e, _cabi.EPI_BIAS, M=M, bias=b4.subs[0].bias)
     gate = _se_gate(pk, ws, b4, ws.e, n_seg, T, 3072)
-    _cabi.call("b200d_se_apply_relu", ptr(ws.e), ptr(gate), ptr(ws.x), n_seg, T, 3072, s)
+    stats16 = ws.stats16[:n_seg]
+    _cabi.call("b200d_se_apply_relu_stats", ptr(ws.e), ptr(gate), ptr(ws.x), n_seg, T, 3072, ptr(stats16), s)
     if taps is not None:
         taps["encoder"] = ws.x[:M].clone()
     # ---- decoder: attentive statistics pooling + embedding projection
-    stats16 = ws.stats16[:n_seg]
-    _cabi.call("b200d_time_stats", ptr(ws.x), n_seg, T, 3072, 1, ptr(stats16), s)
     segbias = ws.segbias[:n_seg]
     gemm(stats16, pk.tdnn_wctx, segbias, _cabi.EPI_BIAS_F32, bias=pk.tdnn_b)
     gemm(ws.x, pk.tdnn_wx, ws.hid, _cabi.EPI_TDNN, M=M, scale=pk.tdnn_scale, shift=pk.tdnn_shift, rowvec=segbias, rows_per_seg=T)
@@ -314,8 +314,10 @@ class TitaNetB200:
     """Speaker-embedding extractor: `embed_segments` is the device-side replacement of the
     `_extract_embeddings` dataloader loop of upstream ClusteringDiarizer."""
 
-    def __init__(self, state_dict, device="cuda", max_frames: int = 49152):
+    def __init__(self, state_dict, device="cuda", max_frames: int = None):
         _cabi.require_device()
+        if max_frames is None:  # frames per launch group: ~21 KB of fp16 activations per frame (2.7 GB at the default)
+            max_frames = int(os.environ.get("B200D_MAX_FRAMES", 131072))
         self.device = torch.device(device)
         self.pk = pack_weights(state_dict, self.device)
         self.max_frames = max_frames
