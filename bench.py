@@ -37,6 +37,11 @@ WORKLOADS = {
     "general_10min": ("general", 600.0, 3, 3),
     "telephonic_4h": ("telephonic", 14400.0, 12, 4),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu --set full capture
+# profiles/r01_ncu_full_gemm2cta_depthwise_featurize_v2.txt: gemm_tcgen05_2cta_kernel<bias>, M = 120 649 frames (799 windows of
+# 151), N = K = 1024 -> 213.7 MB read + 166.2 MB written (algorithmic: 247 MB A + 2 MB W + 247 MB out; part of A is still L2-resident)
+NCU_GEMM_TRAFFIC = {"bytes_per_launch": 379982592, "launch": "M=120649 N=1024 K=1024 bias epilogue", "algorithmic_bytes": 496275456,
+                    "source": "profiles/r01_ncu_full_gemm2cta_depthwise_featurize_v2.txt"}
 METRIC = "diarized audio-hours/sec (embed+NME-SC, device-timed)"
 UNIT = "audio-hours/s"
 
@@ -195,7 +200,7 @@ def run_b200(args):
         roofline = {
             "kernel": "gemm_tcgen05_kernel (TitaNet-L pointwise convs / projections + spectral A*V)",
             "bound": "tensor", "achieved": round(gemm_tflops, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": round(gemm_tflops / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["src"],
+            "frac": round(gemm_tflops / peaks["tflops"], 4), "traffic": NCU_GEMM_TRAFFIC, "peak_source": peaks["src"],
             "launches_per_step": g["calls"], "avg_launch_ms": round(g["ms"] / max(g["calls"], 1), 4),
             "share_of_step": round(g["ms"] / (dev_ms / args.steps), 3),
             "step_titanet_tflops": round(flops / (stage_ms.get("embed", float("nan")) * 1e-3) / 1e12, 1),

@@ -26,16 +26,58 @@ __device__ __forceinline__ void store4h(__half* p, const float (&v)[4]) {
 // ------------------------------------------------------------------------------------ depthwise
 // Thread = 2 channels x a strip of kDwTT consecutive output frames of one window.  All kDwTT + k - 1 input rows of the
 // strip are requested up front (independent 4-byte loads, a warp touches 128 contiguous bytes per row), so the DRAM /
-// L2 latency is paid once per strip instead of once per row; the k x 2 filter taps and a sliding window of the last
-// k converted rows live in registers (fully unrolled: the ring index is a compile-time constant).  Every input row is
-// loaded once per strip (read amplification (TT + k - 1) / TT, the halo from L1/L2) and the output is written once.
+// L2 latency is paid once per strip; every input row is loaded once per strip (read amplification (TT + k - 1) / TT,
+// the halo from L1/L2) and the output is written once.
+// Arithmetic: the fp32 version of this kernel was ISSUE-bound (ncu: 127 M warp instructions per launch, 57 % issue
+// utilisation at 23 % of DRAM peak; a third of the instructions were address / predicate arithmetic), so
+//  * the taps are applied with packed half2 FMAs straight on the loaded fp16 pairs, in partial sums of at most 5 taps
+//    (relative rms error 5e-4 against 2e-4 for fp32 accumulation + fp16 store, whose rounding dominates both; upstream
+//    runs this conv under fp16 autocast on CUDA),
+//  * the channel count is a template parameter, so row addresses are immediates off one base pointer, and
+//  * strips that do not touch a window edge take a predicate-free path.
 constexpr int kDwTT = 32;
 
-template <int KS>
+template <int KS, int CT, bool EDGE>
+__device__ __forceinline__ void depthwise_strip(const __half* __restrict__ xs, __half* __restrict__ ys, const __half2 (&wt)[KS], int t0,
+                                                int T, int C_rt) {
+  constexpr int PAD = KS / 2;
+  constexpr int ROWS = kDwTT + KS - 1;
+  constexpr int GROUP = 5;
+  const size_t C = CT > 0 ? static_cast<size_t>(CT) : static_cast<size_t>(C_rt);
+  const __half* x0 = xs + (static_cast<long long>(t0) - PAD) * static_cast<long long>(C);
+  __half2 raw[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    uint32_t u;
+    if constexpr (EDGE) {
+      const int t = t0 - PAD + r;
+      u = (t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint32_t*>(x0 + r * C)) : 0u;
+    } else {
+      u = __ldg(reinterpret_cast<const uint32_t*>(x0 + r * C));
+    }
+    raw[r] = *reinterpret_cast<__half2*>(&u);
+  }
+  __half* y0 = ys + static_cast<size_t>(t0) * C;
+#pragma unroll
+  for (int tt = 0; tt < kDwTT; ++tt) {
+    if (!EDGE || t0 + tt < T) {
+      __half2 acc;
+#pragma unroll
+      for (int j0 = 0; j0 < KS; j0 += GROUP) {
+        __half2 part = __hmul2(wt[j0], raw[tt + j0]);
+#pragma unroll
+        for (int j = j0 + 1; j < j0 + GROUP && j < KS; ++j) part = __hfma2(wt[j], raw[tt + j], part);
+        acc = (j0 == 0) ? part : __hadd2(acc, part);
+      }
+      *reinterpret_cast<__half2*>(y0 + tt * C) = acc;
+    }
+  }
+}
+
+template <int KS, int CT>
 __global__ void __launch_bounds__(256, 2) depthwise_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                            const float* __restrict__ w, int n_seg, int T, int C, int strips) {
   constexpr int PAD = KS / 2;
-  constexpr int ROWS = kDwTT + KS - 1;
   const int cp = blockIdx.y * blockDim.x + threadIdx.x;  // channel pair
   if (cp * 2 >= C) return;
   const int strip = blockIdx.x;
@@ -44,33 +86,14 @@ __global__ void __launch_bounds__(256, 2) depthwise_kernel(const __half* __restr
   const int c = cp * 2;
   const __half* xs = x + (static_cast<size_t>(seg) * T) * C + c;
   __half* ys = y + (static_cast<size_t>(seg) * T) * C + c;
-  uint32_t raw[ROWS];
+  __half2 wt[KS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const int t = t0 - PAD + r;
-    raw[r] = (t >= 0 && t < T) ? __ldg(reinterpret_cast<const uint32_t*>(xs + static_cast<size_t>(t) * C)) : 0u;
+  for (int j = 0; j < KS; ++j) {
+    const float2 f = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(j) * C + c));
+    wt[j] = __floats2half2_rn(f.x, f.y);
   }
-  float2 wt[KS];
-#pragma unroll
-  for (int j = 0; j < KS; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(j) * C + c));
-  auto cvt = [](uint32_t u) -> float2 { return __half22float2(*reinterpret_cast<const __half2*>(&u)); };
-  float2 win[KS];
-#pragma unroll
-  for (int j = 0; j < KS - 1; ++j) win[j] = cvt(raw[j]);
-#pragma unroll
-  for (int tt = 0; tt < kDwTT; ++tt) {
-    win[(tt + KS - 1) % KS] = cvt(raw[tt + KS - 1]);
-    if (t0 + tt < T) {
-      float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < KS; ++j) {
-        const float2 v = win[(tt + j) % KS];
-        acc.x = fmaf(wt[j].x, v.x, acc.x);
-        acc.y = fmaf(wt[j].y, v.y, acc.y);
-      }
-      *reinterpret_cast<__half2*>(ys + static_cast<size_t>(t0 + tt) * C) = __floats2half2_rn(acc.x, acc.y);
-    }
-  }
+  if (t0 >= PAD && t0 + kDwTT + PAD <= T) depthwise_strip<KS, CT, false>(xs, ys, wt, t0, T, C);
+  else depthwise_strip<KS, CT, true>(xs, ys, wt, t0, T, C);
 }
 
 // ------------------------------------------------------------------------------------ time statistics
@@ -286,13 +309,19 @@ extern "C" int b200d_depthwise_conv(const void* x, void* y, const float* w, int3
   dim3 grid(static_cast<unsigned>(n_seg) * strips, (C / 2 + threads - 1) / threads);
   const __half* xi = reinterpret_cast<const __half*>(x);
   __half* yo = reinterpret_cast<__half*>(y);
+  cudaStream_t st = as_stream(stream);
+#define B200D_DW(KS)                                                                                      \
+  if (C == 1024) depthwise_kernel<KS, 1024><<<grid, threads, 0, st>>>(xi, yo, w, n_seg, T, C, strips);   \
+  else if (C == 128) depthwise_kernel<KS, 128><<<grid, threads, 0, st>>>(xi, yo, w, n_seg, T, C, strips); \
+  else depthwise_kernel<KS, 0><<<grid, threads, 0, st>>>(xi, yo, w, n_seg, T, C, strips)
   switch (ksize) {
-    case 3: depthwise_kernel<3><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
-    case 7: depthwise_kernel<7><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
-    case 11: depthwise_kernel<11><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
-    case 15: depthwise_kernel<15><<<grid, threads, 0, as_stream(stream)>>>(xi, yo, w, n_seg, T, C, strips); break;
+    case 3: B200D_DW(3); break;
+    case 7: B200D_DW(7); break;
+    case 11: B200D_DW(11); break;
+    case 15: B200D_DW(15); break;
     default: return b200d::set_error(B200D_EINVAL, "%s: unsupported kernel size (3, 7, 11, 15)%s", "b200d_depthwise_conv");
   }
+#undef B200D_DW
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
