@@ -169,6 +169,10 @@ int b200d_fuse_scales(int32_t n_scales, const float* const* cos_host, const int3
 int b200d_interp_scales(int32_t n_scales, const float* const* emb_host, const int32_t* const* map_host, const float* weights_host,
                         float* out, int32_t n_base, int32_t d, void* stream);
 int b200d_masked_rowsum(const float* mat, int32_t n, const int32_t* labels, float* out, void* stream);
+/*  gather_segment_mean  out[s] = mean over i in [seg_off[s], seg_off[s+1]) of x[idx[i]] (online_clustering.merge_vectors for
+ *                       every cluster of a chunk in one launch; fixed summation order).  x float32 [*][d], out [n_seg][d]  */
+int b200d_gather_segment_mean(const float* x, int32_t d, const int32_t* idx, const int32_t* seg_off, int32_t n_seg, float* out,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * NME-SC graph + spectrum (getKneighborsConnections, getAffinityGraphMat, getLaplacian,

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "b200d_fuse_scales": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "b200d_interp_scales": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "b200d_masked_rowsum": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_gather_segment_mean": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_row_rank": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200d_laplacian_from_rank": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_graph_reach_rank": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
@@ -126,7 +127,7 @@ def check(rc, name):
 KERNELS_PER_CALL = {
     "b200d_featurize": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_apply_relu": 1, "b200d_se_apply_relu_stats": 1,
     "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
-    "b200d_masked_rowsum": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
+    "b200d_masked_rowsum": 1, "b200d_gather_segment_mean": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
     "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
     "b200d_resid_norms": 1, "b200d_kmeans": 1,
 }

@@ -177,6 +177,20 @@ __global__ void __launch_bounds__(256) masked_rowsum_kernel(const float* __restr
   if (lane == 0) out[row] = acc;
 }
 
+
+// out[s] = mean over i in [seg_off[s], seg_off[s+1]) of x[idx[i]]  (fixed summation order: deterministic).
+// The merged embedding of online_clustering.merge_vectors for every cluster of a long-form chunk in one launch.
+__global__ void __launch_bounds__(256) gather_segment_mean_kernel(const float* __restrict__ x, int d, const int* __restrict__ idx,
+                                                                  const int* __restrict__ seg_off, float* __restrict__ out) {
+  const int s = blockIdx.x;
+  const int a = __ldg(seg_off + s), b = __ldg(seg_off + s + 1);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = a; i < b; ++i) acc += __ldg(x + static_cast<size_t>(__ldg(idx + i)) * d + c);
+    out[static_cast<size_t>(s) * d + c] = b > a ? acc / static_cast<float>(b - a) : 0.f;
+  }
+}
+
 }  // namespace b200d
 
 using namespace b200d;
@@ -238,6 +252,14 @@ extern "C" int b200d_interp_scales(int32_t n_scales, const float* const* emb_hos
 extern "C" int b200d_masked_rowsum(const float* mat, int32_t n, const int32_t* labels, float* out, void* stream) {
   B200D_CHECK_ARG(mat && labels && out && n > 0);
   masked_rowsum_kernel<<<(n + 7) / 8, 256, 0, as_stream(stream)>>>(mat, n, labels, out);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_gather_segment_mean(const float* x, int32_t d, const int32_t* idx, const int32_t* seg_off, int32_t n_seg, float* out,
+                                         void* stream) {
+  B200D_CHECK_ARG(x && idx && seg_off && out && d > 0 && n_seg > 0);
+  gather_segment_mean_kernel<<<n_seg, 256, 0, as_stream(stream)>>>(x, d, idx, seg_off, out);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }

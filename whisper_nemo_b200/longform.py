@@ -124,39 +124,52 @@ class LongFormSpeakerClustering:
 
     def _reduce_chunk(self, emb_part: torch.Tensor, mat: torch.Tensor, Y_part: torch.Tensor, class_target_vol: torch.Tensor,
                       offset_index: int):
-        """run_reducer for every cluster of one chunk.  Returns ([merged_embs per cluster], [index mappings])."""
-        n = emb_part.shape[0]
+        """run_reducer for every cluster of one chunk.  Returns ([merged_embs per cluster], [index mappings]).
+        The index bookkeeping (<= 50 clusters) is host work on the labels; the embedding traffic is three device
+        operations for the whole chunk: within-cluster affinity mass, merged means, one gather."""
+        n, d = emb_part.shape
+        dev = emb_part.device
         y_host = Y_part.cpu()
+        vols = [int(v) for v in class_target_vol.tolist()]
         mass_host = None
-        if mat is not None and int(class_target_vol.sum()) > 0:
-            mass = torch.empty(n, dtype=torch.float32, device=emb_part.device)
+        if mat is not None and sum(vols) > 0:
+            mass = torch.empty(n, dtype=torch.float32, device=dev)
             y32 = Y_part.to(torch.int32).contiguous()
             _cabi.call("b200d_masked_rowsum", ptr(mat), n, ptr(y32), ptr(mass), _s())
             mass_host = mass.cpu()
-        merged_list, mapping_list = [], []
-        for spk_idx, merge_quantity in enumerate(class_target_vol.tolist()):
+        mapping_list, sizes = [], []
+        sel_idx, seg_off, order = [], [0], []  # merged-mean members / their segment offsets / final gather order
+        n_avg = 0
+        for spk_idx, merge_quantity in enumerate(vols):
             target = torch.where(y_host == spk_idx)[0]
             if merge_quantity > 0:
                 if merge_quantity > target.shape[0] - 1:
                     raise ValueError("merge_quantity is larger than the half of targeted speaker's labels")
-                order = torch.argsort(mass_host[target], descending=True)
-                selected, rest = order[: merge_quantity + 1], order[merge_quantity + 1 :]
-                rest_sorted = rest.sort()[0]
-                tgt_dev = target.to(emb_part.device)
-                avg = emb_part.index_select(0, tgt_dev[selected.to(emb_part.device)]).mean(dim=0, keepdim=True)
-                if rest_sorted.numel() > 0:
-                    keep = emb_part.index_select(0, tgt_dev[rest_sorted.to(emb_part.device)])
-                    merged = torch.cat([keep, avg], dim=0)
-                else:
-                    merged = avg
-                mapping = (target[rest_sorted] + offset_index, target[selected] + offset_index)
-                if target.shape[0] - merge_quantity != merged.shape[0]:
+                rank = torch.argsort(mass_host[target], descending=True)
+                selected, rest_sorted = rank[: merge_quantity + 1], rank[merge_quantity + 1 :].sort()[0]
+                sel_idx.append(target[selected])
+                seg_off.append(seg_off[-1] + selected.numel())
+                order.append(target[rest_sorted])
+                order.append(torch.tensor([n + n_avg]))  # row of the merged vector in [emb_part ; means]
+                n_avg += 1
+                mapping_list.append((target[rest_sorted] + offset_index, target[selected] + offset_index))
+                sizes.append(int(rest_sorted.numel()) + 1)
+                if target.shape[0] - merge_quantity != sizes[-1]:
                     raise ValueError("Reducer output is not matched to the target quantity")
             else:
-                merged = emb_part.index_select(0, target.to(emb_part.device))
-                mapping = (target + offset_index, torch.arange(0))
-            merged_list.append(merged)
-            mapping_list.append(mapping)
+                order.append(target)
+                mapping_list.append((target + offset_index, torch.arange(0)))
+                sizes.append(int(target.numel()))
+        src = emb_part
+        if n_avg > 0:
+            idx_d = torch.cat(sel_idx).to(torch.int32).to(dev)
+            off_d = torch.tensor(seg_off, dtype=torch.int32).to(dev)
+            means = torch.empty(n_avg, d, dtype=torch.float32, device=dev)
+            x = emb_part.contiguous()
+            _cabi.call("b200d_gather_segment_mean", ptr(x), d, ptr(idx_d), ptr(off_d), n_avg, ptr(means), _s())
+            src = torch.cat([emb_part, means], dim=0)
+        merged_all = src.index_select(0, torch.cat(order).to(dev)) if order else src[:0]
+        merged_list = list(torch.split(merged_all, sizes, dim=0))
         return merged_list, mapping_list
 
     def long_forward_infer(self, embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
