@@ -113,12 +113,13 @@ def _fuse(cos_list, map_list, mm_list, weights, n_base) -> torch.Tensor:
     return fused
 
 
-def getMultiScaleCosAffinityMatrix(multiscale_weights, embeddings_in_scales, timestamps_in_scales) -> torch.Tensor:
+def getMultiScaleCosAffinityMatrix(multiscale_weights, embeddings_in_scales, timestamps_in_scales, scale_mapping=None) -> torch.Tensor:
     """Fused N_base x N_base affinity, the unnormalised weighted sum of the per-scale min-max
     scaled cosine matrices (range [0, sum w]).  The per-scale N x N expansions of upstream's
     repeat_interleave are never materialised."""
     weights = torch.as_tensor(multiscale_weights).reshape(-1).tolist()
-    mapping = get_argmin_mat(timestamps_in_scales)
+    # `scale_mapping`: get_argmin_mat(timestamps) computed by the caller while the GPU was still embedding
+    mapping = scale_mapping if scale_mapping is not None else get_argmin_mat(timestamps_in_scales)
     dev = embeddings_in_scales[0].device
     n_base = int(timestamps_in_scales[-1].shape[0])
     cos_list, mm_list, map_list = [], [], []
@@ -543,7 +544,7 @@ class SpeakerClustering:
     def forward_infer(self, embeddings_in_scales: torch.Tensor, timestamps_in_scales: torch.Tensor,
                       multiscale_segment_counts: torch.Tensor, multiscale_weights: torch.Tensor, oracle_num_speakers: int = -1,
                       max_rp_threshold: float = 0.15, max_num_speakers: int = 8, enhanced_count_thres: int = ENHANCED_COUNT_THRES,
-                      sparse_search_volume: int = 30, fixed_thres: float = -1.0) -> torch.Tensor:
+                      sparse_search_volume: int = 30, fixed_thres: float = -1.0, scale_mapping=None) -> torch.Tensor:
         self.embeddings_in_scales, self.timestamps_in_scales = split_input_data(embeddings_in_scales, timestamps_in_scales,
                                                                                 multiscale_segment_counts)
         emb = self.embeddings_in_scales[-1]
@@ -555,7 +556,7 @@ class SpeakerClustering:
             est_num_of_spk_enhanced = -1
         if oracle_num_speakers > 0:
             max_num_speakers = oracle_num_speakers
-        mat = getMultiScaleCosAffinityMatrix(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales)
+        mat = getMultiScaleCosAffinityMatrix(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales, scale_mapping)
         self.fused_affinity = mat
         return self.forward_unit_infer(mat=mat, oracle_num_speakers=oracle_num_speakers, max_rp_threshold=max_rp_threshold,
                                        max_num_speakers=max_num_speakers, sparse_search_volume=sparse_search_volume,

@@ -91,32 +91,25 @@ __global__ void __launch_bounds__(kTriThreads, 2) tridiag_kernel(float* __restri
     for (int i = j + 1 + slot; i < n; i += slots) {
       float* row = A + static_cast<size_t>(i) * n;
       const float vpi = s_vp[i], wpi = s_wp[i];
-      float acc0 = 0.f, acc1 = 0.f;
-      // the pass is L2-LATENCY bound (a few rows per warp, each a dependent chain of ~1 us round trips if streamed):
-      // request the whole row slice first (up to 32 independent 128-byte requests per warp), then update it
-      for (int kb = j + 1; kb < n; kb += 1024) {
-        float a[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int k = kb + lane + 32 * q;
-          a[q] = (k < n) ? __ldcg(row + k) : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          const int k0 = kb + lane + 32 * q, k1 = k0 + 32;
-          if (k0 < n) {
-            const float v = a[q] - vpi * s_wp[k0] - wpi * s_vp[k0];
-            __stcg(row + k0, v);
-            acc0 = fmaf(v, s_v[k0], acc0);
-          }
-          if (k1 < n) {
-            const float v = a[q + 1] - vpi * s_wp[k1] - wpi * s_vp[k1];
-            __stcg(row + k1, v);
-            acc1 = fmaf(v, s_v[k1], acc1);
-          }
-        }
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      int k = j + 1 + lane;
+      // four independent 128-byte requests in flight per warp: the pass is L2-latency bound, not bandwidth bound
+      for (; k + 96 < n; k += 128) {
+        const float a0 = __ldcg(row + k), a1 = __ldcg(row + k + 32), a2 = __ldcg(row + k + 64), a3 = __ldcg(row + k + 96);
+        const float v0 = a0 - vpi * s_wp[k] - wpi * s_vp[k];
+        const float v1 = a1 - vpi * s_wp[k + 32] - wpi * s_vp[k + 32];
+        const float v2 = a2 - vpi * s_wp[k + 64] - wpi * s_vp[k + 64];
+        const float v3 = a3 - vpi * s_wp[k + 96] - wpi * s_vp[k + 96];
+        __stcg(row + k, v0); __stcg(row + k + 32, v1); __stcg(row + k + 64, v2); __stcg(row + k + 96, v3);
+        acc0 = fmaf(v0, s_v[k], acc0); acc1 = fmaf(v1, s_v[k + 32], acc1);
+        acc2 = fmaf(v2, s_v[k + 64], acc2); acc3 = fmaf(v3, s_v[k + 96], acc3);
       }
-      const float acc = warp_sum(acc0 + acc1);
+      for (; k < n; k += 32) {
+        const float v = __ldcg(row + k) - vpi * s_wp[k] - wpi * s_vp[k];
+        __stcg(row + k, v);
+        acc0 = fmaf(v, s_v[k], acc0);
+      }
+      const float acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
       if (lane == 0) pw[i] = beta * acc;
     }
     __threadfence();

@@ -163,6 +163,15 @@ class ClusteringDiarizer:
             path = os.path.join(self._speaker_dir, f"subsegments_scale{scale_idx}.json")
             entries = su.segments_manifest_to_subsegments_manifest(speech_manifest, path, window, shift)
             self._scales[scale_idx] = self._plan_scale(entries)
+        # per recording and scale: row range of its windows in the scale's embedding matrix + the [start, end] stamps
+        for plan in self._scales.values():
+            uniq_arr = np.asarray(plan["uniq"])
+            plan["rows"], plan["stamps"] = {}, {}
+            for u in self.AUDIO_RTTM_MAP.keys():
+                sel = np.nonzero(uniq_arr == u)[0]
+                if len(sel):
+                    plan["rows"][u] = sel
+                    plan["stamps"][u] = torch.tensor([[plan["t0"][i], plan["t1"][i]] for i in sel])  # float32, as upstream
 
     def _plan_scale(self, entries: List[dict]) -> dict:
         """Window descriptors of one scale: sample ranges in the concatenated waveform, and the frame
@@ -239,6 +248,7 @@ class ClusteringDiarizer:
             sparse_search_volume=int(_get(clus, "sparse_search_volume", 30)),
             chunk_cluster_count=_get(clus, "chunk_cluster_count", None),
             embeddings_per_chunk=_get(clus, "embeddings_per_chunk", None),
+            scale_mapping=e.get("scale_mapping"),
         )
         return labels, sc
 
@@ -253,18 +263,20 @@ class ClusteringDiarizer:
         per_scale = {}
         for scale_idx, plan in self._scales.items():
             embs = self._extract_embeddings(plan, wav_dev)
-            e_by, t_by = {}, {}
-            uniq_arr = np.asarray(plan["uniq"])
-            for u in self.AUDIO_RTTM_MAP.keys():
-                sel = np.nonzero(uniq_arr == u)[0]
-                if len(sel) == 0:
-                    continue
-                e_by[u] = embs[int(sel[0]) : int(sel[-1]) + 1] if (np.diff(sel) == 1).all() else embs[torch.from_numpy(sel).to(self.device)]
-                t_by[u] = [[plan["t0"][i], plan["t1"][i]] for i in sel]
-            per_scale[scale_idx] = (e_by, t_by)
+            e_by = {}
+            for u, sel in plan["rows"].items():
+                contiguous = len(sel) == int(sel[-1]) - int(sel[0]) + 1
+                e_by[u] = embs[int(sel[0]) : int(sel[-1]) + 1] if contiguous else embs[torch.from_numpy(sel).to(self.device)]
+            per_scale[scale_idx] = (e_by, plan["stamps"])
         timer.stop(h)
         self.multiscale_embeddings_and_timestamps = per_scale
         self.embs_and_timestamps = su.get_embs_and_timestamps(per_scale, self.multiscale_args_dict)
+        # host work that only needs the window times runs here, while the GPU is still busy with the embeddings queued above
+        from .clustering import get_argmin_mat
+
+        for uniq_id, e in self.embs_and_timestamps.items():
+            split = [int(x) for x in e["multiscale_segment_counts"].tolist()]
+            e["scale_mapping"] = get_argmin_mat(list(torch.split(e["timestamps"], split, dim=0)))
         h = timer.start("cluster")
         pending = {}
         for uniq_id in self.AUDIO_RTTM_MAP.keys():

@@ -14,6 +14,7 @@ k-means (clustering.py), and the within-cluster affinity mass that ranks merge c
 bookkeeping on <= 50 cluster sizes and index lists.
 """
 import ctypes
+import os
 from typing import List, Tuple
 
 import numpy as np
@@ -24,10 +25,13 @@ from ._cabi import ptr
 from .clustering import SpeakerClustering, _s, get_argmin_mat, cos_affinity, _fuse, split_input_data
 
 
-def get_scale_interpolated_embs(multiscale_weights, embeddings_in_scales, timestamps_in_scales):
+_CHUNK_STREAMS: List[torch.cuda.Stream] = []
+
+
+def get_scale_interpolated_embs(multiscale_weights, embeddings_in_scales, timestamps_in_scales, scale_mapping=None):
     """One embedding per base-scale window: the weighted sum over scales of the embedding of the
     nearest window of each scale.  Returns (float32 [n_base, d] on device, mapping list)."""
-    mapping = get_argmin_mat(timestamps_in_scales)
+    mapping = scale_mapping if scale_mapping is not None else get_argmin_mat(timestamps_in_scales)
     dev = embeddings_in_scales[0].device
     n_base = int(timestamps_in_scales[-1].shape[0])
     d = int(embeddings_in_scales[0].shape[1])
@@ -109,16 +113,18 @@ class LongFormSpeakerClustering:
     def forward_infer(self, embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
                       oracle_num_speakers: int = -1, max_rp_threshold: float = 0.15, max_num_speakers: int = 8,
                       sparse_search_volume: int = 30, fixed_thres: float = -1.0, chunk_cluster_count=50,
-                      embeddings_per_chunk=10000) -> torch.Tensor:
+                      embeddings_per_chunk=10000, scale_mapping=None) -> torch.Tensor:
+        """scale_mapping: optional precomputed clustering.get_argmin_mat(timestamps) (pure index arithmetic on the window
+        times; the diarizer computes it on the host while the GPU is still embedding)."""
         if embeddings_per_chunk is not None and int(torch.max(multiscale_segment_counts)) > embeddings_per_chunk:
             return self.long_forward_infer(embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
                                            oracle_num_speakers, max_rp_threshold, max_num_speakers, sparse_search_volume, fixed_thres,
-                                           int(chunk_cluster_count), int(embeddings_per_chunk))
+                                           int(chunk_cluster_count), int(embeddings_per_chunk), scale_mapping)
         labels = self.speaker_clustering.forward_infer(
             embeddings_in_scales=embeddings_in_scales, timestamps_in_scales=timestamps_in_scales,
             multiscale_segment_counts=multiscale_segment_counts, multiscale_weights=multiscale_weights,
             oracle_num_speakers=oracle_num_speakers, max_rp_threshold=max_rp_threshold, max_num_speakers=max_num_speakers,
-            sparse_search_volume=sparse_search_volume, fixed_thres=fixed_thres)
+            sparse_search_volume=sparse_search_volume, fixed_thres=fixed_thres, scale_mapping=scale_mapping)
         self.timestamps_in_scales = self.speaker_clustering.timestamps_in_scales
         return labels
 
@@ -174,11 +180,11 @@ class LongFormSpeakerClustering:
 
     def long_forward_infer(self, embeddings_in_scales, timestamps_in_scales, multiscale_segment_counts, multiscale_weights,
                            oracle_num_speakers, max_rp_threshold, max_num_speakers, sparse_search_volume, fixed_thres,
-                           chunk_cluster_count, embeddings_per_chunk) -> torch.Tensor:
+                           chunk_cluster_count, embeddings_per_chunk, scale_mapping=None) -> torch.Tensor:
         self.check_input(embeddings_per_chunk, chunk_cluster_count, max_num_speakers)
         self.embeddings_in_scales, self.timestamps_in_scales = split_input_data(embeddings_in_scales, timestamps_in_scales,
                                                                                 multiscale_segment_counts)
-        emb, _ = get_scale_interpolated_embs(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales)
+        emb, _ = get_scale_interpolated_embs(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales, scale_mapping)
         n_total = emb.shape[0]
         total_emb: List[torch.Tensor] = []
         window_range_list: List[Tuple[int, int]] = []
@@ -190,10 +196,7 @@ class LongFormSpeakerClustering:
             from . import sharding
 
             rank, world = sharding.rank_world()
-        per_chunk = {}
-        for win_index in range(n_chunks):
-            if win_index % world != rank:
-                continue
+        def cluster_chunk(win_index: int, clusterer: SpeakerClustering):
             if embeddings_per_chunk * (win_index + 1) > n_total:  # last chunk is aligned to the end (overlaps the previous one)
                 offset_index = n_total - embeddings_per_chunk
             else:
@@ -208,15 +211,48 @@ class LongFormSpeakerClustering:
                 mat = _fuse([cos], [ident], [mm], [1.0], emb_part.shape[0])
                 del cos
                 overcluster_count = min(chunk_cluster_count, mat.shape[0])
-                Y_part = self.speaker_clustering.forward_unit_infer(
+                Y_part = clusterer.forward_unit_infer(
                     mat=mat, oracle_num_speakers=overcluster_count, max_rp_threshold=max_rp_threshold,
                     max_num_speakers=chunk_cluster_count, sparse_search_volume=sparse_search_volume)
             num_to_be_merged = int(min(embeddings_per_chunk, emb_part.shape[0]) - chunk_cluster_count)
             y_host = Y_part.cpu()
             min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
             class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
-            per_chunk[win_index] = self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
-            del mat
+            return self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
+
+        mine = [w for w in range(n_chunks) if w % world == rank]
+        n_streams = min(len(mine), max(1, int(os.environ.get("B200D_CHUNK_STREAMS", "2"))))
+        per_chunk = {}
+        if n_streams <= 1:
+            for w in mine:
+                per_chunk[w] = cluster_chunk(w, self.speaker_clustering)
+        else:
+            # chunks are independent and each one's kernels (80-CTA GEMMs, one-CTA Jacobi, host round trips) leave most of
+            # the GPU idle: run them on separate streams from separate host threads (ctypes releases the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+
+            main = torch.cuda.current_stream()
+            if len(_CHUNK_STREAMS) < n_streams:
+                _CHUNK_STREAMS.extend(torch.cuda.Stream() for _ in range(n_streams - len(_CHUNK_STREAMS)))
+            streams = _CHUNK_STREAMS[:n_streams]
+            for st in streams:
+                st.wait_stream(main)
+            dev_index = emb.device.index
+
+            def work(w, st):
+                torch.cuda.set_device(dev_index)
+                with torch.cuda.stream(st), torch.no_grad():
+                    merged_list, mapping_list = cluster_chunk(w, SpeakerClustering())
+                    for m in merged_list:
+                        m.record_stream(main)
+                    return merged_list, mapping_list
+
+            with ThreadPoolExecutor(max_workers=n_streams) as pool:
+                futures = {w: pool.submit(work, w, streams[i % n_streams]) for i, w in enumerate(mine)}
+                for w, fut in futures.items():
+                    per_chunk[w] = fut.result()
+            for st in streams:
+                main.wait_stream(st)
         if world > 1:  # tiny payload: <= chunk_cluster_count x 192 floats + the index lists of one chunk per entry
             payload = {w: ([m.cpu() for m in ml], mp) for w, (ml, mp) in per_chunk.items()}
             gathered = [None] * world

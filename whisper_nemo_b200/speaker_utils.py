@@ -156,7 +156,7 @@ def get_embs_and_timestamps(multiscale_embeddings_and_timestamps: dict, multisca
             if len(e[uniq_id]) != len(t[uniq_id]):
                 raise ValueError("Mismatch of counts between embedding vectors and timestamps")
             embs.append(e[uniq_id])
-            stamps.append(torch.tensor(t[uniq_id]))
+            stamps.append(t[uniq_id] if torch.is_tensor(t[uniq_id]) else torch.tensor(t[uniq_id]))
             counts.append(e[uniq_id].shape[0])
         out[uniq_id] = {"multiscale_weights": torch.tensor(weights).unsqueeze(0).float(), "embeddings": torch.cat(embs, dim=0),
                         "timestamps": torch.cat(stamps, dim=0), "multiscale_segment_counts": torch.tensor(counts)}
