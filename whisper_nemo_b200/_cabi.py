@@ -164,8 +164,11 @@ def call(name, *args):
         e1.record()
         work, key = 0.0, name
         if name == "b200d_gemm_f16":
-            work = 2.0 * args[4] * args[5] * args[6]
-            key = f"{name}[{_EPI_NAMES[args[9]._obj.mode]}]"
+            M, N, mode = args[4], args[5], args[9]._obj.mode
+            work = 2.0 * M * N * args[6]
+            # same rule as b200d_gemm_f16's dispatch (gemm_tcgen05.cu): which launches run the CTA-pair kernel
+            pair = N % 256 == 0 and ((M >= 4096) if mode == EPI_CHEB else (-(-M // 256) * (N // 256) >= 74))
+            key = f"{name}[{_EPI_NAMES[mode]}{'|2cta' if pair else ''}]"
         elif name == "b200d_small_eig":
             key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"
         _profile.setdefault(key, []).append((e0, e1, work))
