@@ -120,6 +120,11 @@ typedef struct b200d_gemm_epilogue {
 
 int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K,
                    void* out, int32_t ldo, const b200d_gemm_epilogue* epi, void* stream);
+/* Large GEMMs run on a cluster-launched CTA-pair kernel (tcgen05 cta_group::2) that must not share the device with
+ * kernels of other streams (observed device deadlock against a register-heavy kernel on B200 / driver 580.159).  A host
+ * that is about to use several streams calls this with 0 (every GEMM then takes the 1-CTA kernel) and restores the
+ * returned previous value afterwards.  Process-wide; returns the previous setting.                                */
+int b200d_gemm_set_pair_kernel(int32_t enable);
 
 /* SqueezeExcite = b200d_time_stats(with_std=0) -> b200d_gemm_f16(fc.0, BIAS_RELU with zero bias)
  * -> b200d_gemm_f16(fc.2, SIGMOID_F32) -> gate float32 [n_seg][C].                                 */

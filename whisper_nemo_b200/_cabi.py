@@ -47,6 +47,7 @@ _SIGNATURES = {
     "b200d_depthwise_conv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                  POINTER(GemmEpilogue), c_void_p]),
+    "b200d_gemm_set_pair_kernel": (c_int32, [c_int32]),
     "b200d_time_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_se_apply_relu": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_se_apply_relu_stats": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -176,6 +177,19 @@ def call(name, *args):
         rc = fn(*args)
     launch_count += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
+
+
+class single_cta_gemms:
+    """Context manager around a multi-stream region: the cluster-launched CTA-pair GEMM is switched off inside
+    (see b200d_gemm_set_pair_kernel in include/b200d.h)."""
+
+    def __enter__(self):
+        self.prev = load().b200d_gemm_set_pair_kernel(0)
+        return self
+
+    def __exit__(self, *exc):
+        load().b200d_gemm_set_pair_kernel(self.prev)
+        return False
 
 
 def require_device():

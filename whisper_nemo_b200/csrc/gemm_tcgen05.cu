@@ -15,6 +15,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -572,6 +573,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+// The cluster-launched CTA-pair kernel must have the GPU to itself: on B200 / driver 580.159 a __cluster_dims__(2)
+// tcgen05 kernel sharing the device with a register-heavy kernel of ANOTHER stream (depthwise_kernel: 3 CTAs x 20 k
+// registers per SM) deadlocked the device (tools/concurrency_check.py big2cta depthwise), while the cta_group::1 kernel
+// in the same situation is fine.  Hosts that run several streams switch the pair kernel off for that region.
+static std::atomic<int> g_pair_kernel_enabled{1};
 static std::once_flag g_encode_once;
 
 static EncodeTiledFn get_encode() {
@@ -666,6 +672,10 @@ static int dispatch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
 
 using namespace b200d;
 
+extern "C" int b200d_gemm_set_pair_kernel(int32_t enable) {
+  return g_pair_kernel_enabled.exchange(enable ? 1 : 0);
+}
+
 extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K, void* out,
                               int32_t ldo, const b200d_gemm_epilogue* epi, void* stream) {
   B200D_CHECK_ARG(A && W && out && epi);
@@ -689,7 +699,8 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
   const int block_n = (N % 256 == 0) ? 256 : 128;
   // CTA-pair kernel when there is at least one 256 x 256 tile per TPC (the large pointwise convs), and for the
   // Chebyshev products of 64-vector blocks on large graphs (L2-traffic bound: the pair halves the W bytes per SM)
-  static const bool allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
+  static const bool env_allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
+  const bool allow_2cta = env_allow_2cta && g_pair_kernel_enabled.load(std::memory_order_relaxed) != 0;
   const long long tiles2 = static_cast<long long>((M + 255) / 256) * (N / 256);
   const bool use_2cta = allow_2cta && block_n == 256 && (mode == B200D_EPI_CHEB ? M >= 4096 : tiles2 >= kNumSMs / 2);
   CUtensorMap ta, tb;

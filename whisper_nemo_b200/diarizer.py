@@ -90,6 +90,7 @@ class ClusteringDiarizer:
                                                            _get(p, "multiscale_weights"))
         self._cluster_params = _get(self.cfg, "diarizer.clustering.parameters")
         self.shard_windows = bool(shard_windows)
+        self._embed_streams: List[torch.cuda.Stream] = []
         self._speaker_model = self._init_speaker_model(speaker_model)
         self.stage_ms: Dict[str, float] = {}
         self.results: Dict[str, dict] = {}
@@ -226,6 +227,42 @@ class ClusteringDiarizer:
             out.index_copy_(0, idx_t, emb)
         return out
 
+    def _embed_all_scales(self, wav_dev: torch.Tensor) -> Dict[int, torch.Tensor]:
+        """Embeddings of every scale.  B200D_EMBED_STREAMS > 1 keeps several scales in flight on separate streams (own
+        activation workspaces); off by default: the multi-stream region has to give up the CTA-pair GEMM (see
+        _cabi.single_cta_gemms), which costs more than the overlap wins."""
+        n_streams = min(len(self._scales), max(1, int(os.environ.get("B200D_EMBED_STREAMS", "1"))))
+        if n_streams <= 1 or self.shard_windows:
+            return {k: self._extract_embeddings(plan, wav_dev) for k, plan in self._scales.items()}
+        from concurrent.futures import ThreadPoolExecutor
+
+        main = torch.cuda.current_stream()
+        if len(self._embed_streams) < n_streams:
+            self._embed_streams.extend(torch.cuda.Stream() for _ in range(n_streams - len(self._embed_streams)))
+        streams = self._embed_streams[:n_streams]
+        for st in streams:
+            st.wait_stream(main)
+        dev_index = self.device.index
+        free = list(streams)
+
+        def work(scale_idx, plan):
+            torch.cuda.set_device(dev_index)
+            st = free.pop()  # list.pop / append are atomic under the GIL; at most n_streams workers run
+            try:
+                with torch.cuda.stream(st), torch.no_grad():
+                    out = self._extract_embeddings(plan, wav_dev)
+                    out.record_stream(main)
+                    return scale_idx, out
+            finally:
+                free.append(st)
+
+        main.synchronize()
+        with _cabi.single_cta_gemms(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+            results = dict(f.result() for f in [pool.submit(work, k, plan) for k, plan in self._scales.items()])
+            for st in streams:
+                st.synchronize()
+        return results
+
     def _cluster_one(self, uniq_id: str, e: dict):
         from .longform import LongFormSpeakerClustering
 
@@ -261,8 +298,9 @@ class ClusteringDiarizer:
         timer.stop(h)
         h = timer.start("embed")
         per_scale = {}
+        scale_embs = self._embed_all_scales(wav_dev)
         for scale_idx, plan in self._scales.items():
-            embs = self._extract_embeddings(plan, wav_dev)
+            embs = scale_embs[scale_idx]
             e_by = {}
             for u, sel in plan["rows"].items():
                 contiguous = len(sel) == int(sel[-1]) - int(sel[0]) + 1

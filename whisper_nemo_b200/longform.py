@@ -247,12 +247,13 @@ class LongFormSpeakerClustering:
                         m.record_stream(main)
                     return merged_list, mapping_list
 
-            with ThreadPoolExecutor(max_workers=n_streams) as pool:
+            main.synchronize()  # nothing of the single-stream phase (CTA-pair GEMMs) may still be running
+            with _cabi.single_cta_gemms(), ThreadPoolExecutor(max_workers=n_streams) as pool:
                 futures = {w: pool.submit(work, w, streams[i % n_streams]) for i, w in enumerate(mine)}
                 for w, fut in futures.items():
                     per_chunk[w] = fut.result()
-            for st in streams:
-                main.wait_stream(st)
+                for st in streams:
+                    st.synchronize()  # the multi-stream region is drained before the pair kernel is allowed again
         if world > 1:  # tiny payload: <= chunk_cluster_count x 192 floats + the index lists of one chunk per entry
             payload = {w: ([m.cpu() for m in ml], mp) for w, (ml, mp) in per_chunk.items()}
             gathered = [None] * world

@@ -321,13 +321,15 @@ class TitaNetB200:
         self.device = torch.device(device)
         self.pk = pack_weights(state_dict, self.device)
         self.max_frames = max_frames
-        self._ws = None
+        self._ws = {}  # one activation workspace per launching stream (concurrent scales must not share buffers)
 
     def _workspace(self, T):
+        key = torch.cuda.current_stream().cuda_stream
         max_segs = max(1, self.max_frames // T)
-        if self._ws is None or self._ws.max_segs < max_segs:
-            self._ws = Workspace(self.max_frames, max(max_segs, 1024), self.device)
-        return self._ws
+        ws = self._ws.get(key)
+        if ws is None or ws.max_segs < max_segs:
+            ws = self._ws[key] = Workspace(self.max_frames, max(max_segs, 1024), self.device)
+        return ws
 
     @torch.no_grad()
     def embed_segments(self, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int, taps: dict = None):
