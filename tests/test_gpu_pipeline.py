@@ -356,3 +356,63 @@ def test_short_and_ragged_speech_regions_match_oracle(dev, oracle_model, weights
         embeddings_per_chunk=clus.embeddings_per_chunk).cpu()
     assert best_permutation_agreement(got.numpy(), ro["labels"]) == 1.0
     assert os.path.exists(tmp_path / "b200" / "pred_rttms" / "mono_file.rttm")
+
+
+def test_two_hour_recording_longform_properties(dev, weights, tmp_path):
+    """Towards BASELINE config #5 (multi-hour recording): 2 hours, 6 speakers, telephonic YAML -> 28 800 base windows, three
+    long-form chunks clustered on concurrent streams.  Size-independent properties only (no CPU oracle at this size)."""
+    from whisper_nemo_b200 import ClusteringDiarizer
+
+    cfg, wav, turns = make_session_cfg(tmp_path, "telephonic", 7200.0, 6, seed=55)
+    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights)
+    diar.diarize()
+    r = diar.results["mono_file"]
+    lab1 = r["labels"].copy()
+    k = len(set(lab1.tolist()))
+    ts = r["timestamps"].numpy()
+    mid = ts.mean(1)
+    truth = np.full(len(mid), -1)
+    for a, b, s in turns:
+        truth[(mid >= a) & (mid <= b)] = s
+    ok = truth >= 0
+    agree = best_permutation_agreement(lab1[ok], truth[ok])
+    print(f"2 h telephonic: N={len(lab1)} speakers {k} agreement with the 6 true speakers {agree:.4f} stages {diar.stage_ms}")
+    assert len(lab1) > 20000 and r["fused_affinity"] is None
+    assert 2 <= k <= 8
+    assert set(np.unique(lab1).tolist()) == set(range(k))
+    diar.run_device()
+    assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
+
+
+def test_longform_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path):
+    """The long-form branch on real (synthetic-audio) embeddings: 5 minutes, 4 speakers, telephonic YAML with
+    embeddings_per_chunk lowered to 500 (3 chunks, over-clustered to 20 each) on both sides."""
+    from oracle.clustering_diarizer import OracleClusteringDiarizer
+    from whisper_nemo_b200 import ClusteringDiarizer
+
+    kw = dict(embeddings_per_chunk=500, chunk_cluster_count=20)
+    cfg_o, _, _ = make_session_cfg(tmp_path / "oracle", "telephonic", 300.0, 4, seed=12, **kw)
+    cfg_g, _, turns = make_session_cfg(tmp_path / "b200", "telephonic", 300.0, 4, seed=12, **kw)
+    state = torch.get_rng_state()
+    oracle = OracleClusteringDiarizer(cfg_o, oracle_model)
+    oracle.diarize()
+    torch.set_rng_state(state)
+    diar = ClusteringDiarizer(cfg=cfg_g, speaker_model=weights)
+    diar.diarize()
+    ro, rg = oracle.results["mono_file"], diar.results["mono_file"]
+    assert ro["fused_affinity"] is None and rg["fused_affinity"] is None  # both took the long-form branch
+    eo = oracle.embs_and_timestamps["mono_file"]
+    # stage parity: the oracle's embeddings through the B200 long-form clustering
+    from whisper_nemo_b200.longform import LongFormSpeakerClustering
+
+    clus = cfg_g.diarizer.clustering.parameters
+    args = dict(max_num_speakers=int(clus.max_num_speakers), max_rp_threshold=float(clus.max_rp_threshold),
+                sparse_search_volume=int(clus.sparse_search_volume), chunk_cluster_count=20, embeddings_per_chunk=500)
+    stage = LongFormSpeakerClustering().forward_infer(eo["embeddings"].to(dev), eo["timestamps"], eo["multiscale_segment_counts"],
+                                                      eo["multiscale_weights"], **args).cpu()
+    stage_agree = best_permutation_agreement(stage.numpy(), ro["labels"])
+    e2e_agree = best_permutation_agreement(rg["labels"], ro["labels"])
+    print(f"long-form 5 min: N={len(ro['labels'])} speakers oracle {len(set(ro['labels'].tolist()))} stage {len(set(stage.tolist()))} "
+          f"e2e {len(set(rg['labels'].tolist()))}; agreement stage {stage_agree:.4f} end-to-end {e2e_agree:.4f}")
+    assert len(set(stage.tolist())) == len(set(ro["labels"].tolist()))
+    assert stage_agree >= 0.999

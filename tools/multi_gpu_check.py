@@ -27,7 +27,7 @@ def main():
     domain = sys.argv[2] if len(sys.argv) > 2 else "telephonic"
     weights = checkpoint.calibrated(dev)
     work = os.path.join(tempfile.gettempdir(), f"b200d_mgpu_r{rank}")
-    cfg, _, _ = make_session_cfg(work, domain, seconds, 4, seed=7)
+    cfg, _, _ = make_session_cfg(work, domain, seconds, 4 if seconds < 3000 else 8, seed=7)
     results = {}
     for mode in ("single", "sharded"):
         diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights, shard_windows=(mode == "sharded"))
