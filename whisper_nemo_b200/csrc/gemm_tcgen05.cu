@@ -152,7 +152,7 @@ __device__ __forceinline__ void unpack8_f16(uint4 u, float* v) {
 }
 
 // Epilogue on 32 consecutive columns [n0, n0+32) of one row.
-template <int MODE>
+template <int MODE, bool STORE = true>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int n0, float* acc) {
   const b200d_gemm_epilogue& e = p.epi;
   if constexpr (MODE == B200D_EPI_BIAS || MODE == B200D_EPI_BIAS_RELU || MODE == B200D_EPI_BIAS_F32) {
@@ -193,7 +193,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 1.f / (1.f + __expf(-acc[j]));
   }
-  if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
+  if constexpr (!STORE) {
+    return;
+  } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
     float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -393,7 +395,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 constexpr int B2_BYTES = 128 * BLOCK_K * 2;             // this CTA's half of the 256-row W tile
 constexpr int STAGES2 = 6;
-constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_BYTES + B2_BYTES) + 256;
+// fp16 epilogues stage 32 rows x 64 columns per warp in shared memory (row pitch 144 B: conflict-free both ways) and
+// write them out as full 128-byte lines: the row-per-thread 16-byte stores of the first version reached only
+// 1.6 TB/s on the store-bound K = 128 GEMMs (ncu r01 v3: attention projection 583 MB in 359 us)
+constexpr int STAGE_PITCH = 144;
+constexpr int STAGE_BYTES = 4 * 32 * STAGE_PITCH;
+constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_BYTES + B2_BYTES) + 256 + STAGE_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -441,6 +448,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tfull = empty + STAGES2;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(full) + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -536,7 +544,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if constexpr (MODE == B200D_EPI_CHEB) {
 #pragma unroll 1
         for (int t = 0; t < BN / 128; ++t) cheb_epilogue_tile(p, row, t_row + t * 128, n_blk * (BN / 128) + t);
-      } else {
+      } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
@@ -547,6 +555,35 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
             epilogue_chunk<MODE>(p, row, n_blk * BN + c * 32, acc_f);
+          }
+        }
+      } else {
+        uint8_t* stage = stage_base + wq * 32 * STAGE_PITCH;
+        const int row_w0 = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32;  // first row of this warp
+        __half* out16 = reinterpret_cast<__half*>(p.out);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          float acc_f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
+          if (row < p.M) epilogue_chunk<MODE, false>(p, row, n_blk * BN + c * 32, acc_f);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(stage + lane * STAGE_PITCH + (c & 1) * 64 + j * 2) = pack8_f16(acc_f + j);
+          if (c & 1) {
+            __syncwarp();
+            const int col0 = n_blk * BN + (c - 1) * 32;  // 64 columns = 128 bytes per row
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3), seg = lane & 7;
+              const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + seg * 16);
+              if (row_w0 + rr < p.M)
+                *reinterpret_cast<uint4*>(out16 + static_cast<size_t>(row_w0 + rr) * p.ldo + col0 + seg * 8) = v;
+            }
+            __syncwarp();
           }
         }
       }
