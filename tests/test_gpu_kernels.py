@@ -276,3 +276,41 @@ def test_multiscale_affinity_matches_oracle(dev):
     err = (got.cpu() - want).abs().max().item()
     print(f"fused affinity [0, {weights.sum().item():.0f}] range: max abs err {err:.3e}")
     assert err <= 1e-4  # BASELINE.json: fused affinity within 1e-4 absolute (range [0, sum w] = [0, 3])
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (1000, 1024, 1024), (20011, 1024, 1024), (19000, 3072, 128), (513, 384, 3072)])
+def test_gemm_epilogues_match_torch(dev, M, N, K):
+    """tcgen05 GEMM (1-CTA and CTA-pair kernels; the pair kernel takes the shapes with >= 74 tiles of 256 x 256) against
+    torch fp32 on the same fp16 operands: every fused epilogue, ragged M."""
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200 import titanet as tn
+
+    g = torch.Generator().manual_seed(M + N)
+    T = 151
+    A = (torch.randn(M, K, generator=g) * 0.5).half().to(dev)
+    W = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).half().to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = A.float() @ W.float().t()
+    n_seg = (M + T - 1) // T
+    out = torch.empty(M, N, dtype=torch.float16, device=dev)
+    tol = 2e-3 * max(1.0, ref.abs().max().item())  # fp16 output rounding
+    tn.gemm(A, W, out, _cabi.EPI_BIAS, bias=bias)
+    assert (out.float() - (ref + bias)).abs().max().item() <= tol
+    tn.gemm(A, W, out, _cabi.EPI_BIAS_RELU, bias=bias)
+    assert (out.float() - torch.relu(ref + bias)).abs().max().item() <= tol
+    aux = torch.randn(M, N, generator=g).half().to(dev)
+    gate = torch.rand(n_seg, N, generator=g).to(dev)
+    tn.gemm(A, W, out, _cabi.EPI_SE_RES, bias=bias, rowvec=gate, aux16=aux, rows_per_seg=T)
+    want = torch.relu(aux.float() * gate.repeat_interleave(T, 0)[:M] + ref + bias)
+    assert (out.float() - want).abs().max().item() <= tol
+    out32 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    tn.gemm(A, W, out32, _cabi.EPI_BIAS_F32, bias=bias)
+    assert (out32 - (ref + bias)).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    tn.gemm(A, W, out32, _cabi.EPI_SIGMOID_F32)
+    assert (out32 - torch.sigmoid(ref)).abs().max().item() <= 1e-5
+    if N % 128 == 0 and N <= 256:
+        scale, shift = (torch.rand(N, generator=g) + 0.5).to(dev), (torch.randn(N, generator=g) * 0.1).to(dev)
+        rb = torch.randn(n_seg, N, generator=g).to(dev)
+        tn.gemm(A, W, out, _cabi.EPI_TDNN, scale=scale, shift=shift, rowvec=rb, rows_per_seg=T)
+        want = torch.tanh(scale * torch.relu(ref + rb.repeat_interleave(T, 0)[:M]) + shift)
+        assert (out.float() - want).abs().max().item() <= 2e-3

@@ -133,6 +133,7 @@ KERNELS_PER_CALL = {
     "b200d_resid_norms": 1, "b200d_kmeans": 1,
 }
 launch_count = 0
+_pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None  # mirrors b200d_gemm_set_pair_kernel for the profile labels
 _profile = None  # {name: [(event0, event1, work)]} while a profiled step runs
 
 
@@ -168,7 +169,7 @@ def call(name, *args):
             M, N, mode = args[4], args[5], args[9]._obj.mode
             work = 2.0 * M * N * args[6]
             # same rule as b200d_gemm_f16's dispatch (gemm_tcgen05.cu): which launches run the CTA-pair kernel
-            pair = N % 256 == 0 and ((M >= 4096) if mode == EPI_CHEB else (-(-M // 256) * (N // 256) >= 74))
+            pair = _pair_kernel_on and N % 256 == 0 and ((M >= 4096) if mode == EPI_CHEB else (-(-M // 256) * (N // 256) >= 74))
             key = f"{name}[{_EPI_NAMES[mode]}{'|2cta' if pair else ''}]"
         elif name == "b200d_small_eig":
             key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"
@@ -184,11 +185,15 @@ class single_cta_gemms:
     (see b200d_gemm_set_pair_kernel in include/b200d.h)."""
 
     def __enter__(self):
+        global _pair_kernel_on
         self.prev = load().b200d_gemm_set_pair_kernel(0)
+        _pair_kernel_on = False
         return self
 
     def __exit__(self, *exc):
+        global _pair_kernel_on
         load().b200d_gemm_set_pair_kernel(self.prev)
+        _pair_kernel_on = bool(self.prev)
         return False
 
 
