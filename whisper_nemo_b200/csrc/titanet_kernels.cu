@@ -114,7 +114,17 @@ __global__ void __launch_bounds__(64 * kTsSlices) time_stats_kernel(const __half
   const __half* xs = x + static_cast<size_t>(seg) * T * C + c;
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) {
-    for (int t = slice; t < T; t += kTsSlices) {
+    int t = slice;
+    for (; t + 3 * kTsSlices < T; t += 4 * kTsSlices) {  // four independent row requests in flight per thread
+      float v0[4], v1[4], v2[4], v3[4];
+      load4h(xs + static_cast<size_t>(t) * C, v0);
+      load4h(xs + static_cast<size_t>(t + kTsSlices) * C, v1);
+      load4h(xs + static_cast<size_t>(t + 2 * kTsSlices) * C, v2);
+      load4h(xs + static_cast<size_t>(t + 3 * kTsSlices) * C, v3);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += (v0[q] + v1[q]) + (v2[q] + v3[q]);
+    }
+    for (; t < T; t += kTsSlices) {
       float v[4];
       load4h(xs + static_cast<size_t>(t) * C, v);
 #pragma unroll
@@ -206,14 +216,26 @@ __global__ void __launch_bounds__(64 * kTsSlices) se_apply_stats_kernel(const __
     __half* ys = y + static_cast<size_t>(seg) * T * C + c;
     const float4 gt = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(seg) * C + c));
     const float gv[4] = {gt.x, gt.y, gt.z, gt.w};
-    for (int t = slice; t < T; t += kTsSlices) {
-      float v[4];
-      load4h(xs + static_cast<size_t>(t) * C, v);
+    auto body = [&](int t, float (&v)[4]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) v[q] = __half2float(__float2half_rn(fmaxf(v[q] * gv[q], 0.f)));
       store4h(ys + static_cast<size_t>(t) * C, v);
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s1[q] += v[q]; s2[q] = fmaf(v[q], v[q], s2[q]); }
+    };
+    int t = slice;
+    for (; t + 3 * kTsSlices < T; t += 4 * kTsSlices) {
+      float v0[4], v1[4], v2[4], v3[4];
+      load4h(xs + static_cast<size_t>(t) * C, v0);
+      load4h(xs + static_cast<size_t>(t + kTsSlices) * C, v1);
+      load4h(xs + static_cast<size_t>(t + 2 * kTsSlices) * C, v2);
+      load4h(xs + static_cast<size_t>(t + 3 * kTsSlices) * C, v3);
+      body(t, v0); body(t + kTsSlices, v1); body(t + 2 * kTsSlices, v2); body(t + 3 * kTsSlices, v3);
+    }
+    for (; t < T; t += kTsSlices) {
+      float v[4];
+      load4h(xs + static_cast<size_t>(t) * C, v);
+      body(t, v);
     }
   }
 #pragma unroll
@@ -252,10 +274,7 @@ __global__ void __launch_bounds__(64 * kTsSlices) attn_pool_kernel(const __half*
 #pragma unroll
   for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; z[q] = 0.f; s1[q] = 0.f; s2[q] = 0.f; }
   if (active) {
-    for (int t = slice; t < T; t += kTsSlices) {
-      float xv[4], ev[4];
-      load4h(xs + static_cast<size_t>(t) * C, xv);
-      load4h(es + static_cast<size_t>(t) * C, ev);
+    auto body = [&](const float (&xv)[4], const float (&ev)[4]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float mn = fmaxf(m[q], ev[q]);
@@ -266,6 +285,21 @@ __global__ void __launch_bounds__(64 * kTsSlices) attn_pool_kernel(const __half*
         s2[q] = s2[q] * r + wgt * xv[q] * xv[q];
         m[q] = mn;
       }
+    };
+    int t = slice;
+    for (; t + 3 * kTsSlices < T; t += 4 * kTsSlices) {  // eight independent row requests in flight per thread
+      float x0[4], x1[4], x2[4], x3[4], e0[4], e1[4], e2[4], e3[4];
+      load4h(xs + static_cast<size_t>(t) * C, x0); load4h(es + static_cast<size_t>(t) * C, e0);
+      load4h(xs + static_cast<size_t>(t + kTsSlices) * C, x1); load4h(es + static_cast<size_t>(t + kTsSlices) * C, e1);
+      load4h(xs + static_cast<size_t>(t + 2 * kTsSlices) * C, x2); load4h(es + static_cast<size_t>(t + 2 * kTsSlices) * C, e2);
+      load4h(xs + static_cast<size_t>(t + 3 * kTsSlices) * C, x3); load4h(es + static_cast<size_t>(t + 3 * kTsSlices) * C, e3);
+      body(x0, e0); body(x1, e1); body(x2, e2); body(x3, e3);
+    }
+    for (; t < T; t += kTsSlices) {
+      float xv[4], ev[4];
+      load4h(xs + static_cast<size_t>(t) * C, xv);
+      load4h(es + static_cast<size_t>(t) * C, ev);
+      body(xv, ev);
     }
   }
 #pragma unroll
