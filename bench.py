@@ -37,6 +37,10 @@ WORKLOADS = {
     "general_10min": ("general", 600.0, 3, 3),
     "telephonic_4h": ("telephonic", 14400.0, 12, 4),
 }
+# BASELINE config #4: a batch of 10-minute recordings in ONE manifest, dealt to the ranks by sharding.assign_recordings
+# (strong scaling over the batch).  --batch R sets the batch size (64 in BASELINE.json; smaller values keep the host-side
+# synthesis short).
+BATCH_WORKLOAD = "general_10min_batch"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu --set full capture
 # profiles/r01_ncu_full_gemm2cta_depthwise_featurize_v2.txt: gemm_tcgen05_2cta_kernel<bias>, M = 120 649 frames (799 windows of
 # 151), N = K = 1024 -> 213.7 MB read + 166.2 MB written (algorithmic: 247 MB A + 2 MB W + 247 MB out; part of A is still L2-resident)
@@ -103,10 +107,23 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _session(work_dir, workload, seed):
-    """Synthetic recording + manifest + config for one rank (cached under work_dir)."""
+def _session(work_dir, workload, seed, batch=0, rank=0, world=1):
+    """Synthetic recording(s) + manifest + config for one rank.  Returns (cfg, seconds of audio this rank diarizes)."""
     from tests.util import make_session_cfg
 
+    if workload == BATCH_WORKLOAD:
+        from whisper_nemo_b200 import config, sharding, synth
+
+        mine = sharding.assign_recordings([600.0] * batch, world)[rank]
+        entries = []
+        for i in mine:
+            wav_path, rttm_path, _, _ = synth.make_session(work_dir, f"rec{i:03d}", 600.0, 3, seed=1000 + i)
+            entries.append({"audio_filepath": wav_path, "rttm_filepath": rttm_path})
+        cfg = config.load_config("general")
+        man = os.path.join(work_dir, "manifest.json")
+        synth.write_manifest(man, entries)
+        cfg.diarizer.manifest_filepath, cfg.diarizer.out_dir, cfg.diarizer.oracle_vad = man, work_dir, True
+        return cfg, 600.0 * len(mine)
     domain, seconds, speakers, _ = WORKLOADS[workload]
     cfg, wav, turns = make_session_cfg(work_dir, domain, seconds, speakers, seed)
     return cfg, seconds
@@ -138,7 +155,8 @@ def run_b200(args):
 
     workload = args.workload
     work_dir = os.path.join(tempfile.gettempdir(), f"b200d_bench_{workload}_r{rank}")
-    cfg, seconds = _session(work_dir, workload, seed=100 + rank)
+    cfg, seconds = _session(work_dir, workload, seed=100 + rank, batch=args.batch, rank=rank, world=world)
+    batch_mode = workload == BATCH_WORKLOAD
     weights = checkpoint.calibrated(dev)
     t0 = time.perf_counter()
     diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights).to("cuda")
@@ -215,17 +233,21 @@ def run_b200(args):
                        {"calls": v["calls"], "ms": round(v["ms"], 3), "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)})
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         hours = seconds / 3600.0
-        value = world * hours * args.steps / (dev_ms * 1e-3)
-        e2e_val = world * hours * args.steps / (e2e_ms * 1e-3)
-        res = diar.results["mono_file"]
+        total_hours = (600.0 * args.batch / 3600.0) if batch_mode else world * hours
+        value = total_hours * args.steps / (dev_ms * 1e-3)
+        e2e_val = total_hours * args.steps / (e2e_ms * 1e-3)
+        res = next(iter(diar.results.values()))
         cpu = cpu_baseline_sample(args, weights) if not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong" if batch_mode else "weak", "vs_baseline": None,
             "dtype": "fp16 tensor-core GEMMs (fp32 accumulate), fp32 featurizer/affinity/eigen", "data": "synthetic",
-            "config": {"workload": f"{workload} (BASELINE.json configs[{WORKLOADS[workload][3]}]): {seconds:.0f} s synthetic "
-                                   f"{WORKLOADS[workload][2]}-speaker 16 kHz recording per GPU, diar_infer_{WORKLOADS[workload][0]}.yaml, oracle VAD, "
-                                   "TitaNet-L random-init seed 1234", "windows_per_recording": windows, "frames_per_recording": frames,
+            "config": {"workload": (f"{workload} (BASELINE.json configs[3]): batch of {args.batch} x 600 s synthetic 3-speaker recordings in one "
+                                    f"manifest, diar_infer_general.yaml, dealt to {world} rank(s) by recording, oracle VAD, TitaNet-L random-init seed 1234")
+                       if batch_mode else
+                       (f"{workload} (BASELINE.json configs[{WORKLOADS[workload][3]}]): {seconds:.0f} s synthetic "
+                        f"{WORKLOADS[workload][2]}-speaker 16 kHz recording per GPU, diar_infer_{WORKLOADS[workload][0]}.yaml, oracle VAD, "
+                        "TitaNet-L random-init seed 1234"), "windows_per_recording": windows, "frames_per_recording": frames,
                        "base_scale_windows": int(len(res["labels"])), "speakers_found": int(res["debug"]["n_clusters"]),
                        "p_hat": int(res["debug"]["p_hat"]), "sharding": "one recording per GPU, no collective" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (waveform 230 MB/h, activations > 1 GB per step); no explicit flush"},
@@ -276,7 +298,7 @@ def _reference_weights():
 
 
 def cpu_baseline_sample(args, weights, sample_s=150.0):
-    domain, seconds, speakers, _ = WORKLOADS[args.workload]
+    domain, seconds, speakers, _ = WORKLOADS["general_10min" if args.workload == BATCH_WORKLOAD else args.workload]
     sample_s = min(sample_s, seconds)
     threads = os.cpu_count() or 1
     v, stages = _oracle_run(sample_s, domain, speakers, 100, weights, threads)
@@ -290,7 +312,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    domain, seconds, speakers, idx = WORKLOADS[args.workload]
+    domain, seconds, speakers, idx = WORKLOADS["general_10min" if args.workload == BATCH_WORKLOAD else args.workload]
     total = args.steps + args.warmup
     sample_s = min(seconds, 120.0 if total <= 8 else 60.0)
     threads = os.cpu_count() or 1
@@ -319,7 +341,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="meeting_1h", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="meeting_1h", choices=sorted(WORKLOADS) + [BATCH_WORKLOAD])
+    ap.add_argument("--batch", type=int, default=64, help="recordings in the batch workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profiling", action="store_true", help="allow < 3 warm-up steps and skip the extras (only for runs under ncu; never a bench value)")
     args = ap.parse_args()

@@ -15,7 +15,19 @@ from whisper_nemo_b200 import ClusteringDiarizer, checkpoint
 domain, seconds, reps = sys.argv[1], float(sys.argv[2]), int(sys.argv[3])
 dev = torch.device("cuda", 0)
 weights = checkpoint.calibrated(dev)
-cfg, _, _ = make_session_cfg(tempfile.mkdtemp(), domain, seconds, 3, seed=3)
+if domain.startswith("batch"):  # batchN: N recordings in one manifest (general YAML)
+    from whisper_nemo_b200 import config, synth
+
+    root = tempfile.mkdtemp()
+    entries = []
+    for i in range(int(domain[5:])):
+        w, r, _, _ = synth.make_session(root, f"rec{i}", seconds, 2 + i % 3, seed=40 + i)
+        entries.append({"audio_filepath": w, "rttm_filepath": r})
+    cfg = config.load_config("general")
+    synth.write_manifest(os.path.join(root, "m.json"), entries)
+    cfg.diarizer.manifest_filepath, cfg.diarizer.out_dir, cfg.diarizer.oracle_vad = os.path.join(root, "m.json"), root, True
+else:
+    cfg, _, _ = make_session_cfg(tempfile.mkdtemp(), domain, seconds, 3, seed=3)
 diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights)
 diar._prepare()
 wav = diar._wav_host.to(dev)

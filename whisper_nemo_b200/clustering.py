@@ -459,15 +459,17 @@ def kmeans_torch(X: torch.Tensor, num_clusters: int, threshold: float = 1e-4, it
 
 
 # ----------------------------------------------------------------------------- enhanced count
-def addAnchorEmb(emb: torch.Tensor, anchor_sample_n: int, anchor_spk_n: int, sigma: float) -> torch.Tensor:
-    """Host-side (CPU torch RNG, as upstream): synthetic anchor speakers for very short recordings."""
+def addAnchorEmb(emb: torch.Tensor, anchor_sample_n: int, anchor_spk_n: int, sigma: float, generator=None) -> torch.Tensor:
+    """Host-side (CPU torch RNG, as upstream): synthetic anchor speakers for very short recordings.  `generator`: a CPU
+    torch.Generator seeded like upstream's torch.manual_seed(seed) -- same stream of draws without touching (or racing on)
+    the process-global RNG when several recordings are clustered from separate threads."""
     emb_dim = emb.shape[1]
     std_org = torch.std(emb, dim=0)
     sigma = torch.tensor(sigma)
     new_emb_list = []
     for _ in range(anchor_spk_n):
-        emb_m = torch.tile(torch.randn(1, emb_dim), (anchor_sample_n, 1))
-        emb_noise = torch.randn(anchor_sample_n, emb_dim).T
+        emb_m = torch.tile(torch.randn(1, emb_dim, generator=generator), (anchor_sample_n, 1))
+        emb_noise = torch.randn(anchor_sample_n, emb_dim, generator=generator).T
         emb_noise = torch.matmul(torch.diag(std_org), emb_noise / torch.max(torch.abs(emb_noise), dim=0)[0].unsqueeze(0)).T
         new_emb_list.append(emb_m + sigma * emb_noise)
     new_emb_list.append(emb)
@@ -482,18 +484,14 @@ def getEnhancedSpeakerCount(emb: torch.Tensor, random_test_count: int = 5, ancho
     dev = emb.device
     emb_cpu = emb.detach().float().cpu()
     est: List[int] = []
-    rng_state = torch.get_rng_state()
-    try:
-        for seed in range(random_test_count):
-            torch.manual_seed(seed)
-            emb_aug = addAnchorEmb(emb_cpu, anchor_sample_n, anchor_spk_n, sigma).to(dev)
-            mat = getCosAffinityMatrix(emb_aug)
-            nmesc = NMESC(mat, max_num_speakers=emb.shape[0], max_rp_threshold=0.15, sparse_search=True, sparse_search_volume=10,
-                          fixed_thres=-1.0, nme_mat_size=300)
-            est_num_of_spk, _ = nmesc.forward()
-            est.append(int(est_num_of_spk))
-    finally:
-        torch.set_rng_state(rng_state)
+    for seed in range(random_test_count):
+        gen = torch.Generator(device="cpu").manual_seed(seed)  # == torch.manual_seed(seed) followed by global draws
+        emb_aug = addAnchorEmb(emb_cpu, anchor_sample_n, anchor_spk_n, sigma, generator=gen).to(dev)
+        mat = getCosAffinityMatrix(emb_aug)
+        nmesc = NMESC(mat, max_num_speakers=emb.shape[0], max_rp_threshold=0.15, sparse_search=True, sparse_search_volume=10,
+                      fixed_thres=-1.0, nme_mat_size=300)
+        est_num_of_spk, _ = nmesc.forward()
+        est.append(int(est_num_of_spk))
     return max(int(torch.mode(torch.tensor(est))[0].item()) - anchor_spk_n, 1)
 
 

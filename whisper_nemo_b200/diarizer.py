@@ -91,6 +91,7 @@ class ClusteringDiarizer:
         self._cluster_params = _get(self.cfg, "diarizer.clustering.parameters")
         self.shard_windows = bool(shard_windows)
         self._embed_streams: List[torch.cuda.Stream] = []
+        self._cluster_streams: List[torch.cuda.Stream] = []
         self._speaker_model = self._init_speaker_model(speaker_model)
         self.stage_ms: Dict[str, float] = {}
         self.results: Dict[str, dict] = {}
@@ -263,7 +264,7 @@ class ClusteringDiarizer:
                 st.synchronize()
         return results
 
-    def _cluster_one(self, uniq_id: str, e: dict):
+    def _cluster_one(self, uniq_id: str, e: dict, chunk_streams: int = None):
         from .longform import LongFormSpeakerClustering
 
         clus = self._cluster_params
@@ -273,7 +274,7 @@ class ClusteringDiarizer:
                 raise ValueError("Provided option as oracle num of speakers but num_speakers in manifest is null")
         else:
             num_speakers = -1
-        sc = LongFormSpeakerClustering(shard_chunks=self.shard_windows)
+        sc = LongFormSpeakerClustering(shard_chunks=self.shard_windows, chunk_streams=chunk_streams)
         labels = sc.forward_infer(
             embeddings_in_scales=e["embeddings"],
             timestamps_in_scales=e["timestamps"],
@@ -316,12 +317,39 @@ class ClusteringDiarizer:
             split = [int(x) for x in e["multiscale_segment_counts"].tolist()]
             e["scale_mapping"] = get_argmin_mat(list(torch.split(e["timestamps"], split, dim=0)))
         h = timer.start("cluster")
+        todo = [u for u in self.AUDIO_RTTM_MAP.keys() if u in self.embs_and_timestamps]
+        n_streams = min(len(todo), max(1, int(os.environ.get("B200D_RECORDING_STREAMS", "4"))))
         pending = {}
-        for uniq_id in self.AUDIO_RTTM_MAP.keys():
-            if uniq_id not in self.embs_and_timestamps:
-                continue
-            labels, sc = self._cluster_one(uniq_id, self.embs_and_timestamps[uniq_id])
-            pending[uniq_id] = (labels, sc)
+        if n_streams <= 1 or self.shard_windows:
+            for uniq_id in todo:
+                pending[uniq_id] = self._cluster_one(uniq_id, self.embs_and_timestamps[uniq_id])
+        else:
+            # recordings are independent and one recording's clustering is a chain of small kernels and host round trips:
+            # several recordings in flight on separate streams (multi-stream region: CTA-pair GEMM off, see _cabi)
+            from concurrent.futures import ThreadPoolExecutor
+
+            main = torch.cuda.current_stream()
+            if len(self._cluster_streams) < n_streams:
+                self._cluster_streams.extend(torch.cuda.Stream() for _ in range(n_streams - len(self._cluster_streams)))
+            free = list(self._cluster_streams[:n_streams])
+            dev_index = self.device.index
+            main.synchronize()
+
+            def work(uniq_id):
+                torch.cuda.set_device(dev_index)
+                st = free.pop()
+                try:
+                    with torch.cuda.stream(st), torch.no_grad():
+                        labels, sc = self._cluster_one(uniq_id, self.embs_and_timestamps[uniq_id], chunk_streams=1)
+                        labels.record_stream(main)
+                        st.synchronize()
+                        return uniq_id, (labels, sc)
+                finally:
+                    free.append(st)
+
+            with _cabi.single_cta_gemms(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+                for uniq_id, res in [f.result() for f in [pool.submit(work, u) for u in todo]]:
+                    pending[uniq_id] = res
         timer.stop(h)
         labels_host = {}
         self.results = {}

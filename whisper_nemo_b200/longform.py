@@ -88,10 +88,12 @@ def get_merge_quantity(num_to_be_removed: int, pre_clus_labels: torch.Tensor, mi
 
 
 class LongFormSpeakerClustering:
-    def __init__(self, shard_chunks: bool = False):
+    def __init__(self, shard_chunks: bool = False, chunk_streams: int = None):
         """shard_chunks: under torch.distributed, deal the (independent) chunks of the long-form path to the ranks and
-        gather their reduced embeddings; everything else runs replicated and gives the same labels on every rank."""
+        gather their reduced embeddings; everything else runs replicated and gives the same labels on every rank.
+        chunk_streams: chunks clustered concurrently on this many streams (default: B200D_CHUNK_STREAMS, 2)."""
         self.shard_chunks = bool(shard_chunks)
+        self.chunk_streams = chunk_streams
         self.speaker_clustering = SpeakerClustering()
         self.embeddings_in_scales: List[torch.Tensor] = []
         self.timestamps_in_scales: List[torch.Tensor] = []
@@ -221,7 +223,8 @@ class LongFormSpeakerClustering:
             return self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
 
         mine = [w for w in range(n_chunks) if w % world == rank]
-        n_streams = min(len(mine), max(1, int(os.environ.get("B200D_CHUNK_STREAMS", "2"))))
+        want = self.chunk_streams if self.chunk_streams is not None else int(os.environ.get("B200D_CHUNK_STREAMS", "2"))
+        n_streams = min(len(mine), max(1, want))
         per_chunk = {}
         if n_streams <= 1:
             for w in mine:
