@@ -205,9 +205,13 @@ def run_b200(args):
     elif rank == 0:
         diar.run_device(wav_dev=wav_dev, timers=True)
         stage_ms = dict(diar.stage_ms)
+        from whisper_nemo_b200 import clustering as _cl
+
+        _cl.spectral_log.clear()
         _cabi.start_profile()
         diar.run_device(wav_dev=wav_dev, timers=False)
         prof = _cabi.stop_profile()
+        spectral = list(_cl.spectral_log)
         g = {"calls": 0, "ms": 0.0, "work": 0.0}      # the dominant kernel: gemm_tcgen05_2cta_kernel (all its launches)
         g_all = {"calls": 0, "ms": 0.0, "work": 0.0}  # every tcgen05 GEMM launch, small projections included
         for key, v in prof.items():
@@ -255,6 +259,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(len(res["labels"]) * 8), "ms_per_step": round(e2e_ms / args.steps, 3)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}, "kernels_ms_per_step": kernels, "host_prepare_s": round(prep_s, 3),
+            "spectral_solver": spectral,
         }
         print(json.dumps(line))
     if world > 1:

@@ -246,6 +246,23 @@ def test_one_hour_meeting_properties(dev, weights, tmp_path):
     assert all(b[0] >= a[1] - 1e-3 for a, b in zip(rttm, rttm[1:]))
     diar.run_device()
     assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
+    # stage parity at FULL size: the same (GPU) embeddings through the CPU oracle's long-form clustering -- two dense
+    # eigh(10 000 x 10 000) + k-means(50) on the host, about a minute -- must give the labels of the device path
+    from oracle.longform_clustering import LongFormSpeakerClustering as OracleLF
+
+    e = diar.embs_and_timestamps["mono_file"]
+    clus = cfg.diarizer.clustering.parameters
+    torch.set_num_threads(os.cpu_count() or 8)
+    state = torch.get_rng_state()
+    want = OracleLF().forward_infer(e["embeddings"].cpu(), e["timestamps"], e["multiscale_segment_counts"], e["multiscale_weights"],
+                                    max_num_speakers=int(clus.max_num_speakers), max_rp_threshold=float(clus.max_rp_threshold),
+                                    sparse_search_volume=int(clus.sparse_search_volume), chunk_cluster_count=clus.chunk_cluster_count,
+                                    embeddings_per_chunk=clus.embeddings_per_chunk)
+    torch.set_rng_state(state)
+    stage_agree = best_permutation_agreement(lab1, want.numpy())
+    print(f"   oracle long-form clustering on the same embeddings: {len(set(want.tolist()))} speakers, label agreement {stage_agree:.5f}")
+    assert len(set(want.tolist())) == k
+    assert stage_agree >= 0.999
 
 
 def test_multi_recording_manifest_matches_oracle(dev, oracle_model, weights, tmp_path):

@@ -268,6 +268,7 @@ class SpectralStats:
 
 
 last_spectral_stats = SpectralStats()
+spectral_log: List[dict] = []  # one entry per bottom_eigvecs call (bounded; bench.py reports and clears it)
 
 
 def _gemm_cheb(A16, lda, vt_in, ldvt, n, nb4, out, deg, x, xprev, ca, cb, cc, vt_out):
@@ -395,6 +396,9 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         X.copy_(cur)
         cholqr(X)
         cholqr(X, vt[0])
+    if len(spectral_log) < 256:
+        spectral_log.append({"n": n, "k": k, "block": b, "outer": st.outer, "gemms": st.gemms, "resid": st.max_resid,
+                             "converged": st.converged, "history": [float(f"{h:.2e}") for h in history]})
     return X[:, :k].contiguous()
 
 
