@@ -433,3 +433,23 @@ def test_longform_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path
           f"e2e {len(set(rg['labels'].tolist()))}; agreement stage {stage_agree:.4f} end-to-end {e2e_agree:.4f}")
     assert len(set(stage.tolist())) == len(set(ro["labels"].tolist()))
     assert stage_agree >= 0.999
+
+
+def test_in_memory_waveform_api_matches_file_path(dev, weights, tmp_path):
+    """diarize_waveform(tensor, speech_regions) -- no disk round trip -- returns the (start_ms, end_ms, speaker) triples that
+    the reference builds by parsing the RTTM file of the manifest-driven call (diarize.py:209-216)."""
+    from whisper_nemo_b200 import ClusteringDiarizer
+
+    cfg, wav, turns = make_session_cfg(tmp_path, "telephonic", 75.0, 3, seed=17)
+    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights)
+    diar.diarize()
+    file_ts = []
+    with open(tmp_path / "pred_rttms" / "mono_file.rttm") as f:
+        for line in f.readlines():
+            lst = line.split(" ")
+            s = int(float(lst[5]) * 1000)
+            file_ts.append([s, s + int(float(lst[8]) * 1000), int(lst[11].split("_")[-1])])
+    regions = [(a, b) for a, b, _ in turns]
+    for source in (torch.from_numpy(wav), torch.from_numpy(wav).to(dev)):
+        mem_ts = ClusteringDiarizer(cfg=cfg, speaker_model=weights).diarize_waveform(source, regions)
+        assert mem_ts == file_ts

@@ -394,3 +394,63 @@ class ClusteringDiarizer:
         self._write_outputs()
         self.host_seconds = {"prepare": t1 - t0, "device_path": t2 - t1, "write": time.perf_counter() - t2}
         return None
+
+    # ------------------------------------------------------------------ in-memory fast path
+    def diarize_waveform(self, waveform, speech_regions, uniq_id: str = "mono_file", write_rttm_dir: Optional[str] = None):
+        """Diarize one recording that is already in memory -- no WAV / manifest / RTTM round trip through the disk.
+
+        The reference holds the 16 kHz mono waveform as a tensor before it writes `mono_file.wav` for NeMo
+        (diarize.py:187-196) and parses the RTTM back into (start_ms, end_ms, speaker) triples right after
+        (diarize.py:209-216); this entry point takes the tensor and returns those triples directly.
+          waveform        float32 [n] torch tensor (host or CUDA) or numpy array, 16 kHz mono
+          speech_regions  [(start_s, end_s), ...] from any VAD
+        Returns [[start_ms, end_ms, speaker_index], ...] exactly as diarize.py builds `speaker_ts` from the RTTM text
+        (same %.3f rounding).  `write_rttm_dir`: also write `<dir>/<uniq_id>.rttm`."""
+        wav = torch.as_tensor(waveform)
+        if wav.dim() != 1:
+            raise ValueError("waveform must be mono: shape [n]")
+        wav = wav.to(torch.float32)
+        n = int(wav.numel())
+        self.AUDIO_RTTM_MAP = {uniq_id: {"audio_filepath": uniq_id + ".wav", "rttm_filepath": None, "offset": 0, "duration": None,
+                                         "text": "-", "num_speakers": None, "uem_filepath": None, "ctm_filepath": None}}
+        self._wav_offset = {uniq_id: (0, n)}
+        regions = su._merge_on_grid([[float(a), float(b)] for a, b in speech_regions], 5)
+        total_s = n / self.sample_rate
+        self._scales = {}
+        for scale_idx, (window, shift) in self.multiscale_args_dict["scale_dict"].items():
+            entries = []
+            for a, b in regions:
+                a, b = max(a, 0.0), min(b, total_s)
+                if b <= a:
+                    continue
+                for start, dur in su.get_subsegments(offset=round(a, 5), window=window, shift=shift, duration=round(b - a, 5)):
+                    if dur > su.MIN_SUBSEGMENT_DURATION:
+                        entries.append({"audio_filepath": uniq_id + ".wav", "offset": start, "duration": dur, "label": "UNK", "uniq_id": uniq_id})
+            self._scales[scale_idx] = self._plan_scale(entries)
+        for plan in self._scales.values():
+            sel = np.arange(len(plan["uniq"]))
+            plan["rows"], plan["stamps"] = {}, {}
+            if len(sel):
+                plan["rows"][uniq_id] = sel
+                plan["stamps"][uniq_id] = torch.tensor([[plan["t0"][i], plan["t1"][i]] for i in sel])
+        if wav.is_cuda:
+            wav_dev = wav.contiguous()
+        else:
+            self._wav_host = wav.contiguous().pin_memory()
+            wav_dev = None
+        self.run_device(wav_dev=wav_dev)
+        r = self.results[uniq_id]
+        turns, _ = su.generate_cluster_labels(r["timestamps"], r["labels"])
+        r["rttm_labels"] = turns
+        if write_rttm_dir:
+            os.makedirs(write_rttm_dir, exist_ok=True)
+            su.labels_to_rttmfile(turns, uniq_id, write_rttm_dir)
+        speaker_ts = []
+        for line in turns:
+            start, end, speaker = line.split()
+            start_s = float("{:.3f}".format(float(start)))
+            dur_s = float("{:.3f}".format(float(end) - float(start)))
+            s_ms = int(start_s * 1000)
+            speaker_ts.append([s_ms, s_ms + int(dur_s * 1000), int(speaker.split("_")[-1])])
+        return speaker_ts
+
