@@ -302,22 +302,29 @@ __global__ void __launch_bounds__(256) right_mul_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ residuals
-// out[j] += sum_r (w[r][j] - theta[j] x[r][j])^2 ; out must be zeroed by the caller.
-__global__ void __launch_bounds__(256) resid_kernel(const float* __restrict__ w, const float* __restrict__ x, const float* __restrict__ theta,
-                                                     int n, int b, int ld, float* __restrict__ out) {
-  __shared__ float s_acc[4][kMaxB];
-  const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;  // 4 row groups x 64 columns
+// out[j] = sum_r (w[r][j] - theta[j] x[r][j])^2.  One CTA, 16 row groups x 64 columns, combined in a fixed order: the
+// value steers the convergence test of the subspace iteration, so it must not depend on the order of atomics (a flipped
+// iteration count would make two runs on the same input differ in the last bits of the eigenvectors).
+__global__ void __launch_bounds__(1024) resid_kernel(const float* __restrict__ w, const float* __restrict__ x, const float* __restrict__ theta,
+                                                      int n, int b, int ld, float* __restrict__ out) {
+  __shared__ float s_acc[16][kMaxB];
+  const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
   float acc = 0.f;
   if (col < b) {
     const float th = theta[col];
-    for (int r = blockIdx.x * 4 + rg; r < n; r += gridDim.x * 4) {
+    for (int r = rg; r < n; r += 16) {
       const float d = w[static_cast<size_t>(r) * ld + col] - th * x[static_cast<size_t>(r) * ld + col];
       acc = fmaf(d, d, acc);
     }
   }
   s_acc[rg][col] = acc;
   __syncthreads();
-  if (rg == 0 && col < b) atomicAdd(out + col, s_acc[0][col] + s_acc[1][col] + s_acc[2][col] + s_acc[3][col]);
+  if (rg == 0 && col < b) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) t += s_acc[g][col];
+    out[col] = t;
+  }
 }
 
 }  // namespace b200d
@@ -372,11 +379,7 @@ extern "C" int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld,
 extern "C" int b200d_resid_norms(const float* w, const float* x, const float* theta, int32_t n, int32_t b, int32_t ld, float* out,
                                  void* stream) {
   B200D_CHECK_ARG(w && x && theta && out && n > 0 && b > 0 && b <= kMaxB && ld >= b);
-  cudaStream_t s = as_stream(stream);
-  B200D_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * b, s));
-  int grid = (n + 3) / 4;
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  resid_kernel<<<grid, 256, 0, s>>>(w, x, theta, n, b, ld, out);
+  resid_kernel<<<1, 1024, 0, as_stream(stream)>>>(w, x, theta, n, b, ld, out);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
