@@ -222,7 +222,7 @@ int b200d_topp_binarize(const float* mat, int32_t n, int32_t p, void* a_bf16, in
 /* g[b][b] = X^T Y (fp32 block partials, fixed-order fp64 combine); x,y float32 [n][ld]; b in {32, 64} */
 size_t b200d_gram_workspace_bytes(int32_t n, int32_t b);
 int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, int32_t ld, float* g, void* ws, size_t ws_bytes, void* stream);
-/* Symmetric eigendecomposition of g[b][b] (b even, <= 96) by parallel cyclic Jacobi in fp64:
+/* Symmetric eigendecomposition of g[b][b] (b even, <= 128) by parallel cyclic Jacobi in fp64:
  * evals ascending float32 [b], evecs float32 [b][b] (columns).  mode 1: scaled Cholesky instead --
  * returns Q = S R^-1 in evecs with (Y Q)^T (Y Q) = I for g = Y^T Y (CholQR).                       */
 int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream);

@@ -207,7 +207,8 @@ def _clustered_graph(n, k, p, seed):
     return oc.getCosAffinityMatrix(x), lab
 
 
-@pytest.mark.parametrize("n,k,p", [(40, 3, 6), (64, 2, 8), (150, 3, 12), (2399, 4, 60), (6000, 8, 200), (4000, 50, 80)])
+@pytest.mark.parametrize("n,k,p", [(40, 3, 6), (64, 2, 8), (97, 8, 10), (128, 30, 12), (129, 30, 12), (150, 3, 12), (200, 25, 15),
+                                   (2399, 4, 60), (6000, 8, 200), (4000, 50, 80)])
 def test_spectral_embedding_subspace(dev, n, k, p):
     """The k lowest eigenvectors span the same subspace as torch.linalg.eigh's (principal angles ~ 0)."""
     from oracle import offline_clustering as oc

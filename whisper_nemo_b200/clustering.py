@@ -32,7 +32,7 @@ COS_EPS = 3.5e-4  # offline_clustering.cos_similarity
 MIN_SAMPLES_FOR_NMESC = 6
 NME_MAT_SIZE = 512
 ENHANCED_COUNT_THRES = 80
-DENSE_EIG_MAX = 96  # spectral embedding of graphs up to this size: one Jacobi solve instead of subspace iteration
+DENSE_EIG_MAX = 128  # spectral embedding of graphs up to this size: one Jacobi solve instead of subspace iteration
 
 
 def _s():

@@ -16,7 +16,8 @@ namespace b200d {
 
 constexpr int kGramRows = 256;  // rows per CTA
 constexpr int kMaxB = 64;       // block width of the subspace iteration (gram / right_mul / resid)
-constexpr int kMaxJacobi = 96;  // largest dense eigenproblem of small_eig (2 * 96^2 fp64 = 147 KB of shared memory)
+constexpr int kMaxJacobi = 128;  // largest dense eigenproblem of small_eig: A fp64 + V fp64 up to 96 (147 KB of shared memory),
+                                // A fp64 + V fp32 above (128: 196 KB)
 
 // ------------------------------------------------------------------------------------ gram
 template <int B>
@@ -72,11 +73,12 @@ __global__ void gram_combine_kernel(const float* __restrict__ part, int nparts, 
 // ------------------------------------------------------------------------------------ small_eig
 // mode 0: eigen-decomposition by parallel cyclic Jacobi (round-robin pairing) in fp64.
 // mode 1: scaled Cholesky G = S^-1 R^T R S^-1, returns Q = S R^-1 so that (Y Q)^T (Y Q) = I.
+template <typename VT>
 __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict__ g, int b, float* __restrict__ evals,
                                                          float* __restrict__ evecs, int mode) {
   extern __shared__ double sd[];
-  double* A = sd;            // [b][b]
-  double* V = sd + b * b;    // [b][b]
+  double* A = sd;                                   // [b][b]
+  VT* V = reinterpret_cast<VT*>(sd + b * b);        // [b][b] accumulated rotations (fp32 only for b > 96)
   __shared__ double s_c[kMaxJacobi / 2], s_s[kMaxJacobi / 2];
   __shared__ int s_p[kMaxJacobi / 2], s_q[kMaxJacobi / 2];
   __shared__ double s_scale[kMaxJacobi];
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
     const int i = e / b, j = e - i * b;
     // symmetrise the input (the Gram partials are symmetric only up to rounding)
     A[e] = 0.5 * (static_cast<double>(g[i * b + j]) + static_cast<double>(g[j * b + i]));
-    V[e] = (i == j) ? 1.0 : 0.0;
+    V[e] = static_cast<VT>((i == j) ? 1.0 : 0.0);
   }
   __syncthreads();
 
@@ -125,17 +127,17 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
       for (int i = b - 1; i >= 0; --i) {
         double s = (i == c) ? 1.0 : 0.0;
         if (i > c) {
-          V[i * b + c] = 0.0;
+          V[i * b + c] = static_cast<VT>(0.0);
           continue;
         }
-        for (int k = i + 1; k <= c; ++k) s -= A[i * b + k] * V[k * b + c];
-        V[i * b + c] = s / A[i * b + i];
+        for (int k = i + 1; k <= c; ++k) s -= A[i * b + k] * static_cast<double>(V[k * b + c]);
+        V[i * b + c] = static_cast<VT>(s / A[i * b + i]);
       }
     }
     __syncthreads();
     for (int e = tid; e < b * b; e += nth) {
       const int i = e / b;
-      evecs[e] = static_cast<float>(s_scale[i] * V[e]);
+      evecs[e] = static_cast<float>(s_scale[i] * static_cast<double>(V[e]));
     }
     if (tid < b && evals) evals[tid] = static_cast<float>(A[tid * b + tid]);
     return;
@@ -198,9 +200,9 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
         const double ap = A[r * b + p], aq = A[r * b + q];
         A[r * b + p] = c * ap - s * aq;
         A[r * b + q] = s * ap + c * aq;
-        const double vp = V[r * b + p], vq = V[r * b + q];
-        V[r * b + p] = c * vp - s * vq;
-        V[r * b + q] = s * vp + c * vq;
+        const double vp = static_cast<double>(V[r * b + p]), vq = static_cast<double>(V[r * b + q]);
+        V[r * b + p] = static_cast<VT>(c * vp - s * vq);
+        V[r * b + q] = static_cast<VT>(s * vp + c * vq);
       }
       __syncthreads();
       // rows: A <- J^T A  (a warp walks 32 consecutive columns of one pair: conflict-free shared-memory rows)
@@ -352,13 +354,15 @@ extern "C" int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, 
 
 extern "C" int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream) {
   B200D_CHECK_ARG(g && evecs && b >= 2 && b <= kMaxJacobi && b % 2 == 0 && (mode == 0 || mode == 1) && (mode == 1 || evals));
-  const size_t smem = static_cast<size_t>(2) * b * b * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxJacobi * kMaxJacobi * sizeof(double)));
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 96 * 96 * sizeof(double)));
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kMaxJacobi * kMaxJacobi * (sizeof(double) + sizeof(float))));
     attr_set = true;
   }
-  small_eig_kernel<<<1, 512, smem, as_stream(stream)>>>(g, b, evals, evecs, mode);
+  if (b <= 96) small_eig_kernel<double><<<1, 512, static_cast<size_t>(2) * b * b * sizeof(double), as_stream(stream)>>>(g, b, evals, evecs, mode);
+  else small_eig_kernel<float><<<1, 512, static_cast<size_t>(b) * b * (sizeof(double) + sizeof(float)), as_stream(stream)>>>(g, b, evals, evecs, mode);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
