@@ -39,7 +39,7 @@ def test_workspace_queries_are_pure_host_functions():
     from whisper_nemo_b200 import _cabi
 
     lib = _cabi.load()
-    assert lib.b200d_eigvals_workspace_bytes(30, 600) == 30 * 600 * 4 * 4
+    assert lib.b200d_eigvals_workspace_bytes(30, 600) == 30 * 600 * 4 * 4 + 30 * 4
     assert lib.b200d_gram_workspace_bytes(1000, 32) == 4 * 32 * 32 * 4
     assert lib.b200d_kmeans_workspace_bytes(100, 4, 4, 30) > 0
     assert lib.b200d_eigvals_workspace_bytes(0, 10) == 0

@@ -35,14 +35,13 @@ __device__ __forceinline__ float block_sum_512(float v, float* s_red) {
 
 // a [batch][n][n] (destroyed), d [batch][n], e [batch][n], pbuf [batch][2][n]
 __global__ void __launch_bounds__(kTriThreads, 2) tridiag_kernel(float* __restrict__ a, int n, int cpm, float* __restrict__ d,
-                                                                  float* __restrict__ e, float* __restrict__ pbuf) {
+                                                                  float* __restrict__ e, float* __restrict__ pbuf, unsigned* __restrict__ bar) {
   extern __shared__ float sm[];
   float* s_vp = sm;           // v' (previous step's Householder vector), indexed by absolute row
   float* s_wp = sm + n;       // w'
   float* s_v = sm + 2 * n;    // v  (current step)
   float* s_r = sm + 3 * n;    // updated pivot row / scratch
   __shared__ float s_red[kTriWarps];
-  cg::grid_group grid = cg::this_grid();
 
   const int b = blockIdx.x / cpm, c = blockIdx.x % cpm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,32 +87,64 @@ __global__ void __launch_bounds__(kTriThreads, 2) tridiag_kernel(float* __restri
 
     // ---- fused pass over the owned rows of the trailing block (rows / cols j+1 .. n-1)
     float* pw = pb + static_cast<size_t>(j & 1) * n;
-    for (int i = j + 1 + slot; i < n; i += slots) {
+    // two rows of the warp are processed together: eight independent 128-byte requests in flight per warp (the pass is
+    // L2-latency bound, not bandwidth bound)
+    for (int i = j + 1 + slot; i < n; i += 2 * slots) {
+      const int i2 = i + slots;
+      const bool two = i2 < n;
       float* row = A + static_cast<size_t>(i) * n;
+      float* row2 = A + static_cast<size_t>(two ? i2 : i) * n;
       const float vpi = s_vp[i], wpi = s_wp[i];
+      const float vpi2 = two ? s_vp[i2] : 0.f, wpi2 = two ? s_wp[i2] : 0.f;
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      float bcc0 = 0.f, bcc1 = 0.f, bcc2 = 0.f, bcc3 = 0.f;
       int k = j + 1 + lane;
-      // four independent 128-byte requests in flight per warp: the pass is L2-latency bound, not bandwidth bound
       for (; k + 96 < n; k += 128) {
         const float a0 = __ldcg(row + k), a1 = __ldcg(row + k + 32), a2 = __ldcg(row + k + 64), a3 = __ldcg(row + k + 96);
-        const float v0 = a0 - vpi * s_wp[k] - wpi * s_vp[k];
-        const float v1 = a1 - vpi * s_wp[k + 32] - wpi * s_vp[k + 32];
-        const float v2 = a2 - vpi * s_wp[k + 64] - wpi * s_vp[k + 64];
-        const float v3 = a3 - vpi * s_wp[k + 96] - wpi * s_vp[k + 96];
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        if (two) { b0 = __ldcg(row2 + k); b1 = __ldcg(row2 + k + 32); b2 = __ldcg(row2 + k + 64); b3 = __ldcg(row2 + k + 96); }
+        const float w0 = s_wp[k], w1 = s_wp[k + 32], w2 = s_wp[k + 64], w3 = s_wp[k + 96];
+        const float p0 = s_vp[k], p1 = s_vp[k + 32], p2 = s_vp[k + 64], p3 = s_vp[k + 96];
+        const float u0 = s_v[k], u1 = s_v[k + 32], u2 = s_v[k + 64], u3 = s_v[k + 96];
+        const float v0 = a0 - vpi * w0 - wpi * p0, v1 = a1 - vpi * w1 - wpi * p1;
+        const float v2 = a2 - vpi * w2 - wpi * p2, v3 = a3 - vpi * w3 - wpi * p3;
         __stcg(row + k, v0); __stcg(row + k + 32, v1); __stcg(row + k + 64, v2); __stcg(row + k + 96, v3);
-        acc0 = fmaf(v0, s_v[k], acc0); acc1 = fmaf(v1, s_v[k + 32], acc1);
-        acc2 = fmaf(v2, s_v[k + 64], acc2); acc3 = fmaf(v3, s_v[k + 96], acc3);
+        acc0 = fmaf(v0, u0, acc0); acc1 = fmaf(v1, u1, acc1); acc2 = fmaf(v2, u2, acc2); acc3 = fmaf(v3, u3, acc3);
+        if (two) {
+          const float y0 = b0 - vpi2 * w0 - wpi2 * p0, y1 = b1 - vpi2 * w1 - wpi2 * p1;
+          const float y2 = b2 - vpi2 * w2 - wpi2 * p2, y3 = b3 - vpi2 * w3 - wpi2 * p3;
+          __stcg(row2 + k, y0); __stcg(row2 + k + 32, y1); __stcg(row2 + k + 64, y2); __stcg(row2 + k + 96, y3);
+          bcc0 = fmaf(y0, u0, bcc0); bcc1 = fmaf(y1, u1, bcc1); bcc2 = fmaf(y2, u2, bcc2); bcc3 = fmaf(y3, u3, bcc3);
+        }
       }
       for (; k < n; k += 32) {
         const float v = __ldcg(row + k) - vpi * s_wp[k] - wpi * s_vp[k];
         __stcg(row + k, v);
         acc0 = fmaf(v, s_v[k], acc0);
+        if (two) {
+          const float y = __ldcg(row2 + k) - vpi2 * s_wp[k] - wpi2 * s_vp[k];
+          __stcg(row2 + k, y);
+          bcc0 = fmaf(y, s_v[k], bcc0);
+        }
       }
       const float acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
-      if (lane == 0) pw[i] = beta * acc;
+      const float bcc = warp_sum((bcc0 + bcc1) + (bcc2 + bcc3));
+      if (lane == 0) {
+        pw[i] = beta * acc;
+        if (two) pw[i2] = beta * bcc;
+      }
     }
-    __threadfence();
-    grid.sync();
+    // barrier among the cpm CTAs of THIS matrix only (the matrices are independent; all CTAs are co-resident under the
+    // cooperative launch): monotone arrival counter in global memory
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(bar + b, 1u);
+      const unsigned target = static_cast<unsigned>(j + 1) * static_cast<unsigned>(cpm);
+      while (*reinterpret_cast<volatile unsigned*>(bar + b) < target) __nanosleep(32);
+      __threadfence();
+    }
+    __syncthreads();
 
     // ---- w = p - (beta/2 v^T p) v ; becomes the pending update
     float kk = 0.f;
@@ -221,7 +252,7 @@ static int tridiag_cpm(int batch, int blocks_per_sm) {
 
 extern "C" size_t b200d_eigvals_workspace_bytes(int32_t batch, int32_t n) {
   if (batch <= 0 || n <= 0) return 0;
-  return static_cast<size_t>(batch) * n * 4 * sizeof(float);  // d, e, p[2]
+  return static_cast<size_t>(batch) * n * 4 * sizeof(float) + static_cast<size_t>(batch) * sizeof(unsigned);  // d, e, p[2], barrier counters
 }
 
 extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t n_low, float* evals, void* ws, size_t ws_bytes,
@@ -235,6 +266,8 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
   float* d = reinterpret_cast<float*>(ws);
   float* e = d + static_cast<size_t>(batch) * n;
   float* pbuf = e + static_cast<size_t>(batch) * n;
+  unsigned* bar = reinterpret_cast<unsigned*>(pbuf + static_cast<size_t>(batch) * 2 * n);
+  B200D_CHECK_CUDA(cudaMemsetAsync(bar, 0, static_cast<size_t>(batch) * sizeof(unsigned), s));
   int n_arg = n;
   const size_t smem = static_cast<size_t>(4) * n * sizeof(float);
   static bool attr_set = false;
@@ -249,7 +282,7 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
     blocks_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
   }
   int cpm = tridiag_cpm(batch, blocks_per_sm);
-  void* args[] = {&a, &n_arg, &cpm, &d, &e, &pbuf};
+  void* args[] = {&a, &n_arg, &cpm, &d, &e, &pbuf, &bar};
   B200D_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tridiag_kernel), dim3(batch * cpm), dim3(kTriThreads), args, smem, s));
   const int wanted = n_low + 1;
   int threads = 32 * (wanted < 32 ? wanted : 32);
