@@ -245,7 +245,8 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong" if batch_mode else "weak", "vs_baseline": None,
-            "dtype": "fp16 tensor-core GEMMs (fp32 accumulate), fp32 featurizer/affinity/eigen", "data": "synthetic",
+            "dtype": "fp16", "dtype_detail": "fp16 tensor-core GEMMs with fp32 accumulation (TitaNet-L), fp32 featurizer / affinity / eigen-solvers, fp64 Sturm + Jacobi",
+            "data": "synthetic",
             "config": {"workload": (f"{workload} (BASELINE.json configs[3]): batch of {args.batch} x 600 s synthetic 3-speaker recordings in one "
                                     f"manifest, diar_infer_general.yaml, dealt to {world} rank(s) by recording, oracle VAD, TitaNet-L random-init seed 1234")
                        if batch_mode else
