@@ -41,11 +41,11 @@ WORKLOADS = {
 # (strong scaling over the batch).  --batch R sets the batch size (64 in BASELINE.json; smaller values keep the host-side
 # synthesis short).
 BATCH_WORKLOAD = "general_10min_batch"
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu --set full capture
-# profiles/r01_ncu_full_gemm2cta_depthwise_featurize_v2.txt: gemm_tcgen05_2cta_kernel<bias>, M = 120 649 frames (799 windows of
-# 151), N = K = 1024 -> 213.7 MB read + 166.2 MB written (algorithmic: 247 MB A + 2 MB W + 247 MB out; part of A is still L2-resident)
-NCU_GEMM_TRAFFIC = {"bytes_per_launch": 379982592, "launch": "M=120649 N=1024 K=1024 bias epilogue", "algorithmic_bytes": 496275456,
-                    "source": "profiles/r01_ncu_full_gemm2cta_depthwise_featurize_v2.txt"}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu --set full capture of
+# this same command (profiles/r01_ncu_full_gemm2cta_final.txt): gemm_tcgen05_2cta_kernel<bias>, M = 131 072 frames, N = K = 1024:
+# 270.3 MB read + 231.1 MB written against 268 MB (A) + 2 MB (W) + 268 MB (out) algorithmic; 86.7 % tensor-pipe active, 192.5 us
+NCU_GEMM_TRAFFIC = {"bytes_per_launch": 501400064, "launch": "M=131072 N=1024 K=1024 bias epilogue", "algorithmic_bytes": 538968064,
+                    "tensor_pipe_active_pct": 86.7, "source": "profiles/r01_ncu_full_gemm2cta_final.txt"}
 METRIC = "diarized audio-hours/sec (embed+NME-SC, device-timed)"
 UNIT = "audio-hours/s"
 
