@@ -355,7 +355,7 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         _cabi.call("b200d_small_eig", ptr(G), b, ptr(theta), ptr(Q), 0, _s())
         _cabi.call("b200d_right_mul", ptr(X), n, b, b, ptr(Q), ptr(X), ptr(vt[0]), ldvt, _s())
         _cabi.call("b200d_right_mul", ptr(W), n, b, b, ptr(Q), ptr(W), None, ldvt, _s())
-        _cabi.call("b200d_resid_norms", ptr(W), ptr(X), ptr(theta), n, b, b, ptr(resid), ptr(gws), gws_bytes, _s())
+        _cabi.call("b200d_resid_norms", ptr(W), ptr(X), ptr(theta), n, b, b, ptr(resid), _s())
         th = theta.cpu().double().numpy()
         rs = np.sqrt(np.maximum(resid.cpu().double().numpy(), 0.0))
         st.max_resid = float(rs[:k].max() / up)
