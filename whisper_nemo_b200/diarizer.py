@@ -28,7 +28,7 @@ import torch
 from . import _cabi
 from . import speaker_utils as su
 from .config import as_config
-from .titanet import HOP, TitaNetB200
+from .titanet import TitaNetB200
 
 
 def _get(cfg, dotted, default=None):

@@ -10,7 +10,6 @@ overlap.  The ground-truth RTTM doubles as oracle VAD (`oracle_vad: True`).
 """
 import json
 import os
-import wave
 from typing import List, Tuple
 
 import numpy as np
