@@ -231,9 +231,10 @@ int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32
  * the W operand of the next CHEB GEMM.                                                                   */
 int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y, void* vt_bf16, int32_t ldvt,
                     void* stream);
-/* out[j] = sum_r (w[r][j] - theta[j] * x[r][j])^2 : squared residual norms of the Ritz pairs.       */
+/* out[j] = sum_r (w[r][j] - theta[j] * x[r][j])^2 : squared residual norms of the Ritz pairs (fixed summation order).
+ * ws: at least ceil(n / 256) * 64 floats (b200d_gram_workspace_bytes(n, b) is always enough).              */
 int b200d_resid_norms(const float* w, const float* x, const float* theta, int32_t n, int32_t b, int32_t ld, float* out,
-                      void* stream);
+                      void* ws, size_t ws_bytes, void* stream);
 
 /* k-means of kmeans_torch / kmeans_plusplus_torch with the RNG draws supplied by the host
  * (torch.manual_seed(0) stream: first-centre index, rand(30) per further centre, fallback randints).

@@ -159,7 +159,7 @@ def test_gram_smalleig_rightmul_resid(dev, n, b):
     # residual norms
     theta = torch.rand(b, device=dev)
     out = torch.empty(b, dtype=torch.float32, device=dev)
-    _cabi.call("b200d_resid_norms", ptr(y), ptr(x), ptr(theta), n, b, b, ptr(out), _cabi._stream())
+    _cabi.call("b200d_resid_norms", ptr(y), ptr(x), ptr(theta), n, b, b, ptr(out), ptr(ws), wsb, _cabi._stream())
     ref_r = ((y.double() - x.double() * theta.double()[None, :]) ** 2).sum(0)
     assert ((out.double() - ref_r).abs() / ref_r).max().item() < 1e-4
 

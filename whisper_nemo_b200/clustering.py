@@ -32,7 +32,8 @@ COS_EPS = 3.5e-4  # offline_clustering.cos_similarity
 MIN_SAMPLES_FOR_NMESC = 6
 NME_MAT_SIZE = 512
 ENHANCED_COUNT_THRES = 80
-DENSE_EIG_MAX = 128  # spectral embedding of graphs up to this size: one Jacobi solve instead of subspace iteration
+DENSE_EIG_MAX = 96   # spectral embedding of graphs up to this size: one Jacobi solve instead of subspace iteration
+DENSE_EIG_LIMIT = 128  # ... and up to this size when the 64-vector block of the iteration would not fit (n < 128, k > 24)
 
 
 def _s():
@@ -355,7 +356,7 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         _cabi.call("b200d_small_eig", ptr(G), b, ptr(theta), ptr(Q), 0, _s())
         _cabi.call("b200d_right_mul", ptr(X), n, b, b, ptr(Q), ptr(X), ptr(vt[0]), ldvt, _s())
         _cabi.call("b200d_right_mul", ptr(W), n, b, b, ptr(Q), ptr(W), None, ldvt, _s())
-        _cabi.call("b200d_resid_norms", ptr(W), ptr(X), ptr(theta), n, b, b, ptr(resid), _s())
+        _cabi.call("b200d_resid_norms", ptr(W), ptr(X), ptr(theta), n, b, b, ptr(resid), ptr(gws), gws_bytes, _s())
         th = theta.cpu().double().numpy()
         rs = np.sqrt(np.maximum(resid.cpu().double().numpy(), 0.0))
         st.max_resid = float(rs[:k].max() / up)
@@ -424,13 +425,13 @@ class SpectralClustering:
         if isinstance(graph, tuple):
             a16, deg = graph
             n = a16.shape[0]
-            if n <= DENSE_EIG_MAX:
+            if n <= DENSE_EIG_MAX or (n <= DENSE_EIG_LIMIT and self.n_clusters + 8 > 32):
                 lap = torch.diag(deg) - a16[:, :n].float()
                 return _dense_bottom_eigvecs(lap, self.n_clusters)
             return bottom_eigvecs(a16, deg, self.n_clusters)
         mat = graph.float().clone()
         n = mat.shape[0]
-        if n > DENSE_EIG_MAX:
+        if n > DENSE_EIG_LIMIT:
             raise NotImplementedError("raw-affinity spectral embedding is only reached for <= min_samples_for_nmesc points")
         mat.fill_diagonal_(0)
         lap = torch.diag(mat.abs().sum(dim=1)) - mat

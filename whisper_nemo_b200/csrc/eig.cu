@@ -170,15 +170,25 @@ __global__ void __launch_bounds__(kTriThreads, 2) tridiag_kernel(float* __restri
   }
 }
 
-// Number of eigenvalues of the symmetric tridiagonal (d, e) strictly below x.
+// Number of eigenvalues of the symmetric tridiagonal (d, e) strictly below x = number of sign changes in the sequence of
+// leading principal minors p_0 = 1, p_1 = d_0 - x, p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1}.  The division-free form is a
+// chain of two dependent multiply-adds per row instead of an fp64 division (~10x shorter); the pair (p_i, p_{i-1}) is
+// rescaled every 8 rows so that it stays inside the fp64 range (growth per row is bounded by the Gershgorin width).
 __device__ __forceinline__ int sturm_count(const double* __restrict__ d, const double* __restrict__ e2, int n, double x, double tiny) {
-  int cnt = 0;
-  double q = d[0] - x;
-  if (q < 0.0) ++cnt;
+  double pm = 1.0, p = d[0] - x;
+  if (p == 0.0) p = -tiny;
+  int cnt = p < 0.0 ? 1 : 0;
   for (int i = 1; i < n; ++i) {
-    if (fabs(q) < tiny) q = -tiny;
-    q = d[i] - x - e2[i - 1] / q;
-    if (q < 0.0) ++cnt;
+    double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
+    if (pn == 0.0) pn = (p < 0.0) ? tiny : -tiny;  // a zero minor counts as a sign change, like q = -tiny in the ratio form
+    cnt += ((pn < 0.0) != (p < 0.0)) ? 1 : 0;
+    pm = p;
+    p = pn;
+    if ((i & 7) == 0) {
+      const double a = fabs(p);
+      if (a > 1e120) { p *= 1e-120; pm *= 1e-120; }
+      else if (a < 1e-120) { p *= 1e120; pm *= 1e120; }
+    }
   }
   return cnt;
 }

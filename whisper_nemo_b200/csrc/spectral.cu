@@ -304,29 +304,34 @@ __global__ void __launch_bounds__(256) right_mul_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ residuals
-// out[j] = sum_r (w[r][j] - theta[j] x[r][j])^2.  One CTA, 16 row groups x 64 columns, combined in a fixed order: the
-// value steers the convergence test of the subspace iteration, so it must not depend on the order of atomics (a flipped
+// out[j] = sum_r (w[r][j] - theta[j] x[r][j])^2: per-CTA partials over 256-row slabs, then a fixed-order combine (the
+// value steers the convergence test of the subspace iteration, so it must not depend on the order of atomics: a flipped
 // iteration count would make two runs on the same input differ in the last bits of the eigenvectors).
-__global__ void __launch_bounds__(1024) resid_kernel(const float* __restrict__ w, const float* __restrict__ x, const float* __restrict__ theta,
-                                                      int n, int b, int ld, float* __restrict__ out) {
-  __shared__ float s_acc[16][kMaxB];
+__global__ void __launch_bounds__(256) resid_partial_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                             const float* __restrict__ theta, int n, int b, int ld, float* __restrict__ part) {
+  __shared__ float s_acc[4][kMaxB];
   const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int r0 = blockIdx.x * kGramRows;
   float acc = 0.f;
   if (col < b) {
     const float th = theta[col];
-    for (int r = rg; r < n; r += 16) {
+    const int r1 = min(n, r0 + kGramRows);
+    for (int r = r0 + rg; r < r1; r += 4) {
       const float d = w[static_cast<size_t>(r) * ld + col] - th * x[static_cast<size_t>(r) * ld + col];
       acc = fmaf(d, d, acc);
     }
   }
   s_acc[rg][col] = acc;
   __syncthreads();
-  if (rg == 0 && col < b) {
-    float t = 0.f;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) t += s_acc[g][col];
-    out[col] = t;
-  }
+  if (rg == 0) part[static_cast<size_t>(blockIdx.x) * kMaxB + col] = (s_acc[0][col] + s_acc[1][col]) + (s_acc[2][col] + s_acc[3][col]);
+}
+
+__global__ void resid_combine_kernel(const float* __restrict__ part, int nparts, int b, float* __restrict__ out) {
+  const int col = threadIdx.x;
+  if (col >= b) return;
+  float t = 0.f;
+  for (int p = 0; p < nparts; ++p) t += part[static_cast<size_t>(p) * kMaxB + col];
+  out[col] = t;
 }
 
 }  // namespace b200d
@@ -381,9 +386,14 @@ extern "C" int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld,
 }
 
 extern "C" int b200d_resid_norms(const float* w, const float* x, const float* theta, int32_t n, int32_t b, int32_t ld, float* out,
-                                 void* stream) {
-  B200D_CHECK_ARG(w && x && theta && out && n > 0 && b > 0 && b <= kMaxB && ld >= b);
-  resid_kernel<<<1, 1024, 0, as_stream(stream)>>>(w, x, theta, n, b, ld, out);
+                                 void* ws, size_t ws_bytes, void* stream) {
+  B200D_CHECK_ARG(w && x && theta && out && ws && n > 0 && b > 0 && b <= kMaxB && ld >= b);
+  const int parts = (n + kGramRows - 1) / kGramRows;
+  if (ws_bytes < static_cast<size_t>(parts) * kMaxB * sizeof(float))
+    return b200d::set_error(B200D_EWORKSPACE, "%s: workspace too small%s", "b200d_resid_norms");
+  float* part = reinterpret_cast<float*>(ws);
+  resid_partial_kernel<<<parts, 256, 0, as_stream(stream)>>>(w, x, theta, n, b, ld, part);
+  resid_combine_kernel<<<1, 64, 0, as_stream(stream)>>>(part, parts, b, out);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
