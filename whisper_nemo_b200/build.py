@@ -36,6 +36,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(_STAMP) and open(_STAMP).read().strip() == digest:
         return LIB_PATH
+    import fcntl
+
+    with open(os.path.join(CSRC, ".build_lock"), "w") as lock:  # several ranks may arrive here at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB_PATH) and os.path.exists(_STAMP) and open(_STAMP).read().strip() == digest:
+            return LIB_PATH
+        return _build_locked(digest, verbose)
+
+
+def _build_locked(digest: str, verbose: bool) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
