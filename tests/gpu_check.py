@@ -1,6 +1,6 @@
 """Staged on-GPU diagnostics (development aid; the judged checks live in tests/ -m gpu).
 
-Usage: python tools/gpu_check.py [gemm] [feat] [titanet] [cluster]
+Usage: python tests/gpu_check.py [gemm] [feat] [titanet] [cluster]
 Prints max errors of each CUDA stage against torch fp32 / the CPU oracle.
 """
 import os
