@@ -231,6 +231,18 @@ int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32
  * the W operand of the next CHEB GEMM.                                                                   */
 int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y, void* vt_bf16, int32_t ldvt,
                     void* stream);
+/* Sparse form of the same step, for graphs built from few neighbours (at most 2 p non-zeros per row):
+ * b200d_csr_from_dense lists the non-zeros of a_bf16 [n][lda] (b200d_topp_binarize's output) row by row in
+ * ascending column order: rowptr int32 [n + 1], colw uint32 [capacity] = column | (1u << 31 when the entry is 1,
+ * else it is 0.5); capacity must be >= the number of non-zeros (2 n p always is).
+ * b200d_spmm_cheb: out = ca * (deg .* x - A x) + cb * x + cc * xprev  (xprev may be NULL), x / xprev float32
+ * [n][ldx], out float32 [n][ldo], b in {32, 64} columns: the arithmetic of the B200D_EPI_CHEB epilogue with the
+ * product taken in fp32 over the CSR lists (upstream: the L @ V products inside torch.linalg.eigh,
+ * offline_clustering.py getSpectralEmbeddings).                                                            */
+int b200d_csr_from_dense(const void* a_bf16, int32_t n, int32_t lda, int32_t* rowptr, uint32_t* colw, int64_t capacity,
+                         void* stream);
+int b200d_spmm_cheb(const int32_t* rowptr, const uint32_t* colw, int32_t n, int32_t b, const float* deg, const float* x,
+                    const float* xprev, int32_t ldx, float ca, float cb, float cc, float* out, int32_t ldo, void* stream);
 /* out[j] = sum_r (w[r][j] - theta[j] * x[r][j])^2 : squared residual norms of the Ritz pairs (fixed summation order).
  * ws: at least ceil(n / 256) * 64 floats (b200d_gram_workspace_bytes(n, b) is always enough).              */
 int b200d_resid_norms(const float* w, const float* x, const float* theta, int32_t n, int32_t b, int32_t ld, float* out,

@@ -1,6 +1,7 @@
 """Kernel-level parity on the B200: every C-ABI entry point of the clustering stage against torch fp64 /
 the CPU oracle on seeded inputs.  Run with `pytest -m gpu`."""
 import ctypes
+import functools
 import math
 
 import numpy as np
@@ -207,29 +208,91 @@ def _clustered_graph(n, k, p, seed):
     return oc.getCosAffinityMatrix(x), lab
 
 
+@pytest.mark.parametrize("n,p", [(64, 5), (1000, 11), (2399, 60), (10000, 11), (4001, 2500)])
+def test_csr_from_dense_and_sparse_chebyshev_step(dev, n, p):
+    """CSR lists of the binarised graph == its non-zeros (ascending columns, 0.5 / 1 flag); one sparse Chebyshev step
+    == ca (D x - A x) + cb x + cc xprev in fp64."""
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200 import clustering as cl
+    from whisper_nemo_b200._cabi import ptr
+
+    g = torch.Generator().manual_seed(n + p)
+    x = torch.randn(n, 24, generator=g)
+    x = x / x.norm(dim=1, keepdim=True)
+    mat = (x @ x.t()).to(dev)
+    a16, deg = cl.getAffinityGraphMat(mat, p)
+    lda = a16.shape[1]
+    capacity = min(2 * p, n) * n
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    colw = torch.full((capacity,), -1, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _cabi.call("b200d_csr_from_dense", ptr(a16), n, lda, ptr(rowptr), ptr(colw), capacity, s)
+    torch.cuda.synchronize()
+    a = a16[:, :n].float().cpu()
+    rp = rowptr.cpu().long()
+    cw = colw.cpu().long() & 0xFFFFFFFF
+    nz = a.nonzero()
+    assert rp[0].item() == 0 and rp[-1].item() == nz.shape[0]
+    assert torch.equal(rp[1:] - rp[:-1], (a != 0).sum(1))
+    got_cols = cw[: nz.shape[0]] & 0x7FFFFFFF
+    got_one = (cw[: nz.shape[0]] >> 31) == 1
+    assert torch.equal(got_cols, nz[:, 1])          # nonzero() is row-major: ascending columns inside each row
+    assert torch.equal(got_one, a[nz[:, 0], nz[:, 1]] == 1.0)
+    for b in (32, 64):
+        xx = torch.randn(n, b, generator=g)
+        xp = torch.randn(n, b, generator=g)
+        ca, cb, cc = 0.37, -1.25, 0.6
+        for prev in (None, xp):
+            out = torch.empty(n, b, device=dev)
+            xd, pd = xx.to(dev), (prev.to(dev) if prev is not None else None)
+            _cabi.call("b200d_spmm_cheb", ptr(rowptr), ptr(colw), n, b, ptr(deg), ptr(xd), ptr(pd), b, ca, cb, cc, ptr(out), b, s)
+            torch.cuda.synchronize()
+            d = deg.cpu().double()[:, None]
+            ref = ca * (d * xx.double() - a.double() @ xx.double()) + cb * xx.double()
+            if prev is not None:
+                ref = ref + cc * prev.double()
+            err = (out.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+            assert err < 2e-6, (n, p, b, err)
+
+
+@functools.lru_cache(maxsize=2)
+def _reference_bottom_eigvecs(n, k, p):
+    from oracle import offline_clustering as oc
+
+    mat, _ = _clustered_graph(n, k, p, seed=n + k)
+    lap = oc.getLaplacian(oc.getAffinityGraphMat(mat, p)).double()
+    lam, vec = torch.linalg.eigh(lap)
+    return lam[: k + 1].clone(), vec[:, :k].clone()
+
+
+@pytest.mark.parametrize("products", ["dense", "csr"])
 @pytest.mark.parametrize("n,k,p", [(40, 3, 6), (64, 2, 8), (97, 8, 10), (128, 30, 12), (129, 30, 12), (150, 3, 12), (200, 25, 15),
-                                   (2399, 4, 60), (6000, 8, 200), (4000, 50, 80)])
-def test_spectral_embedding_subspace(dev, n, k, p):
-    """The k lowest eigenvectors span the same subspace as torch.linalg.eigh's (principal angles ~ 0)."""
+                                   (2399, 4, 60), (6000, 8, 200), (4000, 50, 80), (6000, 50, 11)])
+def test_spectral_embedding_subspace(dev, n, k, p, products, monkeypatch):
+    """The k lowest eigenvectors span the same subspace as torch.linalg.eigh's (principal angles ~ 0), with the dense
+    tcgen05 products and with the CSR row-gather products."""
     from oracle import offline_clustering as oc
     from whisper_nemo_b200 import clustering as cl
 
+    if products == "csr" and (n <= cl.DENSE_EIG_MAX or 2 * p > 200):
+        pytest.skip("Jacobi path / graph too dense for the CSR products")
+    monkeypatch.setattr(cl, "SPARSE_MAX_ROW_NNZ", -1 if products == "dense" else 200)
+    monkeypatch.setattr(cl, "SPARSE_MAX_DENSITY", -1.0)
     mat, _ = _clustered_graph(n, k, p, seed=n + k)
     graph = cl.getAffinityGraphMat(mat.to(dev), p)
     emb = cl.SpectralClustering(n_clusters=k).getSpectralEmbeddings(graph)
     torch.cuda.synchronize()
     st = cl.last_spectral_stats
-    aff = oc.getAffinityGraphMat(mat.clone(), p)
-    lap = oc.getLaplacian(aff).double()
-    lam, vec = torch.linalg.eigh(lap)
-    ref = vec[:, :k]
+    lam, ref = _reference_bottom_eigvecs(n, k, p)
     q, _ = torch.linalg.qr(emb.cpu().double())
     sv = torch.linalg.svdvals(ref.t() @ q)
     gap = (lam[k] - lam[k - 1]).item()
     print(f"spectral n={n} k={k}: method {st.method} outer {st.outer} gemms {st.gemms} resid {st.max_resid:.2e} "
-          f"min cos(angle) {sv.min().item():.8f} gap {gap:.3e} lam_max {lam[-1].item():.1f}")
+          f"min cos(angle) {sv.min().item():.8f} gap {gap:.3e}")
     assert st.converged
     assert sv.min().item() > 1 - 1e-4
+    if n > cl.DENSE_EIG_LIMIT:
+        assert st.method.endswith("-csr") == (products == "csr")
 
 
 @pytest.mark.parametrize("n,dim,k", [(50, 2, 2), (500, 4, 4), (2399, 3, 3), (14399, 8, 8), (10000, 50, 50)])

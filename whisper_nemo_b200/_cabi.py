@@ -69,6 +69,9 @@ _SIGNATURES = {
     "b200d_small_eig": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "b200d_right_mul": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "b200d_resid_norms": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200d_csr_from_dense": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b200d_spmm_cheb": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_float,
+                                  c_void_p, c_int32, c_void_p]),
     "b200d_kmeans_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "b200d_kmeans": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_float,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -138,7 +141,7 @@ KERNELS_PER_CALL = {
     "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
     "b200d_masked_rowsum": 1, "b200d_gather_segment_mean": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
     "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
-    "b200d_resid_norms": 2, "b200d_kmeans": 1,
+    "b200d_resid_norms": 2, "b200d_kmeans": 1, "b200d_csr_from_dense": 3, "b200d_spmm_cheb": 1,
 }
 launch_count = 0
 _pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None  # mirrors b200d_gemm_set_pair_kernel for the profile labels

@@ -19,6 +19,7 @@ the CPU torch generator exactly as upstream draws them; everything else is devic
 There is no CPU fallback: without libb200d.so / an sm_100 device every entry point raises.
 """
 import ctypes
+import os
 import math
 from typing import List, Optional, Tuple
 
@@ -134,6 +135,10 @@ def getMultiScaleCosAffinityMatrix(multiscale_weights, embeddings_in_scales, tim
 
 
 # ----------------------------------------------------------------------------- graph
+class _Graph(tuple):
+    """(A bf16 [n, lda], deg float32 [n]) plus `.p`, the neighbour count it was built from (at most 2 p non-zeros per row)."""
+
+
 def getAffinityGraphMat(affinity_mat_raw: torch.Tensor, p_value: int):
     """0.5 * (B + B^T) of the p-neighbour binarisation.  Returns (A bf16 [n, lda], deg float32 [n])."""
     n = affinity_mat_raw.shape[0]
@@ -148,7 +153,9 @@ def getAffinityGraphMat(affinity_mat_raw: torch.Tensor, p_value: int):
     sel = torch.empty(n, n, dtype=torch.uint8, device=dev)
     mat = affinity_mat_raw.contiguous()
     _cabi.call("b200d_topp_binarize", ptr(mat), n, p_value, ptr(a16), lda, ptr(deg), ptr(sel), _s())
-    return a16, deg
+    graph = _Graph((a16, deg))
+    graph.p = p_value
+    return graph
 
 
 # ----------------------------------------------------------------------------- NME analysis
@@ -285,6 +292,12 @@ def _gemm_cheb(A16, lda, vt_in, ldvt, n, nb4, out, deg, x, xprev, ca, cb, cc, vt
     _cabi.call("b200d_gemm_f16", ptr(A16), lda, ptr(vt_in), ldvt, n, nb4, n, ptr(out), out.stride(0), ctypes.byref(epi), _s())
 
 
+def _spmm_cheb(csr, n, b, out, deg, x, xprev, ca, cb, cc):
+    rowptr, colw = csr
+    _cabi.call("b200d_spmm_cheb", ptr(rowptr), ptr(colw), n, b, ptr(deg), ptr(x), ptr(xprev), x.stride(0), float(ca), float(cb),
+               float(cc), ptr(out), out.stride(0), _s())
+
+
 def _dense_bottom_eigvecs(lap: torch.Tensor, k: int) -> torch.Tensor:
     """All eigenvectors of a small (<= 64) Laplacian by the fp64 Jacobi kernel; returns the k lowest."""
     n = lap.shape[0]
@@ -302,7 +315,23 @@ def _dense_bottom_eigvecs(lap: torch.Tensor, k: int) -> torch.Tensor:
     return evecs[:n, :k].contiguous()
 
 
-def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e-6, max_outer: int = 40, seed: int = 0) -> torch.Tensor:
+# Graphs built from few neighbours take fp32 row-gather products over their CSR lists instead of the dense tcgen05
+# GEMM.  Both are bandwidth bound (n * 2p * b * 4 bytes of gathers against n^2 * 2 bytes of operand + the re-read V
+# tiles); measured on the 1-hour meeting's chunks (n = 10 000, b = 64, two chunks in flight) the two cross at ~3 %
+# non-zeros per row (p = 171: 0.154 ms per product against 0.125 ms dense); the switch sits a factor two below that.
+SPARSE_MAX_ROW_NNZ = int(os.environ.get("B200D_SPARSE_MAX_ROW_NNZ", "32"))  # always below this many non-zeros per row
+SPARSE_MAX_DENSITY = float(os.environ.get("B200D_SPARSE_MAX_DENSITY", str(1.0 / 64.0)))  # ... or this fraction of a row
+
+
+def _use_csr_products(n: int, p: Optional[int]) -> bool:
+    if p is None:
+        return False
+    nnz = 2 * int(p)
+    return nnz <= SPARSE_MAX_ROW_NNZ or nnz <= SPARSE_MAX_DENSITY * n
+
+
+def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e-6, max_outer: int = 40, seed: int = 0,
+                   p: Optional[int] = None) -> torch.Tensor:
     """The k lowest eigenvectors of L = diag(deg) - A for the binarised graph A (bf16 [n, lda]).
 
     Chebyshev-filtered subspace iteration: a block of b = 32 / 64 vectors is repeatedly pushed
@@ -310,7 +339,8 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
     GEMM A*V with V split into three bf16 parts, i.e. fp32-accurate products on an exactly
     representable A), re-orthonormalised by CholQR2 and rotated to Ritz vectors.  Upstream
     calls a dense eigh(N x N) and keeps k columns; k-means only sees the k-dimensional
-    invariant subspace, which is what converges here."""
+    invariant subspace, which is what converges here.  When the graph was built from few neighbours
+    (`p` given, see _use_csr_products) the products run in fp32 over its CSR lists instead."""
     n, lda = a16.shape
     dev = a16.device
     if k + 8 <= 32:
@@ -323,12 +353,25 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         raise NotImplementedError(f"spectral embedding of {k} clusters on {n} points: needs n >= {2 * b} (or n <= {DENSE_EIG_MAX})")
     nb4 = 4 * b
     ldvt = (n + 7) // 8 * 8
-    st = last_spectral_stats
-    st.outer, st.gemms, st.n, st.method, st.converged = 0, 0, n, f"chfsi{b}", False
+    st = SpectralStats()  # per call: long-form chunks run this from several threads
+    sparse = _use_csr_products(n, p)
+    st.outer, st.gemms, st.n, st.method, st.converged = 0, 0, n, f"chfsi{b}" + ("-csr" if sparse else ""), False
     f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
     X, W = f32(n, b), f32(n, b)
     Y = [f32(n, b) for _ in range(3)]
-    vt = [torch.zeros(nb4, ldvt, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    if sparse:
+        capacity = min(2 * int(p), n) * n
+        csr = (torch.empty(n + 1, dtype=torch.int32, device=dev), torch.empty(capacity, dtype=torch.int32, device=dev))
+        _cabi.call("b200d_csr_from_dense", ptr(a16), n, lda, ptr(csr[0]), ptr(csr[1]), capacity, _s())
+        vt = [None, None]
+
+        def step(vin, out, x, xprev, ca, cb, cc, vout):
+            _spmm_cheb(csr, n, b, out, deg, x, xprev, ca, cb, cc)
+    else:
+        vt = [torch.zeros(nb4, ldvt, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+
+        def step(vin, out, x, xprev, ca, cb, cc, vout):
+            _gemm_cheb(a16, lda, vin, ldvt, n, nb4, out, deg, x, xprev, ca, cb, cc, vout)
     G, Q, theta, resid = f32(b, b), f32(b, b), f32(b), f32(b)
     gws_bytes = _cabi.load().b200d_gram_workspace_bytes(n, b)
     gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev)
@@ -350,7 +393,7 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
     for outer in range(max_outer):
         st.outer = outer + 1
         # Rayleigh-Ritz on span(X): W = L X, H = X^T W, X <- X Q, W <- W Q
-        _gemm_cheb(a16, lda, vt[0], ldvt, n, nb4, W, deg, X, None, 1.0, 0.0, 0.0, None)
+        step(vt[0], W, X, None, 1.0, 0.0, 0.0, None)
         st.gemms += 1
         gram(X, W, G)
         _cabi.call("b200d_small_eig", ptr(G), b, ptr(theta), ptr(Q), 0, _s())
@@ -381,7 +424,7 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         sigma1 = e / (0.0 - c)
         sigma = sigma1
         tau = 2.0 / sigma1
-        _gemm_cheb(a16, lda, vt[0], ldvt, n, nb4, Y[0], deg, X, None, sigma1 / e, -c * sigma1 / e, 0.0, vt[1])
+        step(vt[0], Y[0], X, None, sigma1 / e, -c * sigma1 / e, 0.0, vt[1])
         st.gemms += 1
         prev, cur = X, Y[0]
         vin = 1
@@ -389,7 +432,7 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
             nxt = Y[(i - 1) % 3]
             sigma_new = 1.0 / (tau - sigma)
             ca = 2.0 * sigma_new / e
-            _gemm_cheb(a16, lda, vt[vin], ldvt, n, nb4, nxt, deg, cur, prev, ca, -c * ca, -sigma * sigma_new, vt[1 - vin])
+            step(vt[vin], nxt, cur, prev, ca, -c * ca, -sigma * sigma_new, vt[1 - vin])
             st.gemms += 1
             sigma = sigma_new
             prev, cur = cur, nxt
@@ -397,8 +440,9 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         X.copy_(cur)
         cholqr(X)
         cholqr(X, vt[0])
+    last_spectral_stats.__dict__.update(st.__dict__)
     if len(spectral_log) < 256:
-        spectral_log.append({"n": n, "k": k, "block": b, "outer": st.outer, "gemms": st.gemms, "resid": st.max_resid,
+        spectral_log.append({"n": n, "k": k, "p": p, "method": st.method, "block": b, "outer": st.outer, "gemms": st.gemms, "resid": st.max_resid,
                              "converged": st.converged, "history": [float(f"{h:.2e}") for h in history]})
     return X[:, :k].contiguous()
 
@@ -428,7 +472,7 @@ class SpectralClustering:
             if n <= DENSE_EIG_MAX or (n <= DENSE_EIG_LIMIT and self.n_clusters + 8 > 32):
                 lap = torch.diag(deg) - a16[:, :n].float()
                 return _dense_bottom_eigvecs(lap, self.n_clusters)
-            return bottom_eigvecs(a16, deg, self.n_clusters)
+            return bottom_eigvecs(a16, deg, self.n_clusters, p=getattr(graph, "p", None))
         mat = graph.float().clone()
         n = mat.shape[0]
         if n > DENSE_EIG_LIMIT:
