@@ -535,8 +535,26 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int wq = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // SE-residual epilogue: the residual operand (512 bytes of this thread's row per tile) does not depend on the
+    // accumulator, and read on demand it costs one DRAM latency per 32-column chunk -- eight in a row, about as long as
+    // the tile's MMAs.  Its lines are pulled into L2 one tile ahead instead.
+    auto prefetch_aux = [&](int t) {
+      if constexpr (MODE == B200D_EPI_SE_RES) {
+        if (t < total) {
+          const int prow = (t / num_n) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
+          if (prow < p.M) {
+            const char* a = reinterpret_cast<const char*>(reinterpret_cast<const __half*>(p.epi.aux16) +
+                                                          static_cast<size_t>(prow) * p.ldo + (t % num_n) * BN);
+#pragma unroll
+            for (int i = 0; i < BN * 2 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + i * 128));
+          }
+        }
+      }
+    };
+    prefetch_aux(cid);
     for (int tile = cid; tile < total; tile += ncl) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      prefetch_aux(tile + ncl);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
