@@ -395,11 +395,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 constexpr int B2_BYTES = 128 * BLOCK_K * 2;             // this CTA's half of the 256-row W tile
 constexpr int STAGES2 = 6;
-// fp16 epilogues stage 32 rows x 64 columns per warp in shared memory (row pitch 144 B: conflict-free both ways) and
-// write them out as full 128-byte lines: the row-per-thread 16-byte stores of the first version reached only
+// fp16 epilogues stage 32 rows x 64 columns per warp in shared memory and write them out as full 128-byte lines: the row-per-thread 16-byte stores of the first version reached only
 // 1.6 TB/s on the store-bound K = 128 GEMMs (ncu r01 v3: attention projection 583 MB in 359 us)
-constexpr int STAGE_PITCH = 144;
-constexpr int STAGE_BYTES = 4 * 32 * STAGE_PITCH;
+// Eight epilogue warps: two per TMEM lane quarter, each taking one 128-column half of the accumulator.  The epilogue of
+// a 32-column chunk is a latency chain (tcgen05.ld -> wait -> operand loads -> math -> staged store), eight of them in a
+// row took about as long as the tile's MMAs with one warp per quarter (se_res 0.68, bias 0.79 of the bias_relu rate).
+constexpr int EPI_WARPS2 = 8;
+constexpr int THREADS2 = (4 + EPI_WARPS2) * 32;
+// staging rows are 128 bytes with the 16-byte chunk index XOR-ed with (row & 7): conflict-free for the row-per-lane
+// writes and for the line-per-8-lanes reads, without padding (8 x 4 KB fit next to six pipeline stages)
+constexpr int STAGE_PITCH = 128;
+constexpr int STAGE_BYTES = EPI_WARPS2 * 32 * STAGE_PITCH;
 constexpr int SMEM2_BYTES = 1024 + STAGES2 * (A_BYTES + B2_BYTES) + 256 + STAGE_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -436,7 +442,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 template <int MODE, bool BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -464,7 +470,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);   // multicast tcgen05.commit
-      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (leader's copy only)
+      mbar_init(&tempty[i], 2 * EPI_WARPS2);  // epilogue warps of both CTAs (leader's copy only)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -532,10 +538,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp >= 4) {
-    const int wq = warp & 3;
+    const int wq = warp & 3;           // TMEM lane quarter
+    const int half = (warp - 4) >> 2;  // which 128 accumulator columns
     int acc = 0;
     uint32_t acc_phase = 0;
-    // SE-residual epilogue: the residual operand (512 bytes of this thread's row per tile) does not depend on the
+    // SE-residual epilogue: the residual operand (256 bytes of this thread's row per tile) does not depend on the
     // accumulator, and read on demand it costs one DRAM latency per 32-column chunk -- eight in a row, about as long as
     // the tile's MMAs.  Its lines are pulled into L2 one tile ahead instead.
     auto prefetch_aux = [&](int t) {
@@ -544,9 +551,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const int prow = (t / num_n) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
           if (prow < p.M) {
             const char* a = reinterpret_cast<const char*>(reinterpret_cast<const __half*>(p.epi.aux16) +
-                                                          static_cast<size_t>(prow) * p.ldo + (t % num_n) * BN);
+                                                          static_cast<size_t>(prow) * p.ldo + (t % num_n) * BN + half * 128);
 #pragma unroll
-            for (int i = 0; i < BN * 2 / 128; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + i * 128));
+            for (int i = 0; i < 2; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + i * 128));
           }
         }
       }
@@ -560,11 +567,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
       if constexpr (MODE == B200D_EPI_CHEB) {
-#pragma unroll 1
-        for (int t = 0; t < BN / 128; ++t) cheb_epilogue_tile(p, row, t_row + t * 128, n_blk * (BN / 128) + t);
+        cheb_epilogue_tile(p, row, t_row + half * 128, n_blk * (BN / 128) + half);
       } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -576,11 +582,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       } else {
-        uint8_t* stage = stage_base + wq * 32 * STAGE_PITCH;
+        uint8_t* stage = stage_base + (warp - 4) * 32 * STAGE_PITCH;
         const int row_w0 = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32;  // first row of this warp
         __half* out16 = reinterpret_cast<__half*>(p.out);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * 4; c < half * 4 + 4; ++c) {
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -590,14 +596,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (row < p.M) epilogue_chunk<MODE, false>(p, row, n_blk * BN + c * 32, acc_f);
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(stage + lane * STAGE_PITCH + (c & 1) * 64 + j * 2) = pack8_f16(acc_f + j);
+            *reinterpret_cast<uint4*>(stage + lane * STAGE_PITCH + ((((c & 1) * 4 + (j >> 3)) ^ (lane & 7)) << 4)) = pack8_f16(acc_f + j);
           if (c & 1) {
             __syncwarp();
             const int col0 = n_blk * BN + (c - 1) * 32;  // 64 columns = 128 bytes per row
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3), seg = lane & 7;
-              const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + seg * 16);
+              const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + ((seg ^ (rr & 7)) << 4));
               if (row_w0 + rr < p.M)
                 *reinterpret_cast<uint4*>(out16 + static_cast<size_t>(row_w0 + rr) * p.ldo + col0 + seg * 8) = v;
             }
@@ -691,7 +697,7 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (p.N / 256);
   int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-  kern<<<2 * pairs, 256, SMEM2_BYTES, stream>>>(ta, tb, p);
+  kern<<<2 * pairs, THREADS2, SMEM2_BYTES, stream>>>(ta, tb, p);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
