@@ -106,9 +106,10 @@ typedef struct b200d_gemm_epilogue {
   const float* shift;     /* [N]  (TDNN) */
   const float* rowvec;    /* [M / rows_per_seg][N] (SE_RES: sigmoid gate; TDNN: per-segment bias) */
   const void* aux16;      /* __half [M][ldo]  (SE_RES main branch) */
-  /* CHEB: out32 = ca * (deg[m] * x32[m][c] - (A V)[m][c]) + cb * x32[m][c] + cc * xprev32[m][c] for the b = N / 4
-   *       block columns c; W (and, when vt != NULL, the output vt for the next step) is the 3-way bf16 split of V^T
-   *       laid out per 32 block columns as a 128-row tile [hi | mid | lo | pad]: vt [N][ldvt], N = 128 or 256.   */
+  /* CHEB: out32 = ca * (deg[m] * x32[m][c] - (A V)[m][c]) + cb * x32[m][c] + cc * xprev32[m][c] for the b block
+   *       columns c; W (and, when vt != NULL, the output vt for the next step) is the 3-way bf16 split of V^T,
+   *       part q of column c in row q * b + c ([hi | mid | lo]): b = 64 -> N = 192; b = 32 -> N = 128, the last
+   *       32 rows zero.  vt [N][ldvt].                                                                          */
   const float* deg;       /* [M] */
   const float* x32;       /* [M][ldx] */
   const float* xprev32;   /* [M][ldx] or NULL */
@@ -227,8 +228,8 @@ int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, int32_t ld,
  * returns Q = S R^-1 in evecs with (Y Q)^T (Y Q) = I for g = Y^T Y (CholQR).                       */
 int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream);
 /* y[n][b] = x[n][b] * q[b][b] (q NULL: y = x; y may alias x or be NULL); when vt_bf16 != NULL also the
- * 3-way bf16 split of y^T into vt_bf16 [4*b][ldvt] (per 32 columns a 128-row tile [hi | mid | lo | pad]):
- * the W operand of the next CHEB GEMM.                                                                   */
+ * 3-way bf16 split of y^T into vt_bf16 [3*b][ldvt], part q of column j in row q*b + j ([hi | mid | lo]):
+ * the W operand of the next CHEB GEMM (N = 192 for b = 64; N = 128 for b = 32, rows 96..127 zero).       */
 int b200d_right_mul(const float* x, int32_t n, int32_t b, int32_t ld, const float* q, float* y, void* vt_bf16, int32_t ldvt,
                     void* stream);
 /* Sparse form of the same step, for graphs built from few neighbours (at most 2 p non-zeros per row):

@@ -12,12 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _unsplit(vt, b, n):
-    """[4b, ldvt] bf16 tiles [hi | mid | lo | pad] per 32 columns -> float32 [n, b]"""
-    cols = []
-    for t in range(b // 32):
-        base = t * 128
-        cols.append(vt[base : base + 32, :n].float() + vt[base + 32 : base + 64, :n].float() + vt[base + 64 : base + 96, :n].float())
-    return torch.cat(cols, dim=0).t()
+    """[3b (+ padding), ldvt] bf16 parts [hi | mid | lo] of V^T, part q of column j in row q * b + j -> float32 [n, b]"""
+    return (vt[:b, :n].float() + vt[b : 2 * b, :n].float() + vt[2 * b : 3 * b, :n].float()).t()
 
 
 def _lap_batch(n, batch, seed):
@@ -122,6 +118,7 @@ def test_topp_binarize(dev, N, p):
 @pytest.mark.parametrize("n,b", [(500, 32), (5000, 64), (14399, 32)])
 def test_gram_smalleig_rightmul_resid(dev, n, b):
     from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200 import clustering as cl
     from whisper_nemo_b200._cabi import ptr
 
     g = torch.Generator().manual_seed(n + b)
@@ -139,7 +136,7 @@ def test_gram_smalleig_rightmul_resid(dev, n, b):
     _cabi.call("b200d_small_eig", ptr(G), b, None, ptr(Q), 1, _cabi._stream())
     xo = torch.empty_like(x)
     ldvt = (n + 7) // 8 * 8
-    vt = torch.zeros(4 * b, ldvt, dtype=torch.bfloat16, device=dev)
+    vt = torch.zeros(cl.cheb_operand_rows(b), ldvt, dtype=torch.bfloat16, device=dev)
     _cabi.call("b200d_right_mul", ptr(x), n, b, b, ptr(Q), ptr(xo), ptr(vt), ldvt, _cabi._stream())
     torch.cuda.synchronize()
     eye = xo.double().t() @ xo.double()
@@ -165,8 +162,13 @@ def test_gram_smalleig_rightmul_resid(dev, n, b):
     assert ((out.double() - ref_r).abs() / ref_r).max().item() < 1e-4
 
 
-@pytest.mark.parametrize("n,b", [(300, 32), (2399, 32), (5000, 64)])
-def test_cheb_gemm_step(dev, n, b):
+@pytest.mark.parametrize("n,b,pair", [(300, 32, True), (2399, 32, True), (3000, 64, True), (5000, 64, True), (5000, 64, False),
+                                      (10000, 64, False)])
+def test_cheb_gemm_step(dev, n, b, pair):
+    """One Chebyshev step on the tensor cores (N = 128 for 32 vectors, N = 192 for 64; the CTA-pair kernel from 4096 rows
+    unless it is switched off, as inside multi-stream regions) against fp64."""
+    import contextlib
+
     from whisper_nemo_b200 import _cabi
     from whisper_nemo_b200 import clustering as cl
     from whisper_nemo_b200._cabi import ptr
@@ -182,13 +184,15 @@ def test_cheb_gemm_step(dev, n, b):
     x = torch.randn(n, b, generator=g).to(dev)
     xp = torch.randn(n, b, generator=g).to(dev)
     ldvt = lda
-    vt_in = torch.zeros(4 * b, ldvt, dtype=torch.bfloat16, device=dev)
-    vt_out = torch.zeros(4 * b, ldvt, dtype=torch.bfloat16, device=dev)
+    nw = cl.cheb_operand_rows(b)
+    vt_in = torch.zeros(nw, ldvt, dtype=torch.bfloat16, device=dev)
+    vt_out = torch.zeros(nw, ldvt, dtype=torch.bfloat16, device=dev)
     _cabi.call("b200d_right_mul", ptr(x), n, b, b, None, None, ptr(vt_in), ldvt, _cabi._stream())
     out = torch.empty(n, b, dtype=torch.float32, device=dev)
     ca, cb, cc = 0.37, -1.2, 0.6
-    cl._gemm_cheb(a16, lda, vt_in, ldvt, n, 4 * b, out, deg, x, xp, ca, cb, cc, vt_out)
-    torch.cuda.synchronize()
+    with contextlib.nullcontext() if pair else _cabi.single_cta_gemms():
+        cl._gemm_cheb(a16, lda, vt_in, ldvt, n, nw, out, deg, x, xp, ca, cb, cc, vt_out)
+        torch.cuda.synchronize()
     ad = a.to(dev).double()
     want = ca * (deg.double()[:, None] * x.double() - ad @ x.double()) + cb * x.double() + cc * xp.double()
     err = (out.double() - want).abs().max().item()

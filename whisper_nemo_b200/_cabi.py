@@ -180,7 +180,7 @@ def call(name, *args):
             M, N, mode = args[4], args[5], args[9]._obj.mode
             work = 2.0 * M * N * args[6]
             # same rule as b200d_gemm_f16's dispatch (gemm_tcgen05.cu): which launches run the CTA-pair kernel
-            pair = _pair_kernel_on and N % 256 == 0 and ((M >= 4096) if mode == EPI_CHEB else (-(-M // 256) * (N // 256) >= 74))
+            pair = _pair_kernel_on and ((N == 192 and M >= 4096) if mode == EPI_CHEB else (N % 256 == 0 and -(-M // 256) * (N // 256) >= 74))
             key = f"{name}[{_EPI_NAMES[mode]}{'|2cta' if pair else ''}]"
         elif name == "b200d_small_eig":
             key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"

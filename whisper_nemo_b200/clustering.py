@@ -279,7 +279,13 @@ last_spectral_stats = SpectralStats()
 spectral_log: List[dict] = []  # one entry per bottom_eigvecs call (bounded; bench.py reports and clears it)
 
 
-def _gemm_cheb(A16, lda, vt_in, ldvt, n, nb4, out, deg, x, xprev, ca, cb, cc, vt_out):
+def cheb_operand_rows(b: int) -> int:
+    """Rows of the W operand of the Chebyshev GEMM for a block of b vectors: [hi | mid | lo] parts of b rows each
+    (b = 64: N = 192; b = 32: N = 128 with 32 zero rows, the narrowest tile of the kernel)."""
+    return 192 if b == 64 else 128
+
+
+def _gemm_cheb(A16, lda, vt_in, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vt_out):
     epi = GemmEpilogue()
     epi.mode = _cabi.EPI_CHEB
     epi.deg = deg.data_ptr()
@@ -289,7 +295,7 @@ def _gemm_cheb(A16, lda, vt_in, ldvt, n, nb4, out, deg, x, xprev, ca, cb, cc, vt
     epi.ldx = x.stride(0)
     epi.vt = vt_out.data_ptr() if vt_out is not None else None
     epi.ldvt = ldvt
-    _cabi.call("b200d_gemm_f16", ptr(A16), lda, ptr(vt_in), ldvt, n, nb4, n, ptr(out), out.stride(0), ctypes.byref(epi), _s())
+    _cabi.call("b200d_gemm_f16", ptr(A16), lda, ptr(vt_in), ldvt, n, nw, n, ptr(out), out.stride(0), ctypes.byref(epi), _s())
 
 
 def _spmm_cheb(csr, n, b, out, deg, x, xprev, ca, cb, cc):
@@ -351,7 +357,7 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         raise NotImplementedError(f"spectral embedding for {k} clusters: the subspace block is limited to 64 vectors")
     if n < 2 * b:
         raise NotImplementedError(f"spectral embedding of {k} clusters on {n} points: needs n >= {2 * b} (or n <= {DENSE_EIG_MAX})")
-    nb4 = 4 * b
+    nw = cheb_operand_rows(b)
     ldvt = (n + 7) // 8 * 8
     st = SpectralStats()  # per call: long-form chunks run this from several threads
     sparse = _use_csr_products(n, p)
@@ -368,10 +374,10 @@ def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e
         def step(vin, out, x, xprev, ca, cb, cc, vout):
             _spmm_cheb(csr, n, b, out, deg, x, xprev, ca, cb, cc)
     else:
-        vt = [torch.zeros(nb4, ldvt, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        vt = [torch.zeros(nw, ldvt, dtype=torch.bfloat16, device=dev) for _ in range(2)]
 
         def step(vin, out, x, xprev, ca, cb, cc, vout):
-            _gemm_cheb(a16, lda, vin, ldvt, n, nb4, out, deg, x, xprev, ca, cb, cc, vout)
+            _gemm_cheb(a16, lda, vin, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vout)
     G, Q, theta, resid = f32(b, b), f32(b, b), f32(b), f32(b)
     gws_bytes = _cabi.load().b200d_gram_workspace_bytes(n, b)
     gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev)

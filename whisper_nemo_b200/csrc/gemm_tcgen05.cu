@@ -123,9 +123,9 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 
 template <int BLOCK_N>
 struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192) ? 5 : 6;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 or 256: power of two
+  static constexpr int TMEM_COLS = (BLOCK_N > 128) ? 512 : 256;  // two accumulators, allocation a power of two
   static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
@@ -206,8 +206,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   }
 }
 
-// Chebyshev epilogue: the W operand holds V^T split into three bf16 parts, 32 block columns per 128-row tile as
-// [hi | mid | lo | pad], so acc columns (c, 32 + c, 64 + c) of tile t sum to (A V)[row][32 t + c] at ~fp32 accuracy.
+// Chebyshev epilogue.  The W operand holds V^T (b = 32 or 64 block vectors) split into three bf16 parts, part q of
+// vector j in row q * b + j: [hi | mid | lo] (b = 64: N = 192; b = 32: N = 128 with 32 zero rows of padding), so the
+// accumulator columns (j, b + j, 2 b + j) sum to (A V)[row][j] at ~fp32 accuracy on the exactly representable graph.
 __device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
   h = __float2bfloat16_rn(v);
   float r = v - __bfloat162float(h);
@@ -216,23 +217,21 @@ __device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& h, __nv_bflo
   l = __float2bfloat16_rn(r);
 }
 
-// One 128-column accumulator tile of the Chebyshev step: W holds V^T split into three bf16 parts, 32 block columns per
-// 128-row tile as [hi | mid | lo | pad], so accumulator columns (c, 32 + c, 64 + c) of tile `vt_tile` sum to
-// (A V)[row][32 vt_tile + c] at ~fp32 accuracy.  Also emits the same split of the result for the next step.
-__device__ __forceinline__ void cheb_epilogue_tile(const GemmParams& p, int row, uint32_t t_addr, int vt_tile) {
+// 32 block vectors [c0, c0 + 32) of one accumulator row: the Chebyshev step y = ca (deg x - A x) + cb x + cc xprev and
+// the same 3-way split of y for the next step's W operand.
+template <int B>
+__device__ __forceinline__ void cheb_epilogue_cols(const GemmParams& p, int row, uint32_t t_addr, int c0) {
   const b200d_gemm_epilogue& e = p.epi;
-  constexpr int bpad = 32;
-  const int cb = vt_tile * bpad;  // first block column of this tile
   uint32_t r0[32], r1[32], r2[32];
-  tmem_ld32(t_addr, r0);
-  tmem_ld32(t_addr + bpad, r1);
-  tmem_ld32(t_addr + 2 * bpad, r2);
+  tmem_ld32(t_addr + c0, r0);
+  tmem_ld32(t_addr + B + c0, r1);
+  tmem_ld32(t_addr + 2 * B + c0, r2);
   tmem_ld_wait();
   if (row < p.M) {
     const float dg = __ldg(e.deg + row);
-    const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + cb;
-    const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + cb : nullptr;
-    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + cb;
+    const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + c0;
+    const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + c0 : nullptr;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c0;
     __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -244,10 +243,10 @@ __device__ __forceinline__ void cheb_epilogue_tile(const GemmParams& p, int row,
       if (vh) {
         __nv_bfloat16 h, m, l;
         split3_bf16(y, h, m, l);
-        const size_t vrow = static_cast<size_t>(vt_tile) * 128 + j;
+        const size_t vrow = static_cast<size_t>(c0 + j);
         vh[(vrow) * e.ldvt + row] = h;
-        vh[(vrow + bpad) * e.ldvt + row] = m;
-        vh[(vrow + 2 * bpad) * e.ldvt + row] = l;
+        vh[(vrow + B) * e.ldvt + row] = m;
+        vh[(vrow + 2 * B) * e.ldvt + row] = l;
       }
     }
   }
@@ -352,8 +351,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
       if constexpr (MODE == B200D_EPI_CHEB) {
+        constexpr int B = (BLOCK_N == 192) ? 64 : 32;  // one block of vectors per launch (N == BLOCK_N)
 #pragma unroll 1
-        for (int t = 0; t < BLOCK_N / 128; ++t) cheb_epilogue_tile(p, row, t_row + t * 128, n_blk * (BLOCK_N / 128) + t);
+        for (int c0 = 0; c0 < B; c0 += 32) cheb_epilogue_cols<B>(p, row, t_row, c0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -444,7 +444,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 template <int MODE, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int BN = 256;
+  constexpr int BN = (MODE == B200D_EPI_CHEB) ? 192 : 256;  // Chebyshev: 64 vectors x [hi | mid | lo]
+  constexpr int B_HALF_BYTES = (BN / 2) * BLOCK_K * 2;      // bytes this CTA loads per stage (the slot stays B2_BYTES)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -496,12 +497,12 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int tile = cid; tile < total; tile += ncl) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         const int row_a = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
-        const int row_b = n_blk * BN + static_cast<int>(rank) * 128;
+        const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           tma_load_2d_2sm(sA + stage * A_BYTES, &tmA, &full[stage], kb * BLOCK_K, row_a);
           tma_load_2d_2sm(sB + stage * B2_BYTES, &tmB, &full[stage], kb * BLOCK_K, row_b);
-          if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B2_BYTES));
+          if (leader) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_HALF_BYTES));
           else mbar_arrive_leader(&full[stage]);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
@@ -509,7 +510,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      // D fp32, A/B fp16 K-major, N = 256, M = 256 (both CTAs)
+      // D fp32, A/B fp16 K-major, N = BN, M = 256 (both CTAs)
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                  (static_cast<uint32_t>((2 * BLOCK_M) >> 4) << 24);
@@ -567,7 +568,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
       if constexpr (MODE == B200D_EPI_CHEB) {
-        cheb_epilogue_tile(p, row, t_row + half * 128, n_blk * (BN / 128) + half);
+        cheb_epilogue_cols<64>(p, row, t_row, half * 32);
       } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
 #pragma unroll 1
         for (int c = half * 4; c < half * 4 + 4; ++c) {
@@ -695,7 +696,8 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     attr_set = true;
   }
-  const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (p.N / 256);
+  constexpr int BN = (MODE == B200D_EPI_CHEB) ? 192 : 256;
+  const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (p.N / BN);
   int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   kern<<<2 * pairs, THREADS2, SMEM2_BYTES, stream>>>(ta, tb, p);
   B200D_CHECK_LAUNCH();
@@ -724,7 +726,7 @@ static int dispatch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
     case B200D_EPI_TDNN: return launch<BLOCK_N, B200D_EPI_TDNN, false>(ta, tb, p, s);
     case B200D_EPI_BIAS_F32: return launch<BLOCK_N, B200D_EPI_BIAS_F32, false>(ta, tb, p, s);
     case B200D_EPI_SIGMOID_F32: return launch<BLOCK_N, B200D_EPI_SIGMOID_F32, false>(ta, tb, p, s);
-    case B200D_EPI_CHEB: return launch<BLOCK_N, B200D_EPI_CHEB, true>(ta, tb, p, s);
+    default: break;  // B200D_EPI_CHEB is launched by b200d_gemm_f16 directly (its tile width is the block's N)
   }
   return set_error(B200D_EINVAL, "%s: unknown epilogue mode%s", "b200d_gemm_f16");
 }
@@ -741,13 +743,13 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
                               int32_t ldo, const b200d_gemm_epilogue* epi, void* stream) {
   B200D_CHECK_ARG(A && W && out && epi);
   B200D_CHECK_ARG(M > 0 && N > 0 && K > 0);
-  B200D_CHECK_ARG(N % 128 == 0);
+  B200D_CHECK_ARG(N % 128 == 0 || (epi->mode == B200D_EPI_CHEB && N == 192));
   B200D_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0);
   B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const int mode = epi->mode;
   if (mode == B200D_EPI_CHEB) {
-    B200D_CHECK_ARG(N == 128 || N == 256);  // block of 32 or 64 vectors: one or two [hi | mid | lo | pad] tiles
+    B200D_CHECK_ARG(N == 128 || N == 192);  // block of 32 vectors ([hi | mid | lo | pad]) or of 64 ([hi | mid | lo])
     B200D_CHECK_ARG(epi->deg && epi->x32);
     B200D_CHECK_ARG(epi->vt == nullptr || epi->ldvt >= M);
   } else {
@@ -757,21 +759,25 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
     if (mode == B200D_EPI_BIAS || mode == B200D_EPI_BIAS_RELU || mode == B200D_EPI_BIAS_F32) B200D_CHECK_ARG(epi->bias);
   }
   const bool bf16 = mode == B200D_EPI_CHEB;
-  const int block_n = (N % 256 == 0) ? 256 : 128;
+  const int block_n = (mode == B200D_EPI_CHEB) ? N : (N % 256 == 0) ? 256 : 128;
   // CTA-pair kernel when there is at least one 256 x 256 tile per TPC (the large pointwise convs), and for the
   // Chebyshev products of 64-vector blocks on large graphs (L2-traffic bound: the pair halves the W bytes per SM)
   static const bool env_allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
   const bool allow_2cta = env_allow_2cta && g_pair_kernel_enabled.load(std::memory_order_relaxed) != 0;
   const long long tiles2 = static_cast<long long>((M + 255) / 256) * (N / 256);
-  const bool use_2cta = allow_2cta && block_n == 256 && (mode == B200D_EPI_CHEB ? M >= 4096 : tiles2 >= kNumSMs / 2);
+  const bool use_2cta = allow_2cta && (mode == B200D_EPI_CHEB ? (N == 192 && M >= 4096) : (block_n == 256 && tiles2 >= kNumSMs / 2));
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&tb, W, bf16, N, K, ldw, use_2cta ? 128 : block_n);
+  rc = make_map(&tb, W, bf16, N, K, ldw, use_2cta ? (mode == B200D_EPI_CHEB ? 96 : 128) : block_n);
   if (rc) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.epi = *epi;
   if (use_2cta) return dispatch_mode_2cta(ta, tb, p, as_stream(stream));
+  if (mode == B200D_EPI_CHEB) {
+    if (N == 192) return launch<192, B200D_EPI_CHEB, true>(ta, tb, p, as_stream(stream));
+    return launch<128, B200D_EPI_CHEB, true>(ta, tb, p, as_stream(stream));
+  }
   if (block_n == 256) return dispatch_mode<256>(ta, tb, p, as_stream(stream));
   return dispatch_mode<128>(ta, tb, p, as_stream(stream));
 }

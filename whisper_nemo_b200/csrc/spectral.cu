@@ -245,8 +245,8 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16&
   l = __float2bfloat16_rn(r);
 }
 
-// y[n][b] = x[n][b] q[b][b]  (y may alias x).  vt (optional): bf16 [4*b][ldvt]: per 32 columns of y a 128-row tile
-// [hi | mid | lo | pad] of y^T (the W operand layout of the CHEB GEMM).
+// y[n][b] = x[n][b] q[b][b]  (y may alias x).  vt (optional): bf16 [3*b][ldvt] = [hi | mid | lo] of y^T, part q of
+// column j in row q * b + j (the W operand layout of the CHEB GEMM; for b = 32 the buffer has 32 more, zero, rows).
 // q == nullptr: y = x (only the split is produced).
 template <int B>
 __global__ void __launch_bounds__(256) right_mul_kernel(const float* __restrict__ x, int n, int ld, const float* __restrict__ q,
@@ -294,10 +294,10 @@ __global__ void __launch_bounds__(256) right_mul_kernel(const float* __restrict_
       if (row0 + rr < n) {
         __nv_bfloat16 h, m, l;
         split3(so[rr][col], h, m, l);
-        const size_t vrow = static_cast<size_t>(col >> 5) * 128 + (col & 31);  // 32 columns per [hi | mid | lo | pad] tile
+        const size_t vrow = static_cast<size_t>(col);  // part q of vector j in row q * B + j: [hi | mid | lo]
         vt[vrow * ldvt + row0 + rr] = h;
-        vt[(vrow + 32) * ldvt + row0 + rr] = m;
-        vt[(vrow + 64) * ldvt + row0 + rr] = l;
+        vt[(vrow + B) * ldvt + row0 + rr] = m;
+        vt[(vrow + 2 * B) * ldvt + row0 + rr] = l;
       }
     }
   }
