@@ -95,6 +95,47 @@ def test_longform_bookkeeping_equals_oracle():
             assert torch.equal(res[0], res[1])
 
 
+def test_nme_ratios_equal_the_per_p_loop():
+    """The vectorised eigengap analysis == upstream's loop over p (NMESC.getEigRatio), bit for bit, ties included."""
+    from whisper_nemo_b200.clustering import nme_ratios
+
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n = int(rng.integers(20, 600))
+        max_spk = int(rng.integers(2, 12))
+        n_low = min(max_spk, n - 1) + 1
+        np_ = int(rng.integers(1, 40))
+        p_list = sorted(int(v) for v in rng.integers(2, max(3, n // 4), np_))
+        lam = np.sort(rng.random((np_, n_low)) * rng.choice([1e-3, 1.0, 50.0]), axis=1)
+        if trial % 3 == 0:  # exact ties between eigengaps
+            lam = np.round(lam * 4) / 4
+        evals = torch.from_numpy(np.concatenate([lam, lam[:, -1:] + rng.random((np_, 1)) * 10], axis=1).astype(np.float32))
+        spk, g = nme_ratios(evals, p_list, n, max_spk, 1e-10)
+        for i, p_neighbors in enumerate(p_list):
+            lambdas, lam_max = evals[i, :n_low], evals[i, n_low]
+            gap = lambdas[1:] - lambdas[:-1]
+            want_spk = torch.argmax(gap[: min(max_spk, gap.shape[0])]) + 1
+            key = torch.argsort(gap[:max_spk], descending=True)[0]
+            max_eig_gap = gap[key] / (lam_max.item() + 1e-10)
+            want_g = (p_neighbors / n) / (max_eig_gap + 1e-10)
+            assert float(spk[i]) == float(want_spk)
+            assert torch.equal(g[i], want_g.float()) or (torch.isinf(g[i]) and torch.isinf(want_g)), (trial, i, g[i], want_g)
+
+
+@pytest.mark.parametrize("n", [7, 100, 10000, 51261])
+def test_batched_cpu_rng_draws_equal_sequential_draws(n):
+    """kmeans_torch draws its k-means++ uniforms and fallback indices in two batched calls; upstream draws them one
+    center at a time -- the CPU generator must give the same numbers either way."""
+    g = torch.Generator().manual_seed(3)
+    torch.randint(0, n, (1,), generator=g)
+    seq_r = torch.stack([torch.rand(30, generator=g) for _ in range(49)])
+    seq_f = torch.cat([torch.randint(n, (1,), generator=g) for _ in range(200)])
+    g = torch.Generator().manual_seed(3)
+    torch.randint(0, n, (1,), generator=g)
+    assert torch.equal(torch.rand(49, 30, generator=g), seq_r)
+    assert torch.equal(torch.randint(n, (200,), generator=g), seq_f)
+
+
 def test_nmesc_p_value_list_equals_oracle():
     for n in (7, 37, 110, 515, 600, 1023):
         for thr, vol in ((0.25, 30), (0.15, 10), (0.05, 30)):

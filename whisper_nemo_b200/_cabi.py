@@ -145,14 +145,17 @@ KERNELS_PER_CALL = {
 }
 launch_count = 0
 _pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None  # mirrors b200d_gemm_set_pair_kernel for the profile labels
-_profile = None  # {name: [(event0, event1, work)]} while a profiled step runs
+_profile = None  # {name: [(event0, event1, work, stream)]} while a profiled step runs
+_profile_base = None
 
 
 def start_profile():
     """Record a CUDA-event pair around every C-ABI call (bench.py's per-kernel roofline leg; adds event overhead,
     so it is never active during the timed steps)."""
-    global _profile
+    global _profile, _profile_base
     _profile = {}
+    _profile_base = torch.cuda.Event(enable_timing=True)
+    _profile_base.record()
 
 
 def stop_profile():
@@ -162,7 +165,14 @@ def stop_profile():
     torch.cuda.synchronize()
     out = {}
     for name, spans in (prof or {}).items():
-        out[name] = {"calls": len(spans), "ms": sum(e0.elapsed_time(e1) for e0, e1, _ in spans), "work": sum(w for _, _, w in spans)}
+        out[name] = {"calls": len(spans), "ms": sum(e0.elapsed_time(e1) for e0, e1, *_ in spans), "work": sum(sp[2] for sp in spans)}
+    path = os.environ.get("B200D_TIMELINE")  # development aid: per-call (key, stream, start ms, end ms) of the profiled step
+    if path and prof:
+        import json
+
+        rows = [(name, sp[3], _profile_base.elapsed_time(sp[0]), _profile_base.elapsed_time(sp[1])) for name, spans in prof.items() for sp in spans]
+        with open(path, "w") as f:
+            json.dump(sorted(rows, key=lambda r: r[2]), f)
     return out
 
 
@@ -184,11 +194,33 @@ def call(name, *args):
             key = f"{name}[{_EPI_NAMES[mode]}{'|2cta' if pair else ''}]"
         elif name == "b200d_small_eig":
             key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"
-        _profile.setdefault(key, []).append((e0, e1, work))
+        _profile.setdefault(key, []).append((e0, e1, work, torch.cuda.current_stream().cuda_stream))
     else:
         rc = fn(*args)
     launch_count += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
+
+
+class short_gil_switch:
+    """Context manager around a region where several host threads drive one stream each: a thread coming back from a
+    device->host wait needs the GIL to launch its next kernels, and with CPython's default 5 ms switch interval it
+    queued behind the other thread's launch loop for milliseconds (visible as idle gaps on its stream)."""
+
+    def __init__(self, seconds: float = 1e-4):
+        self.seconds = seconds
+
+    def __enter__(self):
+        import sys
+
+        self.prev = sys.getswitchinterval()
+        sys.setswitchinterval(self.seconds)
+        return self
+
+    def __exit__(self, *exc):
+        import sys
+
+        sys.setswitchinterval(self.prev)
+        return False
 
 
 class single_cta_gemms:

@@ -159,6 +159,21 @@ def getAffinityGraphMat(affinity_mat_raw: torch.Tensor, p_value: int):
 
 
 # ----------------------------------------------------------------------------- NME analysis
+def nme_ratios(evals: torch.Tensor, p_value_list: List[int], n: int, max_num_speakers: int, eps: float = 1e-10):
+    """getEigRatio for every p of the sweep at once (host, float32 as upstream's per-p loop): evals [np, n_low + 1] holds
+    the n_low lowest eigenvalues of each Laplacian and, last, its largest.  Returns (speaker counts, g_p) as float32
+    [np]: count = argmax of the first max_num_speakers eigengaps + 1, g_p = (p / n) / (max gap / (lambda_max + eps) + eps)."""
+    lambdas, lam_max = evals[:, :-1], evals[:, -1]
+    gaps = (lambdas[:, 1:] - lambdas[:, :-1])[:, :max_num_speakers]
+    num_of_spk = torch.argmax(gaps, dim=1) + 1
+    max_key = torch.argsort(gaps, dim=1, descending=True)[:, :1]
+    max_eig_gap = gaps.gather(1, max_key)[:, 0] / (lam_max.double() + eps).float()
+    # upstream's `(p / n) / (tensor + eps)` is Tensor.__rtruediv__: reciprocal(tensor + eps) * float32(p / n)
+    p_over_n = (torch.tensor([float(p) for p in p_value_list], dtype=torch.float64) / n).float()
+    g_p = torch.reciprocal(max_eig_gap + eps) * p_over_n
+    return num_of_spk.float(), g_p
+
+
 class NMESC:
     """Normalized-maximum-eigengap analysis (upstream class of the same name): p-neighbour sweep on
     a strided subsample.  The subsample is ranked once; every p of the sweep is then an
@@ -219,18 +234,7 @@ class NMESC:
             _cabi.call("b200d_eigvals_batched", ptr(lap), len(pl), n, n_low, ptr(evals), ptr(ws), ws_bytes, _s())
             evals_all.append(evals)
         evals = torch.cat(evals_all).cpu()  # [np, n_low + 1]  (the sweep's only device->host read)
-        eig_ratio_list = torch.zeros(np_)
-        est_num_of_spk_list = torch.zeros(np_)
-        for i, p_neighbors in enumerate(self.p_value_list):
-            lambdas = evals[i, :n_low]
-            lam_max = evals[i, n_low]
-            lambda_gap_list = lambdas[1:] - lambdas[:-1]
-            num_of_spk = torch.argmax(lambda_gap_list[: min(self.max_num_speakers, lambda_gap_list.shape[0])]) + 1
-            arg_sorted_idx = torch.argsort(lambda_gap_list[: self.max_num_speakers], descending=True)
-            max_key = arg_sorted_idx[0]
-            max_eig_gap = lambda_gap_list[max_key] / (lam_max.item() + self.eps)
-            g_p = (p_neighbors / n) / (max_eig_gap + self.eps)
-            est_num_of_spk_list[i], eig_ratio_list[i] = num_of_spk, g_p
+        est_num_of_spk_list, eig_ratio_list = nme_ratios(evals, self.p_value_list, n, self.max_num_speakers, self.eps)
         index_nn = int(torch.argmin(eig_ratio_list))
         rp_p_value = self.p_value_list[index_nn]
         reach = self._reach(rank, rankT, n, [rp_p_value])
@@ -501,9 +505,11 @@ def kmeans_torch(X: torch.Tensor, num_clusters: int, threshold: float = 1e-4, it
         return torch.zeros(n, dtype=torch.int64, device=dev)
     gen = torch.Generator(device="cpu").manual_seed(int(random_state))
     first = int(torch.randint(0, n, (1,), generator=gen).item())
-    rands = torch.stack([torch.rand(n_local_trials, generator=gen) for _ in range(num_clusters - 1)])
+    # one draw per center / per fallback index upstream; the CPU generator fills a batched draw in the same order
+    # (tests/test_cpu_host.py pins that), and 250 tiny torch calls were ~2 ms on each chunk's critical path
+    rands = torch.rand(num_clusters - 1, n_local_trials, generator=gen)
     n_fb = 4 * num_clusters
-    fallback = torch.cat([torch.randint(n, (1,), generator=gen) for _ in range(n_fb)]).to(torch.int32)
+    fallback = torch.randint(n, (n_fb,), generator=gen).to(torch.int32)
     rands_d, fb_d = rands.to(dev), fallback.to(dev)
     labels = torch.empty(n, dtype=torch.int32, device=dev)
     ws_bytes = _cabi.load().b200d_kmeans_workspace_bytes(n, dim, num_clusters, n_local_trials)

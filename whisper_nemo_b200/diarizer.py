@@ -258,7 +258,7 @@ class ClusteringDiarizer:
                 free.append(st)
 
         main.synchronize()
-        with _cabi.single_cta_gemms(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+        with _cabi.single_cta_gemms(), _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
             results = dict(f.result() for f in [pool.submit(work, k, plan) for k, plan in self._scales.items()])
             for st in streams:
                 st.synchronize()
@@ -347,7 +347,7 @@ class ClusteringDiarizer:
                 finally:
                     free.append(st)
 
-            with _cabi.single_cta_gemms(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+            with _cabi.single_cta_gemms(), _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
                 for uniq_id, res in [f.result() for f in [pool.submit(work, u) for u in todo]]:
                     pending[uniq_id] = res
         timer.stop(h)

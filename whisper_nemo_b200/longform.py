@@ -49,24 +49,27 @@ def get_scale_interpolated_embs(multiscale_weights, embeddings_in_scales, timest
 
 def calculate_removable_counts(removable_counts_mat: torch.Tensor, remain_count: int, num_clus: int) -> torch.Tensor:
     """Spread `remain_count` kept vectors over the clusters as evenly as their sizes allow
-    (water-filling from the largest cluster down); returns how many vectors each cluster gives up."""
-    asc = torch.sort(removable_counts_mat)[0]
-    order = torch.sort(removable_counts_mat, descending=True)[1]
-    padded = torch.cat([torch.tensor([0]), asc, torch.tensor([0])])
+    (water-filling from the largest cluster down); returns how many vectors each cluster gives up.
+    The two orderings come from torch.sort (upstream's tie order); the arithmetic on <= 50 integers is numpy --
+    as torch CPU ops it cost milliseconds per chunk on the critical path of the long-form stage."""
+    asc = torch.sort(removable_counts_mat)[0].numpy()
+    order = torch.sort(removable_counts_mat, descending=True)[1].numpy()
+    counts = removable_counts_mat.numpy().copy()
+    padded = np.concatenate([[0], asc, [0]])
     steps = (padded[1:] - padded[:-1])[:num_clus]
-    level_cost = torch.cumsum(torch.arange(num_clus, 0, -1) * steps, dim=0)
+    level_cost = np.cumsum(np.arange(num_clus, 0, -1) * steps).tolist()
     level = 0
     for level, cost in enumerate(level_cost):
         if remain_count < cost:
             break
     left = remain_count
     for j in range(level):
-        removable_counts_mat[order[: num_clus - j]] -= steps[j]
-        left -= int(steps[j].item()) * (num_clus - j)
+        counts[order[: num_clus - j]] -= steps[j]
+        left -= int(steps[j]) * (num_clus - j)
     share, extra = divmod(left, num_clus - level)
-    removable_counts_mat[order[: num_clus - level]] -= share
-    removable_counts_mat[order[:extra]] -= 1
-    return removable_counts_mat.int()
+    counts[order[: num_clus - level]] -= share
+    counts[order[:extra]] -= 1
+    return torch.from_numpy(counts).int()
 
 
 def get_merge_quantity(num_to_be_removed: int, pre_clus_labels: torch.Tensor, min_count_per_cluster: int) -> torch.Tensor:
@@ -131,52 +134,57 @@ class LongFormSpeakerClustering:
         return labels
 
     def _reduce_chunk(self, emb_part: torch.Tensor, mat: torch.Tensor, Y_part: torch.Tensor, class_target_vol: torch.Tensor,
-                      offset_index: int):
+                      offset_index: int, y_host: torch.Tensor = None):
         """run_reducer for every cluster of one chunk.  Returns ([merged_embs per cluster], [index mappings]).
         The index bookkeeping (<= 50 clusters) is host work on the labels; the embedding traffic is three device
         operations for the whole chunk: within-cluster affinity mass, merged means, one gather."""
         n, d = emb_part.shape
         dev = emb_part.device
-        y_host = Y_part.cpu()
+        y_np = (Y_part.cpu() if y_host is None else y_host).numpy()
         vols = [int(v) for v in class_target_vol.tolist()]
-        mass_host = None
+        mass_np = None
         if mat is not None and sum(vols) > 0:
             mass = torch.empty(n, dtype=torch.float32, device=dev)
             y32 = Y_part.to(torch.int32).contiguous()
             _cabi.call("b200d_masked_rowsum", ptr(mat), n, ptr(y32), ptr(mass), _s())
-            mass_host = mass.cpu()
+            mass_np = mass.cpu().numpy()
+        # members of every cluster in ascending window order (== torch.where(labels == c)[0]) from one stable sort
+        by_label = np.argsort(y_np, kind="stable")
+        bounds = np.searchsorted(y_np[by_label], np.arange(len(vols) + 1))
         mapping_list, sizes = [], []
         sel_idx, seg_off, order = [], [0], []  # merged-mean members / their segment offsets / final gather order
         n_avg = 0
+        none = torch.arange(0)
         for spk_idx, merge_quantity in enumerate(vols):
-            target = torch.where(y_host == spk_idx)[0]
+            target = by_label[bounds[spk_idx] : bounds[spk_idx + 1]]
             if merge_quantity > 0:
                 if merge_quantity > target.shape[0] - 1:
                     raise ValueError("merge_quantity is larger than the half of targeted speaker's labels")
-                rank = torch.argsort(mass_host[target], descending=True)
-                selected, rest_sorted = rank[: merge_quantity + 1], rank[merge_quantity + 1 :].sort()[0]
+                # the ranking is upstream's torch call (its tie order); the index bookkeeping around it is numpy
+                rank = torch.argsort(torch.from_numpy(mass_np[target]), descending=True).numpy()
+                selected, rest_sorted = rank[: merge_quantity + 1], np.sort(rank[merge_quantity + 1 :])
                 sel_idx.append(target[selected])
-                seg_off.append(seg_off[-1] + selected.numel())
+                seg_off.append(seg_off[-1] + selected.size)
                 order.append(target[rest_sorted])
-                order.append(torch.tensor([n + n_avg]))  # row of the merged vector in [emb_part ; means]
+                order.append(np.array([n + n_avg]))  # row of the merged vector in [emb_part ; means]
                 n_avg += 1
-                mapping_list.append((target[rest_sorted] + offset_index, target[selected] + offset_index))
-                sizes.append(int(rest_sorted.numel()) + 1)
+                mapping_list.append((torch.from_numpy(target[rest_sorted] + offset_index), torch.from_numpy(target[selected] + offset_index)))
+                sizes.append(int(rest_sorted.size) + 1)
                 if target.shape[0] - merge_quantity != sizes[-1]:
                     raise ValueError("Reducer output is not matched to the target quantity")
             else:
                 order.append(target)
-                mapping_list.append((target + offset_index, torch.arange(0)))
-                sizes.append(int(target.numel()))
+                mapping_list.append((torch.from_numpy(target + offset_index), none))
+                sizes.append(int(target.size))
         src = emb_part
         if n_avg > 0:
-            idx_d = torch.cat(sel_idx).to(torch.int32).to(dev)
+            idx_d = torch.from_numpy(np.concatenate(sel_idx).astype(np.int32)).to(dev)
             off_d = torch.tensor(seg_off, dtype=torch.int32).to(dev)
             means = torch.empty(n_avg, d, dtype=torch.float32, device=dev)
             x = emb_part.contiguous()
             _cabi.call("b200d_gather_segment_mean", ptr(x), d, ptr(idx_d), ptr(off_d), n_avg, ptr(means), _s())
             src = torch.cat([emb_part, means], dim=0)
-        merged_all = src.index_select(0, torch.cat(order).to(dev)) if order else src[:0]
+        merged_all = src.index_select(0, torch.from_numpy(np.concatenate(order)).to(dev)) if order else src[:0]
         merged_list = list(torch.split(merged_all, sizes, dim=0))
         return merged_list, mapping_list
 
@@ -220,7 +228,7 @@ class LongFormSpeakerClustering:
             y_host = Y_part.cpu()
             min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
             class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
-            return self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index)
+            return self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index, y_host)
 
         mine = [w for w in range(n_chunks) if w % world == rank]
         want = self.chunk_streams if self.chunk_streams is not None else int(os.environ.get("B200D_CHUNK_STREAMS", "2"))
@@ -251,7 +259,7 @@ class LongFormSpeakerClustering:
                     return merged_list, mapping_list
 
             main.synchronize()  # nothing of the single-stream phase (CTA-pair GEMMs) may still be running
-            with _cabi.single_cta_gemms(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+            with _cabi.single_cta_gemms(), _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
                 futures = {w: pool.submit(work, w, streams[i % n_streams]) for i, w in enumerate(mine)}
                 for w, fut in futures.items():
                     per_chunk[w] = fut.result()
