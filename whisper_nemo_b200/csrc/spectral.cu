@@ -73,9 +73,12 @@ __global__ void gram_combine_kernel(const float* __restrict__ part, int nparts, 
 // ------------------------------------------------------------------------------------ small_eig
 // mode 0: eigen-decomposition by parallel cyclic Jacobi (round-robin pairing) in fp64.
 // mode 1: scaled Cholesky G = S^-1 R^T R S^-1, returns Q = S R^-1 so that (Y Q)^T (Y Q) = I.
-template <typename VT>
-__global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict__ g, int b, float* __restrict__ evals,
+// BT: the matrix order when it is known at compile time (32 / 64, the subspace blocks: every index division becomes a
+// shift), 0 = run-time order.
+template <typename VT, int BT>
+__global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict__ g, int b_rt, float* __restrict__ evals,
                                                          float* __restrict__ evecs, int mode) {
+  const int b = BT > 0 ? BT : b_rt;
   extern __shared__ double sd[];
   double* A = sd;                                   // [b][b]
   VT* V = reinterpret_cast<VT*>(sd + b * b);        // [b][b] accumulated rotations (fp32 only for b > 96)
@@ -184,9 +187,12 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
         const double apq = A[p * b + q], app = A[p * b + p], aqq = A[q * b + q];
         double c = 1.0, s = 0.0;
         if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * (fabs(app) + fabs(aqq))) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
+          // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), written with one sqrt, one division
+          // and one rsqrt: this warp's dependent fp64 chain is the serial part of every round
+          const double da = aqq - app, b2 = 2.0 * apq;
+          double t = fabs(b2) / (fabs(da) + sqrt(fma(da, da, b2 * b2)));
+          if (da != 0.0 && ((da < 0.0) != (b2 < 0.0))) t = -t;
+          c = rsqrt(fma(t, t, 1.0));
           s = t * c;
         }
         s_c[k] = c; s_s[k] = s; s_p[k] = p; s_q[k] = q;
@@ -361,13 +367,19 @@ extern "C" int b200d_small_eig(const float* g, int32_t b, float* evals, float* e
   B200D_CHECK_ARG(g && evecs && b >= 2 && b <= kMaxJacobi && b % 2 == 0 && (mode == 0 || mode == 1) && (mode == 1 || evals));
   static bool attr_set = false;
   if (!attr_set) {
-    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 96 * 96 * sizeof(double)));
-    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const int big = 2 * 96 * 96 * sizeof(double);
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           kMaxJacobi * kMaxJacobi * (sizeof(double) + sizeof(float))));
     attr_set = true;
   }
-  if (b <= 96) small_eig_kernel<double><<<1, 512, static_cast<size_t>(2) * b * b * sizeof(double), as_stream(stream)>>>(g, b, evals, evecs, mode);
-  else small_eig_kernel<float><<<1, 512, static_cast<size_t>(b) * b * (sizeof(double) + sizeof(float)), as_stream(stream)>>>(g, b, evals, evecs, mode);
+  cudaStream_t st = as_stream(stream);
+  const size_t smem64 = static_cast<size_t>(2) * b * b * sizeof(double);
+  if (b == 64) small_eig_kernel<double, 64><<<1, 512, smem64, st>>>(g, b, evals, evecs, mode);
+  else if (b == 32) small_eig_kernel<double, 32><<<1, 512, smem64, st>>>(g, b, evals, evecs, mode);
+  else if (b <= 96) small_eig_kernel<double, 0><<<1, 512, smem64, st>>>(g, b, evals, evecs, mode);
+  else small_eig_kernel<float, 0><<<1, 512, static_cast<size_t>(b) * b * (sizeof(double) + sizeof(float)), st>>>(g, b, evals, evecs, mode);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
