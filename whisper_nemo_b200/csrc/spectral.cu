@@ -79,9 +79,13 @@ template <typename VT, int BT>
 __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict__ g, int b_rt, float* __restrict__ evals,
                                                          float* __restrict__ evecs, int mode) {
   const int b = BT > 0 ? BT : b_rt;
+  // rows are b + 1 apart: the column phase of a rotation walks DOWN two columns (lane = row), and with an odd pitch
+  // those 8-byte accesses are conflict-free.  (With lane = pair the 32 scattered columns of one row cost 2-4 wavefronts
+  // per access and the shared-memory pipe, not the fp64 units, bounded the round: ~3700 clk for 64 x 64.)
+  const int pitch = b + 1;
   extern __shared__ double sd[];
-  double* A = sd;                                   // [b][b]
-  VT* V = reinterpret_cast<VT*>(sd + b * b);        // [b][b] accumulated rotations (fp32 only for b > 96)
+  double* A = sd;                                   // [b][pitch]
+  VT* V = reinterpret_cast<VT*>(sd + b * pitch);    // [b][pitch] accumulated rotations (fp32 only for b > 96)
   __shared__ double s_c[kMaxJacobi / 2], s_s[kMaxJacobi / 2];
   __shared__ int s_p[kMaxJacobi / 2], s_q[kMaxJacobi / 2];
   __shared__ double s_scale[kMaxJacobi];
@@ -91,36 +95,36 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
   for (int e = tid; e < b * b; e += nth) {
     const int i = e / b, j = e - i * b;
     // symmetrise the input (the Gram partials are symmetric only up to rounding)
-    A[e] = 0.5 * (static_cast<double>(g[i * b + j]) + static_cast<double>(g[j * b + i]));
-    V[e] = static_cast<VT>((i == j) ? 1.0 : 0.0);
+    A[i * pitch + j] = 0.5 * (static_cast<double>(g[i * b + j]) + static_cast<double>(g[j * b + i]));
+    V[i * pitch + j] = static_cast<VT>((i == j) ? 1.0 : 0.0);
   }
   __syncthreads();
 
   if (mode == 1) {
     if (tid < b) {
-      const double dg = A[tid * b + tid];
+      const double dg = A[tid * pitch + tid];
       s_scale[tid] = dg > 0.0 ? rsqrt(dg) : 1.0;
     }
     __syncthreads();
     for (int e = tid; e < b * b; e += nth) {
       const int i = e / b, j = e - i * b;
-      A[e] *= s_scale[i] * s_scale[j];
+      A[i * pitch + j] *= s_scale[i] * s_scale[j];
     }
     __syncthreads();
     // right-looking Cholesky, upper factor R stored in A's upper triangle
     for (int j = 0; j < b; ++j) {
       if (tid == 0) {
-        const double piv = A[j * b + j];
-        A[j * b + j] = sqrt(piv > 1e-14 ? piv : 1e-14);  // scaled diagonal is 1: 1e-14 ~ fully dependent column
+        const double piv = A[j * pitch + j];
+        A[j * pitch + j] = sqrt(piv > 1e-14 ? piv : 1e-14);  // scaled diagonal is 1: 1e-14 ~ fully dependent column
       }
       __syncthreads();
-      const double rjj = A[j * b + j];
-      for (int i = j + 1 + tid; i < b; i += nth) A[j * b + i] /= rjj;
+      const double rjj = A[j * pitch + j];
+      for (int i = j + 1 + tid; i < b; i += nth) A[j * pitch + i] /= rjj;
       __syncthreads();
       const int m = b - j - 1;
       for (int e = tid; e < m * m; e += nth) {
         const int i = j + 1 + e / m, k = j + 1 + e % m;
-        if (k >= i) A[i * b + k] -= A[j * b + i] * A[j * b + k];
+        if (k >= i) A[i * pitch + k] -= A[j * pitch + i] * A[j * pitch + k];
       }
       __syncthreads();
     }
@@ -130,19 +134,19 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
       for (int i = b - 1; i >= 0; --i) {
         double s = (i == c) ? 1.0 : 0.0;
         if (i > c) {
-          V[i * b + c] = static_cast<VT>(0.0);
+          V[i * pitch + c] = static_cast<VT>(0.0);
           continue;
         }
-        for (int k = i + 1; k <= c; ++k) s -= A[i * b + k] * static_cast<double>(V[k * b + c]);
-        V[i * b + c] = static_cast<VT>(s / A[i * b + i]);
+        for (int k = i + 1; k <= c; ++k) s -= A[i * pitch + k] * static_cast<double>(V[k * pitch + c]);
+        V[i * pitch + c] = static_cast<VT>(s / A[i * pitch + i]);
       }
     }
     __syncthreads();
     for (int e = tid; e < b * b; e += nth) {
-      const int i = e / b;
-      evecs[e] = static_cast<float>(s_scale[i] * static_cast<double>(V[e]));
+      const int i = e / b, j = e - i * b;
+      evecs[e] = static_cast<float>(s_scale[i] * static_cast<double>(V[i * pitch + j]));
     }
-    if (tid < b && evals) evals[tid] = static_cast<float>(A[tid * b + tid]);
+    if (tid < b && evals) evals[tid] = static_cast<float>(A[tid * pitch + tid]);
     return;
   }
 
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
     double off = 0.0, dia = 0.0;
     for (int e = tid; e < b * b; e += nth) {
       const int i = e / b, j = e - i * b;
-      const double v = A[e] * A[e];
+      const double v = A[i * pitch + j] * A[i * pitch + j];
       if (i == j) dia += v; else off += v;
     }
     off = warp_sum(off);
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
         auto player = [&](int slot) -> int { return slot == 0 ? 0 : 1 + (slot - 1 + round) % (b - 1); };
         int p = player(k), q = player(b - 1 - k);
         if (p > q) { const int t = p; p = q; q = t; }
-        const double apq = A[p * b + q], app = A[p * b + p], aqq = A[q * b + q];
+        const double apq = A[p * pitch + q], app = A[p * pitch + p], aqq = A[q * pitch + q];
         double c = 1.0, s = 0.0;
         if (fabs(apq) > 1e-300 && fabs(apq) > 1e-18 * (fabs(app) + fabs(aqq))) {
           // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 apq), written with one sqrt, one division
@@ -200,15 +204,15 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
       __syncthreads();
       // columns: A <- A J, V <- V J
       for (int e = tid; e < b * half; e += nth) {
-        const int r = e / half, k = e - r * half;
+        const int k = e / b, r = e - k * b;  // a warp: 32 consecutive rows of one pair
         const int p = s_p[k], q = s_q[k];
         const double c = s_c[k], s = s_s[k];
-        const double ap = A[r * b + p], aq = A[r * b + q];
-        A[r * b + p] = c * ap - s * aq;
-        A[r * b + q] = s * ap + c * aq;
-        const double vp = static_cast<double>(V[r * b + p]), vq = static_cast<double>(V[r * b + q]);
-        V[r * b + p] = static_cast<VT>(c * vp - s * vq);
-        V[r * b + q] = static_cast<VT>(s * vp + c * vq);
+        const double ap = A[r * pitch + p], aq = A[r * pitch + q];
+        A[r * pitch + p] = c * ap - s * aq;
+        A[r * pitch + q] = s * ap + c * aq;
+        const double vp = static_cast<double>(V[r * pitch + p]), vq = static_cast<double>(V[r * pitch + q]);
+        V[r * pitch + p] = static_cast<VT>(c * vp - s * vq);
+        V[r * pitch + q] = static_cast<VT>(s * vp + c * vq);
       }
       __syncthreads();
       // rows: A <- J^T A  (a warp walks 32 consecutive columns of one pair: conflict-free shared-memory rows)
@@ -216,19 +220,19 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
         const int k = e / b, col = e - k * b;
         const int p = s_p[k], q = s_q[k];
         const double c = s_c[k], s = s_s[k];
-        const double ap = A[p * b + col], aq = A[q * b + col];
-        A[p * b + col] = c * ap - s * aq;
-        A[q * b + col] = s * ap + c * aq;
+        const double ap = A[p * pitch + col], aq = A[q * pitch + col];
+        A[p * pitch + col] = c * ap - s * aq;
+        A[q * pitch + col] = s * ap + c * aq;
       }
       __syncthreads();
     }
   }
   // ascending order; column `rank` of evecs is the eigenvector of the rank-th smallest eigenvalue
   if (tid < b) {
-    const double li = A[tid * b + tid];
+    const double li = A[tid * pitch + tid];
     int rank = 0;
     for (int j = 0; j < b; ++j) {
-      const double lj = A[j * b + j];
+      const double lj = A[j * pitch + j];
       if (lj < li || (lj == li && j < tid)) ++rank;
     }
     evals[rank] = static_cast<float>(li);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(512) small_eig_kernel(const float* __restrict_
   const int* ranks = reinterpret_cast<const int*>(s_scale);
   for (int e = tid; e < b * b; e += nth) {
     const int i = e / b, j = e - i * b;
-    evecs[i * b + ranks[j]] = static_cast<float>(V[e]);
+    evecs[i * b + ranks[j]] = static_cast<float>(V[i * pitch + j]);
   }
 }
 
@@ -367,19 +371,19 @@ extern "C" int b200d_small_eig(const float* g, int32_t b, float* evals, float* e
   B200D_CHECK_ARG(g && evecs && b >= 2 && b <= kMaxJacobi && b % 2 == 0 && (mode == 0 || mode == 1) && (mode == 1 || evals));
   static bool attr_set = false;
   if (!attr_set) {
-    const int big = 2 * 96 * 96 * sizeof(double);
+    const int big = 2 * 96 * 97 * sizeof(double);
     B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kMaxJacobi * kMaxJacobi * (sizeof(double) + sizeof(float))));
+                                          kMaxJacobi * (kMaxJacobi + 1) * (sizeof(double) + sizeof(float))));
     attr_set = true;
   }
   cudaStream_t st = as_stream(stream);
-  const size_t smem64 = static_cast<size_t>(2) * b * b * sizeof(double);
+  const size_t smem64 = static_cast<size_t>(2) * b * (b + 1) * sizeof(double);
   if (b == 64) small_eig_kernel<double, 64><<<1, 512, smem64, st>>>(g, b, evals, evecs, mode);
   else if (b == 32) small_eig_kernel<double, 32><<<1, 512, smem64, st>>>(g, b, evals, evecs, mode);
   else if (b <= 96) small_eig_kernel<double, 0><<<1, 512, smem64, st>>>(g, b, evals, evecs, mode);
-  else small_eig_kernel<float, 0><<<1, 512, static_cast<size_t>(b) * b * (sizeof(double) + sizeof(float)), st>>>(g, b, evals, evecs, mode);
+  else small_eig_kernel<float, 0><<<1, 512, static_cast<size_t>(b) * (b + 1) * (sizeof(double) + sizeof(float)), st>>>(g, b, evals, evecs, mode);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }
