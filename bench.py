@@ -44,8 +44,8 @@ BATCH_WORKLOAD = "general_10min_batch"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu --set full capture of
 # this same command (profiles/r01_ncu_full_gemm2cta_final.txt): gemm_tcgen05_2cta_kernel<bias>, M = 131 072 frames, N = K = 1024:
 # 270.3 MB read + 231.1 MB written against 268 MB (A) + 2 MB (W) + 268 MB (out) algorithmic; 86.7 % tensor-pipe active, 192.5 us
-NCU_GEMM_TRAFFIC = {"bytes_per_launch": 501400064, "launch": "M=131072 N=1024 K=1024 bias epilogue", "algorithmic_bytes": 538968064,
-                    "tensor_pipe_active_pct": 86.7, "source": "profiles/r01_ncu_full_gemm2cta_final.txt"}
+NCU_GEMM_TRAFFIC = {"bytes_per_launch": 501163520, "launch": "M=131072 N=1024 K=1024 bias epilogue", "algorithmic_bytes": 538968064,
+                    "tensor_pipe_active_pct": 85.4, "source": "profiles/r01_ncu_full_gemm2cta_r1end.txt"}
 METRIC = "diarized audio-hours/sec (embed+NME-SC, device-timed)"
 UNIT = "audio-hours/s"
 
