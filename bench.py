@@ -224,7 +224,7 @@ def run_b200(args):
         peaks = _peaks()
         gemm_tflops = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         roofline = {
-            "kernel": "gemm_tcgen05_2cta_kernel (CTA-pair tcgen05 GEMM: TitaNet-L pointwise convs + 64-vector spectral A*V products)",
+            "kernel": "gemm_tcgen05_2cta_kernel (CTA-pair tcgen05 GEMM: the TitaNet-L pointwise convs of the embedding stage)",
             "bound": "tensor", "achieved": round(gemm_tflops, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
             "frac": round(gemm_tflops / peaks["tflops"], 4), "traffic": NCU_GEMM_TRAFFIC, "peak_source": peaks["src"],
             "launches_per_step": g["calls"], "avg_launch_ms": round(g["ms"] / max(g["calls"], 1), 4),
