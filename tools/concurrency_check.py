@@ -33,8 +33,9 @@ def make(variant):
         n, b = 10000, 64
         a16 = (torch.rand(n, n, device=dev) < 0.02).to(torch.bfloat16); deg = a16.float().sum(1)
         x = torch.randn(n, b, device=dev); out = torch.empty(n, b, device=dev)
-        vt = torch.zeros(4 * b, n, dtype=torch.bfloat16, device=dev); vo = torch.zeros(4 * b, n, dtype=torch.bfloat16, device=dev)
-        return lambda: cl._gemm_cheb(a16, n, vt, n, n, 4 * b, out, deg, x, None, 1.0, 0.0, 0.0, vo)
+        nw = cl.cheb_operand_rows(b)
+        vt = torch.zeros(nw, n, dtype=torch.bfloat16, device=dev); vo = torch.zeros(nw, n, dtype=torch.bfloat16, device=dev)
+        return lambda: cl._gemm_cheb(a16, n, vt, n, n, nw, out, deg, x, None, 1.0, 0.0, 0.0, vo)
     if variant == "depthwise":
         x = torch.randn(325 * 151, 1024, device=dev).half(); y = torch.empty_like(x); w = torch.randn(15, 1024, device=dev)
         return lambda: _cabi.call("b200d_depthwise_conv", _cabi.ptr(x), _cabi.ptr(y), _cabi.ptr(w), 325, 151, 1024, 15, _cabi._stream())
