@@ -95,6 +95,41 @@ def test_longform_bookkeeping_equals_oracle():
             assert torch.equal(res[0], res[1])
 
 
+def test_merge_plan_equals_oracle_run_reducer():
+    """plan_cluster_merges (the host half of the long-form reducer) against the oracle's run_reducer cluster by cluster:
+    same kept / merged window lists, and gathering [rows ; means] in the planned order reproduces its merged vectors."""
+    rng = np.random.default_rng(11)
+    for trial in range(25):
+        k = int(rng.integers(2, 12))
+        n = int(rng.integers(6 * k, 400))
+        d = 16
+        emb = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32))
+        labels = torch.from_numpy(rng.integers(0, k, n))
+        labels[:k] = torch.arange(k)
+        target = int(rng.integers(k + 1, max(k + 2, n // 2)))
+        vol = olf.get_merge_quantity(n - target, labels.clone(), max(1, target // k))
+        mat = torch.from_numpy(rng.random((n, n)).astype(np.float32))
+        mat = 0.5 * (mat + mat.t())
+        if trial % 5 == 0:  # ties in the masses
+            mat = torch.round(mat * 2) / 2
+        mass = torch.zeros(n)
+        for c in range(k):
+            idx = torch.where(labels == c)[0]
+            mass[idx] = mat[:, idx][idx, :].sum(0)
+        offset = int(rng.integers(0, 1000))
+        mapping, sizes, sel_idx, seg_off, order, n_avg = lf.plan_cluster_merges(labels.numpy(), [int(v) for v in vol.tolist()],
+                                                                                 mass.numpy(), n, offset)
+        means = [emb[torch.from_numpy(ix)].mean(0) for ix in sel_idx]
+        src = torch.cat([emb] + [m[None] for m in means]) if means else emb
+        merged_all = src[torch.from_numpy(np.concatenate(order))]
+        got = torch.split(merged_all, sizes)
+        assert n_avg == len(sel_idx) == len(seg_off) - 1
+        for c in range(k):
+            want_emb, _, (kept, merged) = olf.run_reducer(emb, c, int(vol[c]), labels, total_affinity_mat=mat)
+            assert torch.equal(mapping[c][0], kept + offset) and torch.equal(mapping[c][1], merged + offset), (trial, c)
+            assert got[c].shape == want_emb.shape and (got[c] - want_emb).abs().max().item() < 1e-6
+
+
 def test_nme_ratios_equal_the_per_p_loop():
     """The vectorised eigengap analysis == upstream's loop over p (NMESC.getEigRatio), bit for bit, ties included."""
     from whisper_nemo_b200.clustering import nme_ratios

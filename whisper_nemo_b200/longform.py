@@ -90,6 +90,44 @@ def get_merge_quantity(num_to_be_removed: int, pre_clus_labels: torch.Tensor, mi
     return removable
 
 
+def plan_cluster_merges(y_np: np.ndarray, vols: List[int], mass_np, n: int, offset_index: int):
+    """Index bookkeeping of run_reducer for all clusters of one chunk (host, no device work).
+    y_np: int64 labels [n]; vols[c]: how many vectors cluster c gives up; mass_np[i]: within-cluster affinity mass of
+    window i (column sum of its cluster's affinity block), needed when any vols[c] > 0.
+    Per cluster, in label order: the merge_quantity + 1 windows of largest mass are replaced by their mean, the others
+    are kept in ascending order.  Returns (mapping_list [(kept + offset, merged + offset)], sizes, sel_idx (members of
+    each mean), seg_off (their segment offsets), order (gather order over [chunk rows ; means]), n_avg)."""
+    # members of every cluster in ascending window order (== torch.where(labels == c)[0]) from one stable sort
+    by_label = np.argsort(y_np, kind="stable")
+    bounds = np.searchsorted(y_np[by_label], np.arange(len(vols) + 1))
+    mapping_list, sizes = [], []
+    sel_idx, seg_off, order = [], [0], []
+    n_avg = 0
+    none = torch.arange(0)
+    for spk_idx, merge_quantity in enumerate(vols):
+        target = by_label[bounds[spk_idx] : bounds[spk_idx + 1]]
+        if merge_quantity > 0:
+            if merge_quantity > target.shape[0] - 1:
+                raise ValueError("merge_quantity is larger than the half of targeted speaker's labels")
+            # the ranking is upstream's torch call (its tie order); the index bookkeeping around it is numpy
+            rank = torch.argsort(torch.from_numpy(mass_np[target]), descending=True).numpy()
+            selected, rest_sorted = rank[: merge_quantity + 1], np.sort(rank[merge_quantity + 1 :])
+            sel_idx.append(target[selected])
+            seg_off.append(seg_off[-1] + selected.size)
+            order.append(target[rest_sorted])
+            order.append(np.array([n + n_avg]))  # row of the merged vector in [emb_part ; means]
+            n_avg += 1
+            mapping_list.append((torch.from_numpy(target[rest_sorted] + offset_index), torch.from_numpy(target[selected] + offset_index)))
+            sizes.append(int(rest_sorted.size) + 1)
+            if target.shape[0] - merge_quantity != sizes[-1]:
+                raise ValueError("Reducer output is not matched to the target quantity")
+        else:
+            order.append(target)
+            mapping_list.append((torch.from_numpy(target + offset_index), none))
+            sizes.append(int(target.size))
+    return mapping_list, sizes, sel_idx, seg_off, order, n_avg
+
+
 class LongFormSpeakerClustering:
     def __init__(self, shard_chunks: bool = False, chunk_streams: int = None):
         """shard_chunks: under torch.distributed, deal the (independent) chunks of the long-form path to the ranks and
@@ -148,34 +186,7 @@ class LongFormSpeakerClustering:
             y32 = Y_part.to(torch.int32).contiguous()
             _cabi.call("b200d_masked_rowsum", ptr(mat), n, ptr(y32), ptr(mass), _s())
             mass_np = mass.cpu().numpy()
-        # members of every cluster in ascending window order (== torch.where(labels == c)[0]) from one stable sort
-        by_label = np.argsort(y_np, kind="stable")
-        bounds = np.searchsorted(y_np[by_label], np.arange(len(vols) + 1))
-        mapping_list, sizes = [], []
-        sel_idx, seg_off, order = [], [0], []  # merged-mean members / their segment offsets / final gather order
-        n_avg = 0
-        none = torch.arange(0)
-        for spk_idx, merge_quantity in enumerate(vols):
-            target = by_label[bounds[spk_idx] : bounds[spk_idx + 1]]
-            if merge_quantity > 0:
-                if merge_quantity > target.shape[0] - 1:
-                    raise ValueError("merge_quantity is larger than the half of targeted speaker's labels")
-                # the ranking is upstream's torch call (its tie order); the index bookkeeping around it is numpy
-                rank = torch.argsort(torch.from_numpy(mass_np[target]), descending=True).numpy()
-                selected, rest_sorted = rank[: merge_quantity + 1], np.sort(rank[merge_quantity + 1 :])
-                sel_idx.append(target[selected])
-                seg_off.append(seg_off[-1] + selected.size)
-                order.append(target[rest_sorted])
-                order.append(np.array([n + n_avg]))  # row of the merged vector in [emb_part ; means]
-                n_avg += 1
-                mapping_list.append((torch.from_numpy(target[rest_sorted] + offset_index), torch.from_numpy(target[selected] + offset_index)))
-                sizes.append(int(rest_sorted.size) + 1)
-                if target.shape[0] - merge_quantity != sizes[-1]:
-                    raise ValueError("Reducer output is not matched to the target quantity")
-            else:
-                order.append(target)
-                mapping_list.append((torch.from_numpy(target + offset_index), none))
-                sizes.append(int(target.size))
+        mapping_list, sizes, sel_idx, seg_off, order, n_avg = plan_cluster_merges(y_np, vols, mass_np, n, offset_index)
         src = emb_part
         if n_avg > 0:
             idx_d = torch.from_numpy(np.concatenate(sel_idx).astype(np.int32)).to(dev)
