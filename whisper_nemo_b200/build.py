@@ -60,7 +60,7 @@ def _build_locked(digest: str, verbose: bool) -> str:
             sys.stderr.write(out)
         if pr.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs 
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     subprocess.check_call(cmd)
     with open(_STAMP, "w") as f:
         f.write(digest)
