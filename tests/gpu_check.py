@@ -9,7 +9,6 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-import numpy as np
 import torch
 
 from whisper_nemo_b200 import _cabi

@@ -1,5 +1,4 @@
 """Shared helpers of the test-suite (not product code)."""
-import json
 import os
 
 import numpy as np
