@@ -12,6 +12,8 @@ import math
 import numpy as np
 import torch
 
+from . import switches
+
 CONSTANT = 1e-5
 
 
@@ -112,7 +114,9 @@ class FilterbankFeatures(torch.nn.Module):
 
     def get_seq_len(self, seq_len):
         pad_amount = self.n_fft // 2 * 2
-        seq_len = torch.floor_divide((seq_len + pad_amount - self.n_fft), self.hop_length) + 1
+        seq_len = torch.floor_divide((seq_len + pad_amount - self.n_fft), self.hop_length)
+        if switches.SEQ_LEN_PLUS_ONE:
+            seq_len = seq_len + 1
         return seq_len.to(dtype=torch.long)
 
     def stft(self, x):
@@ -124,7 +128,7 @@ class FilterbankFeatures(torch.nn.Module):
             center=True,
             window=self.window.to(dtype=torch.float),
             return_complex=True,
-            pad_mode="reflect",
+            pad_mode=switches.STFT_PAD_MODE,
         )
 
     @torch.no_grad()

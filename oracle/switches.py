@@ -10,6 +10,15 @@ which ones change results.
 # seq_len ("timemask") -- irrelevant under fixed_seq collate (all lengths equal).
 PREEMPH_TIMEMASK = True
 
+# features.FilterbankFeatures: torch.stft(center=True) with its default reflect padding, and
+# get_seq_len = floor((len + 2 * (n_fft // 2) - n_fft) / hop) + 1.  Hugging Face's port of a 2025 NeMo main
+# (transformers 5.5 ParakeetFeatureExtractor, in this image) has pad_mode="constant" and no "+ 1", so later 2.x
+# releases may differ in the first / last two frames of every window and in the frame count the per-feature
+# statistics run over.  tests/test_cpu_oracle.py flips both and reproduces that port's features; the CUDA featurizer
+# implements the defaults below.
+STFT_PAD_MODE = "reflect"  # or "constant"
+SEQ_LEN_PLUS_ONE = True
+
 # label_models.EncDecSpeakerLabelModel.__setup_dataloader_from_config uses
 # dataset.fixed_seq_collate_fn: short segments in a batch are *tiled* (repeated)
 # up to the batch max length, and every length becomes that max.

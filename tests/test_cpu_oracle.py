@@ -71,6 +71,43 @@ def test_featurizer_matches_an_independent_stft_pipeline():
     assert feats.shape[2] % 16 == 0 and feats[:, :, T:].abs().max().item() == 0.0
 
 
+def test_featurizer_matches_the_transformers_port_of_nemo(monkeypatch):
+    """transformers' ParakeetFeatureExtractor is an independent port of NeMo's FilterbankFeatures (same 16 kHz /
+    n_fft 512 / win 400 / hop 160 / 80 slaney mels / pre-emphasis 0.97 / 2^-24 log guard / per-feature normalisation)
+    that ships in this image.  With the two version-dependent details switched to that port's choice (constant STFT
+    padding, no "+ 1" in the frame count) the restatement reproduces its features; librosa is absent, so the port gets
+    the mel filterbank that test_mel_filterbank_matches_torchaudio checks."""
+    import types
+
+    fe = pytest.importorskip("transformers.models.parakeet.feature_extraction_parakeet")
+    from oracle import switches
+    from oracle.features import FilterbankFeatures, librosa_mel
+
+    monkeypatch.setattr(fe, "librosa", types.SimpleNamespace(filters=types.SimpleNamespace(
+        mel=lambda sr, n_fft, n_mels, fmin, fmax, norm: librosa_mel(sr, n_fft, n_mels, fmin, fmax))), raising=False)
+    try:
+        extractor = fe.ParakeetFeatureExtractor()
+    except Exception as exc:  # noqa: BLE001 -- the class refuses to build without its optional backends
+        pytest.skip(f"ParakeetFeatureExtractor unavailable: {exc}")
+    monkeypatch.setattr(switches, "STFT_PAD_MODE", "constant")
+    monkeypatch.setattr(switches, "SEQ_LEN_PLUS_ONE", False)
+    g = torch.Generator().manual_seed(9)
+    for n in (24000, 8000, 12345):
+        x = 0.1 * torch.randn(n, generator=g)
+        theirs = extractor(x.numpy(), sampling_rate=16000, return_tensors="pt")
+        want = theirs["input_features"][0]  # [T, 80]
+        frames = int(theirs["attention_mask"][0].sum())
+        ours, lens = FilterbankFeatures()(x[None], torch.tensor([n]))
+        assert int(lens[0]) == frames
+        err = (ours[0, :, :frames].t() - want[:frames]).abs().max().item()
+        assert err < 1e-5, (n, err)  # measured: 0.0 (the same torch ops in the same order)
+    # and the two details do matter: with the defaults the same input differs from the port
+    monkeypatch.setattr(switches, "STFT_PAD_MODE", "reflect")
+    monkeypatch.setattr(switches, "SEQ_LEN_PLUS_ONE", True)
+    ours, lens = FilterbankFeatures()(x[None], torch.tensor([n]))
+    assert int(lens[0]) == frames + 1
+
+
 @pytest.mark.parametrize("dur,w,s", [(10.0, 1.5, 0.75), (600.0, 0.5, 0.25), (3.3, 3.0, 1.5), (0.4, 1.5, 0.75), (1.5, 1.5, 0.75)])
 def test_subsegment_count_formula(dur, w, s):
     segs = osu.get_subsegments(2.0, w, s, dur)
