@@ -132,10 +132,12 @@ def _session(work_dir, workload, seed, batch=0, rank=0, world=1):
 def titanet_flops(diar):
     """Algorithmic FLOPs of the TitaNet-L forward for the planned windows: 2 x (17.49 M MAC per frame + 4.59 M MAC per
     window) (pointwise 15.81 M + depthwise 0.10 M + decoder 1.57 M per frame; SE + projections per window)."""
+    from whisper_nemo_b200.titanet import frames_of
+
     frames = windows = 0
     for plan in diar._scales.values():
         windows += len(plan["len"])
-        frames += int(sum(int(f) // 160 + 1 for f in plan["fixed"]))
+        frames += int(sum(frames_of(int(f)) for f in plan["fixed"]))
     return 2.0 * (17.49e6 * frames + 4.59e6 * windows), frames, windows
 
 

@@ -41,6 +41,8 @@ const char* b200d_last_error(void);
 /* 0 if the current device is sm_100 and the driver entry points were resolved. */
 int b200d_check_device(void);
 
+#define B200D_FEAT_ZERO_PAD 1    /* constant-zero instead of reflect STFT padding */
+#define B200D_FEAT_NO_PLUS_ONE 2 /* frame count floor(len / hop) instead of floor(len / hop) + 1 */
 /* ------------------------------------------------------------------------------------------
  * Featurizer: replaces AudioToSpeechLabelDataset slicing + fixed_seq collate (tiling) and
  * FilterbankFeatures.forward (nemo/collections/asr/parts/preprocessing/features.py):
@@ -51,17 +53,20 @@ int b200d_check_device(void);
  *  seg_start    int32   [n_seg]      first sample of each segment in `wav`
  *  seg_len      int32   [n_seg]      true sample count of each segment (>= 1)
  *  fixed_len    samples every segment is tiled up to (batch max, fixed_seq collate);
- *               frames T = fixed_len / 160 + 1
+ *               frames T = fixed_len / 160 + 1   (fixed_len / 160 with B200D_FEAT_NO_PLUS_ONE)
  *  fb_start     int32   [80]         first FFT bin of each mel filter's support
  *  fb_off       int32   [81]         offsets of each filter's weights in fb_w (fb_off[80] == fb_nnz)
  *  fb_w         float32 [fb_nnz]     packed non-zero filterbank weights (librosa slaney), fb_nnz <= 1024
  *  window       float32 [400]        hann(400, periodic=False)
+ *  variant      0 = FilterbankFeatures as in NeMo 1.x / early 2.x: torch.stft's reflect padding, frame count with "+ 1";
+ *               B200D_FEAT_ZERO_PAD | B200D_FEAT_NO_PLUS_ONE = the later behaviour (the choice of transformers'
+ *               ParakeetFeatureExtractor port): constant-zero padding of the pre-emphasised window, no "+ 1"
  *  out_f16      __half  [n_seg*T][ldo]  channels-last, channels 80..ldo-1 zeroed (ldo >= 80, ldo % 8 == 0)
  *  out_f32      float32 [n_seg][T][80] or NULL (parity taps)
  * ------------------------------------------------------------------------------------------ */
 int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, const int32_t* seg_len,
                     int32_t n_seg, int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off,
-                    const float* fb_w, int32_t fb_nnz, const float* window,
+                    const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant,
                     void* out_f16, int32_t ldo, float* out_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -18,36 +18,54 @@ def _windows(wav, fixed_len, lens, step=3000, first=1000):
     return starts, lens
 
 
+def _featurizer_variant(monkeypatch, variant):
+    """'classic': reflect STFT padding, frame count with "+ 1" (the default of both sides); 'later': constant padding
+    and no "+ 1" -- the variant in which the oracle's featurizer equals transformers' port of NeMo's bit for bit
+    (tests/test_cpu_oracle.py).  Switches the oracle and the CUDA featurizer together."""
+    from oracle import switches
+    from whisper_nemo_b200 import titanet as tn
+
+    if variant == "later":
+        monkeypatch.setattr(switches, "STFT_PAD_MODE", "constant")
+        monkeypatch.setattr(switches, "SEQ_LEN_PLUS_ONE", False)
+        monkeypatch.setattr(tn, "FEATURIZER_VARIANT", tn.FEAT_ZERO_PAD | tn.FEAT_NO_PLUS_ONE)
+
+
+@pytest.mark.parametrize("variant", ["classic", "later"])
 @pytest.mark.parametrize("fixed_len,lens", [(24000, [24000, 24000, 24000, 9000, 801]), (8000, [8000, 8000, 3000]), (48000, [48000, 47000]),
                                             (30400, [30400, 30400, 12345])])
-def test_featurizer_matches_oracle(dev, oracle_model, weights, fixed_len, lens):
+def test_featurizer_matches_oracle(dev, oracle_model, weights, fixed_len, lens, variant, monkeypatch):
     from oracle.clustering_diarizer import collate
     from whisper_nemo_b200 import synth
     from whisper_nemo_b200 import titanet as tn
 
+    _featurizer_variant(monkeypatch, variant)
     wav, _ = synth.synth_recording(30.0, 2, seed=5)
     wav_t = torch.from_numpy(wav)
     pk = tn.pack_weights(weights, dev)
     starts, lens = _windows(wav, fixed_len, lens)
     audio, alens = collate([wav_t[s : s + l] for s, l in zip(starts, lens)])
-    feats, _ = oracle_model.preprocessor(audio, alens)
-    T = fixed_len // 160 + 1
+    feats, flens = oracle_model.preprocessor(audio, alens)
+    T = tn.frames_of(fixed_len)
+    assert int(flens[0]) == T
     ref = feats[:, :, :T].transpose(1, 2).contiguous()
     out16, out32 = tn.featurize(pk, wav_t.to(dev), torch.tensor(starts, dtype=torch.int32, device=dev),
                                 torch.tensor(lens, dtype=torch.int32, device=dev), fixed_len, want_f32=True)
     torch.cuda.synchronize()
     err = (out32.cpu() - ref).abs().max().item()
-    print(f"log-mel fixed_len={fixed_len}: max abs err {err:.3e}")
+    print(f"log-mel fixed_len={fixed_len} ({variant}): max abs err {err:.3e}")
     assert err <= 2e-4  # normalised log-mel, O(1) values; fp32 FFT vs torch.stft
     assert out16[:, 80:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("variant", ["classic", "later"])
 @pytest.mark.parametrize("fixed_len,n", [(24000, 12), (8000, 40), (48000, 5), (20000, 7)])
-def test_titanet_embeddings_match_oracle(dev, oracle_model, weights, fixed_len, n):
+def test_titanet_embeddings_match_oracle(dev, oracle_model, weights, fixed_len, n, variant, monkeypatch):
     from oracle.clustering_diarizer import collate
     from whisper_nemo_b200 import synth
     from whisper_nemo_b200 import titanet as tn
 
+    _featurizer_variant(monkeypatch, variant)
     wav, _ = synth.synth_recording(40.0, 3, seed=7)
     wav_t = torch.from_numpy(wav)
     net = tn.TitaNetB200(weights, dev, max_frames=8192)
@@ -59,7 +77,7 @@ def test_titanet_embeddings_match_oracle(dev, oracle_model, weights, fixed_len, 
     emb = net.embed_segments(wav_t.to(dev), torch.tensor(starts, dtype=torch.int32, device=dev),
                              torch.tensor(lens, dtype=torch.int32, device=dev), fixed_len).cpu()
     cos = torch.nn.functional.cosine_similarity(emb, ref, dim=1)
-    print(f"titanet fixed_len={fixed_len} n={n}: max (1 - cos) {(1 - cos).max().item():.3e}")
+    print(f"titanet fixed_len={fixed_len} n={n} ({variant}): max (1 - cos) {(1 - cos).max().item():.3e}")
     assert (1 - cos).max().item() <= 1e-3  # BASELINE.json: embeddings within 1e-3 cosine
     # the embeddings must carry speaker information (not a constant vector): spread of pairwise cosines
     en = torch.nn.functional.normalize(ref, dim=1)

@@ -43,7 +43,7 @@ _SIGNATURES = {
     "b200d_last_error": (c_char_p, []),
     "b200d_check_device": (c_int32, []),
     "b200d_featurize": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
-                                  c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+                                  c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_depthwise_conv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                  POINTER(GemmEpilogue), c_void_p]),

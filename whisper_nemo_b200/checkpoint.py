@@ -118,7 +118,7 @@ def calibrate_embedding_bn(state_dict: Dict[str, torch.Tensor], device, seed: in
     st = torch.tensor(starts, dtype=torch.int32, device=net.device)
     ln = torch.full((len(starts),), n, dtype=torch.int32, device=net.device)
     pools = []
-    step = max(1, net.max_frames // (n // 160 + 1))
+    step = max(1, net.max_frames // (n // 160 + 1))  # an upper bound on the frames per window in either featurizer variant
     for c0 in range(0, len(starts), step):
         taps = {}
         net.embed_segments(wav_d, st[c0 : c0 + step], ln[c0 : c0 + step], n, taps=taps)

@@ -32,6 +32,7 @@ struct FeatParams {
   int n_seg;
   int fixed_len;
   int T;
+  int zero_pad;  // STFT padding of the (pre-emphasised) window: 0 = reflect (torch.stft's default), 1 = zeros
   const int* fb_start;  // [80] first bin of each filter
   const int* fb_off;    // [81] offsets into fb_w
   const float* fb_w;    // packed non-zero weights
@@ -72,7 +73,9 @@ __global__ void __launch_bounds__(kFeatWarps * 32) featurize_kernel(const FeatPa
     const int s = (i < rep_end) ? (i % len) : (tail_base + (i - rep_end));
     return __ldg(src + s);
   };
-  auto y_at = [&](int j) -> float {  // pre-emphasised signal with torch.stft reflect padding
+  const bool zero_pad = p.zero_pad != 0;
+  auto y_at = [&](int j) -> float {  // pre-emphasised signal with torch.stft's reflect (or constant-zero) padding
+    if (zero_pad && (j < 0 || j >= F)) return 0.f;
     if (j < 0) j = -j;
     if (j >= F) j = 2 * (F - 1) - j;
     if (j < 0) j = 0;  // only for degenerate F < 257; never on this path
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(kFeatWarps * 32) featurize_kernel(const FeatPa
   const bool tiled = len < F;
   auto sample = [&](int j) -> float {  // pre-emphasised, reflect-padded signal at frame-relative position
     if (!tiled) {
+      if (zero_pad && (j < 0 || j >= F)) return 0.f;
       if (j < 0) j = -j;
       if (j >= F) j = 2 * (F - 1) - j;
       const float x0 = __ldg(src + j);
@@ -222,14 +226,17 @@ using namespace b200d;
 
 extern "C" int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, const int32_t* seg_len, int32_t n_seg,
                                int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off, const float* fb_w, int32_t fb_nnz,
-                               const float* window, void* out_f16, int32_t ldo, float* out_f32, void* stream) {
+                               const float* window, int32_t variant, void* out_f16, int32_t ldo, float* out_f32, void* stream) {
   B200D_CHECK_ARG(wav && seg_start && seg_len && fb_start && fb_off && fb_w && window && out_f16);
   B200D_CHECK_ARG(n_seg > 0 && fixed_len >= kNFFT / 2 + 1);
   B200D_CHECK_ARG(ldo >= kMels && ldo % 8 == 0);
   B200D_CHECK_ARG(fb_nnz > 0 && fb_nnz <= kMaxFbNnz);
+  B200D_CHECK_ARG(variant >= 0 && variant <= 3);
   FeatParams p;
   p.wav = wav; p.n_wav = n_wav; p.seg_start = seg_start; p.seg_len = seg_len; p.n_seg = n_seg;
-  p.fixed_len = fixed_len; p.T = fixed_len / kHop + 1;
+  p.fixed_len = fixed_len; p.T = fixed_len / kHop + ((variant & B200D_FEAT_NO_PLUS_ONE) ? 0 : 1);
+  p.zero_pad = (variant & B200D_FEAT_ZERO_PAD) ? 1 : 0;
+  B200D_CHECK_ARG(p.T >= 2);
   p.fb_start = fb_start; p.fb_off = fb_off; p.fb_w = fb_w; p.window = window;
   p.out16 = reinterpret_cast<__half*>(out_f16); p.ldo = ldo; p.out32 = out_f32;
   const size_t smem = (((static_cast<size_t>(p.T) * kMels + 3) & ~static_cast<size_t>(3)) + static_cast<size_t>(kFeatWarps) * kWarpScratch) * sizeof(float);

@@ -31,6 +31,18 @@ HOP = 160
 WIN = 400
 NFFT = 512
 
+# FilterbankFeatures details that differ between NeMo releases: the default is the classic
+# behaviour -- torch.stft's reflect padding and a frame count with "+ 1"; B200D_STFT_PAD_MODE=constant and
+# B200D_SEQ_LEN_PLUS_ONE=0 select what later releases (and transformers' port of the featurizer) do.
+FEAT_ZERO_PAD, FEAT_NO_PLUS_ONE = 1, 2  # include/b200d.h
+FEATURIZER_VARIANT = ((FEAT_ZERO_PAD if os.environ.get("B200D_STFT_PAD_MODE", "reflect") == "constant" else 0)
+                      | (FEAT_NO_PLUS_ONE if os.environ.get("B200D_SEQ_LEN_PLUS_ONE", "1") == "0" else 0))
+
+
+def frames_of(fixed_len: int) -> int:
+    """Feature frames of a window of `fixed_len` samples (FilterbankFeatures.get_seq_len at n_fft 512, hop 160)."""
+    return fixed_len // HOP + (0 if FEATURIZER_VARIANT & FEAT_NO_PLUS_ONE else 1)
+
 
 # ------------------------------------------------------------------------------------------ tables
 def slaney_mel_filterbank(sr: int = 16000, n_fft: int = NFFT, n_mels: int = FEAT) -> np.ndarray:
@@ -212,12 +224,12 @@ def featurize(pk: PackedTitaNet, wav: torch.Tensor, seg_start: torch.Tensor, seg
     """wav float32 [n] on device; seg_start / seg_len int32 [n_seg] on device.  Returns
     (fp16 [n_seg*T, 128], optional float32 [n_seg, T, 80])."""
     n_seg = seg_start.numel()
-    T = fixed_len // HOP + 1
+    T = frames_of(fixed_len)
     if out16 is None:
         out16 = torch.empty(n_seg * T, FEAT_PAD, dtype=torch.float16, device=wav.device)
     out32 = torch.empty(n_seg, T, FEAT, dtype=torch.float32, device=wav.device) if want_f32 else None
     _cabi.call("b200d_featurize", ptr(wav), wav.numel(), ptr(seg_start), ptr(seg_len), n_seg, fixed_len, ptr(pk.fb_start), ptr(pk.fb_off),
-               ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), ptr(out16), out16.stride(0), ptr(out32), _cabi._stream())
+               ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), FEATURIZER_VARIANT, ptr(out16), out16.stride(0), ptr(out32), _cabi._stream())
     return out16, out32
 
 
@@ -335,7 +347,7 @@ class TitaNetB200:
     def embed_segments(self, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int, taps: dict = None):
         """All segments share `fixed_len` (batch max under fixed_seq collate).  Returns float32 [n_seg, 192]."""
         n_seg = seg_start.numel()
-        T = fixed_len // HOP + 1
+        T = frames_of(fixed_len)
         ws = self._workspace(T)
         segs_per_chunk = max(1, self.max_frames // T)
         out = torch.empty(n_seg, EMB, dtype=torch.float32, device=self.device)
