@@ -23,6 +23,36 @@ def test_header_declares_the_bound_symbols():
     assert sorted(_cabi.exported_symbols()) == [d for d in declared]
 
 
+def test_ctypes_signatures_follow_the_header():
+    """Same parameter count, and pointer / integer / float in the same positions, for every declaration of
+    include/b200d.h and its ctypes binding (an argument added on one side only would shift every later one silently)."""
+    from whisper_nemo_b200 import _cabi
+
+    text = open(os.path.join(ROOT, "include", "b200d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = dict(re.findall(r"\b(b200d_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert sorted(decls) == sorted(_cabi._SIGNATURES)
+
+    def kind_c(param):
+        param = param.strip()
+        if "*" in param:
+            return "ptr"
+        if re.match(r"(const\s+)?float\b", param):
+            return "float"
+        return "int"
+
+    def kind_py(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int))):
+            return "ptr"
+        return "float" if t is ctypes.c_float else "int"
+
+    for name, params in decls.items():
+        params = params.strip()
+        c_kinds = [] if params in ("", "void") else [kind_c(q) for q in params.split(",")]
+        py_kinds = [kind_py(t) for t in _cabi._SIGNATURES[name][1]]
+        assert c_kinds == py_kinds, (name, c_kinds, py_kinds)
+
+
 def test_library_exports_every_declared_symbol():
     from whisper_nemo_b200 import _cabi, build
 
