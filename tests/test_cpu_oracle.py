@@ -145,6 +145,44 @@ def test_kmeans_agrees_with_sklearn_on_separated_blobs():
     assert best_permutation_agreement(ours, sk) == 1.0
 
 
+def test_kmeans_plusplus_picks_sklearns_centers_on_the_same_draws():
+    """kmeans_plusplus_torch is upstream's port of sklearn's k-means++ (greedy, 30 local trials).  Fed the same uniform
+    draws and the same first index, the restatement must choose the centers sklearn's own implementation chooses."""
+    from sklearn.cluster import _kmeans
+
+    from oracle import offline_clustering as oc
+
+    class Draws(np.random.RandomState):
+        def __init__(self, first, uniforms):
+            super().__init__(0)
+            self.first, self.uniforms, self.pos = first, uniforms, 0
+
+        def choice(self, n, p=None):
+            return self.first
+
+        def uniform(self, size=None):
+            row = self.uniforms[self.pos]
+            self.pos += 1
+            return row.astype(np.float64)
+
+    rng = np.random.default_rng(21)
+    for trial in range(12):
+        k = int(rng.integers(2, 9))
+        n = int(rng.integers(40, 400))
+        centers = rng.standard_normal((k, 6)) * 6
+        x = (centers[rng.integers(0, k, n)] + rng.standard_normal((n, 6))).astype(np.float32)
+        xt = torch.from_numpy(x)
+        seed = int(rng.integers(0, 1000))
+        # the draws upstream would make after torch.manual_seed(seed)
+        torch.manual_seed(seed)
+        first = int(torch.randint(0, n, (1,)))
+        uniforms = np.stack([torch.rand(30).numpy() for _ in range(k - 1)])
+        _, want = _kmeans._kmeans_plusplus(x.astype(np.float64), k, (x.astype(np.float64) ** 2).sum(1), np.ones(n),
+                                           Draws(first, uniforms), n_local_trials=30)
+        _, got = oc.kmeans_plusplus_torch(xt, k, random_state=seed)
+        assert got.tolist() == want.tolist(), (trial, got.tolist(), want.tolist())
+
+
 def test_laplacian_spectrum_properties():
     g = torch.Generator().manual_seed(9)
     x = torch.randn(120, 8, generator=g)
