@@ -223,6 +223,16 @@ def test_rttm_roundtrip_through_the_reference_parser(tmp_path):
     assert osu.rttm_to_labels(path) == ["0.0 1.125 speaker_0", "1.125 4.0 speaker_1", "5.0 9.5 speaker_0"]
 
 
+def test_oracle_titanet_parameter_count_matches_the_published_figure():
+    """NVIDIA's model card and the TitaNet paper (Koluguri et al., 2022, table 1) give TitaNet-L 25.3 M parameters; the
+    restated architecture (prolog + 3 mega blocks of 3 sub-blocks at 1024 channels + 3072-channel epilog, attentive
+    statistics pooling with a 128-channel bottleneck, 192-d embedding, 16 681-way training head) must land on it."""
+    from oracle.titanet import TitaNetL
+
+    total = sum(p.numel() for p in TitaNetL().parameters())
+    assert abs(total / 1e6 - 25.3) < 0.05, total
+
+
 def test_oracle_titanet_shapes_and_determinism():
     from oracle.titanet import TitaNetL
     from whisper_nemo_b200 import checkpoint
