@@ -1,20 +1,27 @@
 """Benchmark of the diarization hot path: diarized audio-hours / second (embed + NME-SC), BASELINE.json's metric.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload meeting_1h|telephonic_10min|...]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload meeting_1h|telephonic_10min|...] [--shard]
 
 One "step" is one pass of the hot path over one recording per GPU: waveform -> multi-scale windows -> fused
 log-mel + TitaNet-L embeddings -> multi-scale affinity -> NME-SC -> spectral clustering -> labels on the host.
 N = 1 runs BASELINE config #3 (1-hour 8-speaker meeting, diar_infer_meeting.yaml), the configuration the headline
 target is quoted on; N > 1 gives every rank its own recording of the same shape (multi-file batches shard by
-recording, no data-path collective: weak scaling).  Audio is synthetic (whisper_nemo_b200.synth) and the
-TitaNet-L weights are the fixed-seed random init (whisper_nemo_b200.checkpoint); speech regions come from the
-ground-truth RTTM (oracle VAD) -- VAD, WAV decoding and RTTM text are outside the metric.
+recording, no data-path collective: weak scaling) and adds a `strong_4h` object: BASELINE config #5, ONE 4-hour
+recording whose windows, long-form chunks and spectral products are sharded over the N GPUs (NCCL all-gathers).
+`--shard` makes that single-recording sharding the main measurement of any workload (scaling "strong").
+Audio is synthetic (tools/workload.py) and the TitaNet-L weights are the fixed-seed random init
+(whisper_nemo_b200.checkpoint.seeded); speech regions come from the ground-truth RTTM (oracle VAD) -- VAD, WAV decoding
+and RTTM text are outside the metric.
 
-`value`   device-timed (CUDA events) with the waveform already resident in HBM.
-`e2e`     the same call with the waveform in pinned HOST memory: H2D copy of the samples, all device work, and the
-          D2H read of the labels inside the timed region.
-`--impl reference` times the CPU restatement of NeMo's ClusteringDiarizer (oracle/, NeMo itself is not
-installable here) on the box's host cores on a bounded sample of the same workload.
+`value`         device-timed (CUDA events) with the waveform already resident in HBM.
+`e2e`           the same call with the waveform in pinned HOST memory: H2D copy of the samples, all device work, and the
+                D2H read of the labels inside the timed region.
+`diarize_call`  wall clock of the reference-facing `ClusteringDiarizer(cfg).diarize()` itself: WAV read, manifests,
+                windows, H2D, device work, D2H and the RTTM / label files (what a user of the reference sees).
+`--impl reference` times the CPU restatement of NeMo's ClusteringDiarizer (oracle/, NeMo itself is not installable
+here) on the box's host cores on the SAME configuration: one full pass over the recording, its dataloader batches dealt
+round-robin to the W + K steps (each step a bounded sample of the workload), the clustering of the full recording
+timed once after the last step.  That arm imports neither the product's engine nor libb200d.so.
 """
 import argparse
 import json
@@ -41,13 +48,9 @@ WORKLOADS = {
 # (strong scaling over the batch).  --batch R sets the batch size (64 in BASELINE.json; smaller values keep the host-side
 # synthesis short).
 BATCH_WORKLOAD = "general_10min_batch"
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu --set full capture of
-# this same command (profiles/r01_ncu_full_gemm2cta_final.txt): gemm_tcgen05_2cta_kernel<bias>, M = 131 072 frames, N = K = 1024:
-# 270.3 MB read + 231.1 MB written against 268 MB (A) + 2 MB (W) + 268 MB (out) algorithmic; 86.7 % tensor-pipe active, 192.5 us
-NCU_GEMM_TRAFFIC = {"bytes_per_launch": 501163520, "launch": "M=131072 N=1024 K=1024 bias epilogue", "algorithmic_bytes": 538968064,
-                    "tensor_pipe_active_pct": 85.4, "source": "profiles/r01_ncu_full_gemm2cta_r1end.txt"}
 METRIC = "diarized audio-hours/sec (embed+NME-SC, device-timed)"
 UNIT = "audio-hours/s"
+SEED = 100  # recording seed of rank 0 (rank r: SEED + r); the reference arm diarizes rank 0's recording
 
 
 def _peaks():
@@ -57,6 +60,34 @@ def _peaks():
             d = json.load(f)
         return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json, sustained)"}
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, written by
+    `tools/ncu_summarize.py traffic` from the committed `ncu --set full` capture (profiles/ncu_traffic.json carries the
+    capture's file name and the commit it was taken at); None when no capture has been summarised."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line -- a pure function of the command line, identical for both arms."""
+    if args.workload == BATCH_WORKLOAD:
+        text = (f"{args.workload} (BASELINE.json configs[3]): batch of {args.batch} x 600 s synthetic 3-speaker recordings in one manifest, "
+                f"diar_infer_general.yaml, oracle VAD, TitaNet-L random-init seed 1234")
+        sharding = f"recordings dealt to {world} rank(s), no collective"
+    else:
+        domain, seconds, speakers, idx = WORKLOADS[args.workload]
+        text = (f"{args.workload} (BASELINE.json configs[{idx}]): {seconds:.0f} s synthetic {speakers}-speaker 16 kHz recording"
+                f"{'' if args.shard else ' per GPU'}, diar_infer_{domain}.yaml, oracle VAD, TitaNet-L random-init seed 1234")
+        sharding = ("single GPU" if world == 1 else
+                    f"ONE recording over {world} GPUs: windows, long-form chunks and spectral products sharded, NCCL all-gathers" if args.shard else
+                    "one recording per GPU, no collective")
+    return {"workload": text, "sharding": sharding,
+            "l2": "inputs larger than L2 (waveform 230 MB/h, activations > 1 GB per step); no explicit flush"}
 
 
 class ClockSampler:
@@ -109,23 +140,41 @@ class ClockSampler:
 
 def _session(work_dir, workload, seed, batch=0, rank=0, world=1):
     """Synthetic recording(s) + manifest + config for one rank.  Returns (cfg, seconds of audio this rank diarizes)."""
-    from tests.util import make_session_cfg
+    from tools import workload as wl
 
     if workload == BATCH_WORKLOAD:
-        from whisper_nemo_b200 import config, sharding, synth
+        from whisper_nemo_b200 import sharding
 
         mine = sharding.assign_recordings([600.0] * batch, world)[rank]
         entries = []
         for i in mine:
-            wav_path, rttm_path, _, _ = synth.make_session(work_dir, f"rec{i:03d}", 600.0, 3, seed=1000 + i)
+            wav_path, rttm_path, _, _ = wl.make_session(work_dir, f"rec{i:03d}", 600.0, 3, seed=1000 + i)
             entries.append({"audio_filepath": wav_path, "rttm_filepath": rttm_path})
-        cfg = config.load_config("general")
+        cfg = wl.load_domain_config("general")
         man = os.path.join(work_dir, "manifest.json")
-        synth.write_manifest(man, entries)
+        wl.write_manifest(man, entries)
         cfg.diarizer.manifest_filepath, cfg.diarizer.out_dir, cfg.diarizer.oracle_vad = man, work_dir, True
         return cfg, 600.0 * len(mine)
     domain, seconds, speakers, _ = WORKLOADS[workload]
-    cfg, wav, turns = make_session_cfg(work_dir, domain, seconds, speakers, seed)
+    cfg, wav, turns = wl.make_session_cfg(work_dir, domain, seconds, speakers, seed)
+    return cfg, seconds
+
+
+def _shared_session(workload, seed, rank, barrier):
+    """ONE recording for all ranks (single-recording sharding): rank 0 synthesises it into a directory every rank of
+    the box can read, the others wait.  Returns (cfg with a rank-private out_dir, seconds)."""
+    from tools import workload as wl
+
+    domain, seconds, speakers, _ = WORKLOADS[workload]
+    shared = os.path.join(tempfile.gettempdir(), f"b200d_bench_shared_{workload}_s{seed}")
+    if rank == 0:
+        wl.make_session_cfg(shared, domain, seconds, speakers, seed)
+    barrier()
+    cfg = wl.load_domain_config(domain)
+    out = os.path.join(tempfile.gettempdir(), f"b200d_bench_shared_{workload}_s{seed}_out_r{rank}")
+    os.makedirs(out, exist_ok=True)
+    cfg.diarizer.manifest_filepath = os.path.join(shared, "input_manifest.json")
+    cfg.diarizer.out_dir, cfg.diarizer.oracle_vad = out, True
     return cfg, seconds
 
 
@@ -141,6 +190,26 @@ def titanet_flops(diar):
     return 2.0 * (17.49e6 * frames + 4.59e6 * windows), frames, windows
 
 
+def _time_steps(diar, wav_dev, steps, barrier, torch):
+    """(device ms over `steps` passes with the waveform resident, wall ms over `steps` passes from pinned host memory)"""
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        diar.run_device(wav_dev=wav_dev, timers=False)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        diar.run_device(wav_dev=None, timers=False)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    return dev_ms, e2e_ms
+
+
 def run_b200(args):
     import torch
 
@@ -149,28 +218,45 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from whisper_nemo_b200 import ClusteringDiarizer, _cabi, checkpoint
+
+    weights = checkpoint.seeded()
+    # the bounded CPU sample runs BEFORE the process group exists: the other ranks block in the rendezvous (no NCCL barrier
+    # spinning on the host cores next to it, as round 1 had) and torchrun's OMP_NUM_THREADS=1 is overridden explicitly
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and not args.profiling:
+        cpu = cpu_baseline_sample(args, weights)
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-    from whisper_nemo_b200 import ClusteringDiarizer, _cabi, checkpoint
-
-    workload = args.workload
-    work_dir = os.path.join(tempfile.gettempdir(), f"b200d_bench_{workload}_r{rank}")
-    cfg, seconds = _session(work_dir, workload, seed=100 + rank, batch=args.batch, rank=rank, world=world)
-    batch_mode = workload == BATCH_WORKLOAD
-    weights = checkpoint.calibrated(dev)
-    t0 = time.perf_counter()
-    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights).to("cuda")
-    diar._prepare()
-    prep_s = time.perf_counter() - t0
-    wav_dev = diar._wav_host.to(dev)
-    flops, frames, windows = titanet_flops(diar)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_max(vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    workload = args.workload
+    batch_mode = workload == BATCH_WORKLOAD
+    shard = bool(args.shard) and world > 1 and not batch_mode
+    if shard:
+        cfg, seconds = _shared_session(workload, SEED, rank, barrier)
+    else:
+        work_dir = os.path.join(tempfile.gettempdir(), f"b200d_bench_{workload}_r{rank}")
+        cfg, seconds = _session(work_dir, workload, seed=SEED + rank, batch=args.batch, rank=rank, world=world)
+    t0 = time.perf_counter()
+    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights, shard_windows=shard).to("cuda")
+    diar._prepare()
+    prep_s = time.perf_counter() - t0
+    wav_dev = diar._wav_host.to(dev)
+    flops, frames, windows = titanet_flops(diar)
 
     for _ in range(args.warmup):
         diar.run_device(wav_dev=wav_dev, timers=False)
@@ -178,33 +264,31 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
     launches0 = _cabi.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        labels = diar.run_device(wav_dev=wav_dev, timers=False)
-    e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    launches = _cabi.launch_count - launches0
-    # ---- timed: end to end from pinned host memory (H2D of the samples + device work + D2H of the labels)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        labels = diar.run_device(wav_dev=None, timers=False)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    barrier()
+    dev_ms, e2e_ms = _time_steps(diar, wav_dev, args.steps, barrier, torch)
+    launches = (_cabi.launch_count - launches0) // 2  # the two timed loops run the same launches
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms = t.tolist()
-    # ---- untimed extras on rank 0: per-stage times, per-kernel roofline, CPU baseline sample
-    if rank == 0 and args.profiling:
-        print(json.dumps({"profiling_run": True, "ms_per_step": dev_ms / args.steps, "note": "not a bench value"}))
-    elif rank == 0:
+    dev_ms, e2e_ms = all_max([dev_ms, e2e_ms])
+    labels_main = {u: r["labels"].copy() for u, r in diar.results.items()}
+    # ---- wall clock of the reference-facing call itself (prepare + device path + output files), same recording
+    call_s = []
+    for _ in range(0 if args.profiling else 3):
+        barrier()
+        t0 = time.perf_counter()
+        diar.diarize()
+        call_s.append(time.perf_counter() - t0)
+    call_ms = all_max([1e3 * sum(call_s) / max(len(call_s), 1)])[0]
+    host_split = dict(getattr(diar, "host_seconds", {}))
+    # ---- N > 1: BASELINE config #5, one 4-hour recording sharded over all ranks (strong scaling), next to the weak-scaling line
+    strong = None
+    if world > 1 and not shard and not batch_mode and not args.no_strong and not args.profiling:
+        strong = strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch)
+    # ---- untimed extras on rank 0: per-stage times, per-kernel roofline
+    if args.profiling:
+        if rank == 0:
+            print(json.dumps({"profiling_run": True, "ms_per_step": dev_ms / args.steps, "note": "not a bench value"}))
+    elif rank == 0 or shard:
+        # (under --shard every rank has to take part in the collectives of these two extra passes)
         diar.run_device(wav_dev=wav_dev, timers=True)
         stage_ms = dict(diar.stage_ms)
         from whisper_nemo_b200 import clustering as _cl
@@ -214,6 +298,7 @@ def run_b200(args):
         diar.run_device(wav_dev=wav_dev, timers=False)
         prof = _cabi.stop_profile()
         spectral = list(_cl.spectral_log)
+    if rank == 0 and not args.profiling:
         g = {"calls": 0, "ms": 0.0, "work": 0.0}      # the dominant kernel: gemm_tcgen05_2cta_kernel (all its launches)
         g_all = {"calls": 0, "ms": 0.0, "work": 0.0}  # every tcgen05 GEMM launch, small projections included
         for key, v in prof.items():
@@ -225,10 +310,12 @@ def run_b200(args):
                         g[f] += v[f]
         peaks = _peaks()
         gemm_tflops = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        traffic = _ncu_traffic()
         roofline = {
             "kernel": "gemm_tcgen05_2cta_kernel (CTA-pair tcgen05 GEMM: the TitaNet-L pointwise convs of the embedding stage)",
             "bound": "tensor", "achieved": round(gemm_tflops, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": round(gemm_tflops / peaks["tflops"], 4), "traffic": NCU_GEMM_TRAFFIC, "peak_source": peaks["src"],
+            "frac": round(gemm_tflops / peaks["tflops"], 4), "traffic": traffic["bytes_per_launch"] if traffic else None,
+            "traffic_detail": traffic, "peak_source": peaks["src"],
             "launches_per_step": g["calls"], "avg_launch_ms": round(g["ms"] / max(g["calls"], 1), 4),
             "share_of_step": round(g["ms"] / (dev_ms / args.steps), 3),
             "all_gemm_launches": {"calls": g_all["calls"], "ms": round(g_all["ms"], 3),
@@ -239,35 +326,86 @@ def run_b200(args):
                        {"calls": v["calls"], "ms": round(v["ms"], 3), "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)})
                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         hours = seconds / 3600.0
-        total_hours = (600.0 * args.batch / 3600.0) if batch_mode else world * hours
+        total_hours = (600.0 * args.batch / 3600.0) if batch_mode else (hours if shard else world * hours)
         value = total_hours * args.steps / (dev_ms * 1e-3)
         e2e_val = total_hours * args.steps / (e2e_ms * 1e-3)
         res = next(iter(diar.results.values()))
-        cpu = cpu_baseline_sample(args, weights) if not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong" if batch_mode else "weak", "vs_baseline": None,
-            "dtype": "fp16", "dtype_detail": "fp16 tensor-core GEMMs with fp32 accumulation (TitaNet-L), fp32 featurizer / affinity / eigen-solvers, fp64 Sturm + Jacobi",
-            "data": "synthetic",
-            "config": {"workload": (f"{workload} (BASELINE.json configs[3]): batch of {args.batch} x 600 s synthetic 3-speaker recordings in one "
-                                    f"manifest, diar_infer_general.yaml, dealt to {world} rank(s) by recording, oracle VAD, TitaNet-L random-init seed 1234")
-                       if batch_mode else
-                       (f"{workload} (BASELINE.json configs[{WORKLOADS[workload][3]}]): {seconds:.0f} s synthetic "
-                        f"{WORKLOADS[workload][2]}-speaker 16 kHz recording per GPU, diar_infer_{WORKLOADS[workload][0]}.yaml, oracle VAD, "
-                        "TitaNet-L random-init seed 1234"), "windows_per_recording": windows, "frames_per_recording": frames,
-                       "base_scale_windows": int(len(res["labels"])), "speakers_found": int(res["debug"]["n_clusters"]),
-                       "p_hat": int(res["debug"]["p_hat"]), "sharding": "one recording per GPU, no collective" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (waveform 230 MB/h, activations > 1 GB per step); no explicit flush"},
+            "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong" if (batch_mode or shard) else "weak",
+            "vs_baseline": None, "dtype": "fp16",
+            "dtype_detail": "fp16 tensor-core GEMMs with fp32 accumulation (TitaNet-L), fp32 featurizer / affinity / eigen-solvers, fp64 Sturm + Jacobi",
+            "data": "synthetic", "config": workload_config(args, world),
+            "workload_stats": {"windows_per_recording": windows, "frames_per_recording": frames, "base_scale_windows": int(len(res["labels"])),
+                               "speakers_found": int(res["debug"]["n_clusters"]), "p_hat": int(res["debug"]["p_hat"]),
+                               "labels_stable_across_steps": all((labels_main[u] == r["labels"]).all() for u, r in diar.results.items())},
             "e2e": {"value": round(e2e_val, 4), "unit": UNIT, "h2d_bytes_per_step": int(diar._wav_host.numel() * 4),
-                    "d2h_bytes_per_step": int(len(res["labels"]) * 8), "ms_per_step": round(e2e_ms / args.steps, 3)},
+                    "d2h_bytes_per_step": int(sum(len(r["labels"]) for r in diar.results.values()) * 8), "ms_per_step": round(e2e_ms / args.steps, 3)},
+            "diarize_call": {"value": round(total_hours / (call_ms * 1e-3), 4), "unit": UNIT, "ms_per_call": round(call_ms, 1),
+                             "host_seconds_last_call": {k: round(v, 4) for k, v in host_split.items()},
+                             "what": "wall clock of ClusteringDiarizer(cfg).diarize(): WAV read + manifests + windows + H2D + device path + D2H + RTTM/label files"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}, "kernels_ms_per_step": kernels, "host_prepare_s": round(prep_s, 3),
             "spectral_solver": spectral,
         }
+        if strong is not None:
+            line["strong_4h"] = strong
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch, workload="telephonic_4h", steps=3, warmup=2):
+    """BASELINE config #5 on the N GPUs of this run: ONE 4-hour 12-speaker recording (telephonic YAML), windows of every scale,
+    long-form chunks and the rows of the spectral products sharded over the ranks, NCCL all-gathers in the data path; rank 0
+    also diarizes it alone, and the labels must be bit-identical."""
+    from whisper_nemo_b200 import ClusteringDiarizer
+
+    cfg, seconds = _shared_session(workload, 7, rank, barrier)
+    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights, shard_windows=True).to("cuda")
+    diar._prepare()
+    wav_dev = diar._wav_host.to(dev)
+    for _ in range(warmup):
+        diar.run_device(wav_dev=wav_dev, timers=False)
+    dev_ms, e2e_ms = _time_steps(diar, wav_dev, steps, barrier, torch)
+    dev_ms, e2e_ms = all_max([dev_ms, e2e_ms])
+    diar.run_device(wav_dev=wav_dev, timers=True)
+    stage_ms = dict(diar.stage_ms)
+    sharded = next(iter(diar.results.values()))
+    out = None
+    if rank == 0:
+        solo = ClusteringDiarizer(cfg=cfg, speaker_model=weights, shard_windows=False).to("cuda")
+        solo._prepare()
+        solo.run_device(wav_dev=wav_dev, timers=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        solo.run_device(wav_dev=wav_dev, timers=False)
+        e1.record()
+        torch.cuda.synchronize()
+        solo_ms = e0.elapsed_time(e1)
+        alone = next(iter(solo.results.values()))
+        hours = seconds / 3600.0
+        out = {"workload": f"{workload} (BASELINE.json configs[4]): ONE {seconds:.0f} s synthetic 12-speaker recording, diar_infer_telephonic.yaml, "
+                           f"sharded over {world} GPUs", "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
+               "value": round(hours * steps / (dev_ms * 1e-3), 4), "unit": UNIT, "ms_per_step": round(dev_ms / steps, 3),
+               "e2e": {"value": round(hours * steps / (e2e_ms * 1e-3), 4), "ms_per_step": round(e2e_ms / steps, 3)},
+               "one_gpu_ms_per_step": round(solo_ms, 3), "speedup_vs_one_gpu": round(solo_ms / (dev_ms / steps), 3),
+               "labels_identical_to_one_gpu": bool(len(alone["labels"]) == len(sharded["labels"]) and (alone["labels"] == sharded["labels"]).all()),
+               "base_scale_windows": int(len(sharded["labels"])), "speakers_found": int(sharded["debug"]["n_clusters"]),
+               "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
+    barrier()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle/)
+def _oracle_model(weights):
+    from oracle.titanet import TitaNetL
+
+    model = TitaNetL(compute_logits=False)
+    model.load_state_dict(weights, strict=False)
+    return model.eval()
 
 
 def _oracle_run(seconds, domain, speakers, seed, weights, threads):
@@ -275,13 +413,10 @@ def _oracle_run(seconds, domain, speakers, seed, weights, threads):
     import torch
 
     from oracle.clustering_diarizer import OracleClusteringDiarizer
-    from oracle.titanet import TitaNetL
-    from tests.util import make_session_cfg
+    from tools.workload import make_session_cfg
 
     torch.set_num_threads(threads)
-    model = TitaNetL(compute_logits=False)
-    model.load_state_dict(weights, strict=False)
-    model.eval()
+    model = _oracle_model(weights)
     with tempfile.TemporaryDirectory() as tmp:
         cfg, _, _ = make_session_cfg(tmp, domain, seconds, speakers, seed)
         d = OracleClusteringDiarizer(cfg, model)
@@ -293,52 +428,79 @@ def _oracle_run(seconds, domain, speakers, seed, weights, threads):
     return (seconds / 3600.0) / dt, dict(d.stage_seconds)
 
 
-def _reference_weights():
-    import torch
-
-    if torch.cuda.is_available():
-        from whisper_nemo_b200 import checkpoint
-
-        return checkpoint.calibrated(torch.device("cuda", 0))
-    from oracle.titanet import seeded_state_dict
-
-    return seeded_state_dict(1234, compute_logits=False).state_dict()
+def _host_threads():
+    """Cores this process may run on (the GPU box pins the job to a subset of its CPUs)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
-def cpu_baseline_sample(args, weights, sample_s=150.0):
+def cpu_baseline_sample(args, weights, sample_s=120.0):
     domain, seconds, speakers, _ = WORKLOADS["general_10min" if args.workload == BATCH_WORKLOAD else args.workload]
     sample_s = min(sample_s, seconds)
-    threads = os.cpu_count() or 1
-    v, stages = _oracle_run(sample_s, domain, speakers, 100, weights, threads)
+    threads = _host_threads()
+    v, stages = _oracle_run(sample_s, domain, speakers, SEED, weights, threads)
     return {"value": round(v, 6), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first-principles CPU restatement of NeMo ClusteringDiarizer (oracle/, NeMo not installable) on {sample_s:.0f} s of the same "
-                      f"synthetic {domain} workload, fp32, {threads} torch threads; stage seconds {({k: round(x, 2) for k, x in stages.items()})}; "
-                      "clustering cost grows super-linearly with length, so the full-length CPU throughput is lower than this sample's"}
+            "sample": f"first-principles CPU restatement of NeMo ClusteringDiarizer (oracle/, NeMo not installable) on a {sample_s:.0f} s recording of the "
+                      f"same synthetic {domain} workload, end to end, fp32, {threads} torch threads; stage seconds {({k: round(x, 2) for k, x in stages.items()})}; "
+                      "clustering cost grows super-linearly with length, so the full-length CPU throughput (bench.py --impl reference) is lower"}
 
 
 def run_reference(args):
+    """The reference arm: NeMo's ClusteringDiarizer cannot be installed here, so this times its CPU
+    restatement (oracle/) on the SAME workload as the B200 arm -- ONE full pass over rank 0's recording:
+      * the dataloader batches (64 windows each, all scales) are dealt round-robin to W + K steps; every step embeds its
+        share (a bounded, stratified sample of the workload); the W warm-up steps are real work of the pass, just untimed;
+      * after the K timed steps the clustering of the FULL recording (long-form path included) runs once, timed.
+    value = audio hours / (timed embedding seconds x (W + K) / K + clustering seconds): the full-length CPU throughput,
+    with the untimed warm-up share of the (linear, batch-independent) embedding cost filled in at the timed steps' rate."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    import torch
+
+    from oracle.clustering_diarizer import OracleClusteringDiarizer
+    from tools.workload import make_session_cfg
+    from whisper_nemo_b200 import checkpoint  # pure-Python weight initialiser + fixture; loads no native code
+
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
     domain, seconds, speakers, idx = WORKLOADS["general_10min" if args.workload == BATCH_WORKLOAD else args.workload]
-    total = args.steps + args.warmup
-    sample_s = min(seconds, 120.0 if total <= 8 else 60.0)
-    threads = os.cpu_count() or 1
-    weights = _reference_weights()
-    for _ in range(args.warmup):
-        _oracle_run(sample_s, domain, speakers, 100, weights, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v, stages = _oracle_run(sample_s, domain, speakers, 100, weights, threads)
-    dt = time.perf_counter() - t0
-    value = args.steps * (sample_s / 3600.0) / dt
-    cpu = {"value": round(value, 6), "unit": UNIT, "cores": threads, "kind": "port",
-           "sample": f"{sample_s:.0f} s of the synthetic {domain} workload per step (bounded sample of the {seconds:.0f} s recording), CPU restatement of "
-                     f"NeMo ClusteringDiarizer (oracle/), fp32, {threads} torch threads"}
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} (BASELINE.json configs[{idx}]), bounded sample: {sample_s:.0f} s per step"},
+    threads = _host_threads()
+    torch.set_num_threads(threads)
+    model = _oracle_model(checkpoint.seeded())
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        cfg, _, _ = make_session_cfg(tmp, domain, seconds, speakers, SEED)
+        d = OracleClusteringDiarizer(cfg, model)
+        d.prepare()
+        plan = d.plan_batches()
+        step_s = []
+        for step in range(W + K):
+            t0 = time.perf_counter()
+            for item in plan[step::W + K]:
+                d.embed_batch(item)
+            step_s.append(time.perf_counter() - t0)
+        d.finish_embed()
+        t0 = time.perf_counter()
+        d.cluster()
+        cluster_s = time.perf_counter() - t0
+        res = next(iter(d.results.values()))
+    timed_embed_s = sum(step_s[W:])
+    full_pass_s = timed_embed_s * (W + K) / K + cluster_s
+    value = (seconds / 3600.0) / full_pass_s
+    sample = (f"ONE full pass of the CPU restatement of NeMo ClusteringDiarizer (oracle/, fp32, {threads} torch threads) over the {seconds:.0f} s "
+              f"recording: {len(plan)} dataloader batches of 64 windows dealt round-robin to {W} warm-up + {K} timed steps "
+              f"({timed_embed_s:.1f} s timed embedding, {sum(step_s[:W]):.1f} s untimed), then the clustering of the full recording once "
+              f"({cluster_s:.1f} s, {len(res['labels'])} base windows, {res['debug']['n_clusters']} speakers); "
+              f"value = hours / (timed embedding x {(W + K) / K:.3f} + clustering) = hours / {full_pass_s:.1f} s")
+    cpu = {"value": round(value, 6), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round((timed_embed_s + cluster_s) / K * 1e3, 1), "higher_is_better": True,
+            "scaling": "strong" if (args.workload == BATCH_WORKLOAD or args.shard) else "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(args, world),
+            "steps_effective": 1, "full_pass_seconds": round(full_pass_s, 1),
+            "stage_seconds": {"embed_timed": round(timed_embed_s, 2), "embed_untimed_warmup": round(sum(step_s[:W]), 2), "cluster_full": round(cluster_s, 2)},
             "cpu_baseline": cpu, "e2e": {"value": round(value, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -351,6 +513,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="meeting_1h", choices=sorted(WORKLOADS) + [BATCH_WORKLOAD])
     ap.add_argument("--batch", type=int, default=64, help="recordings in the batch workload")
+    ap.add_argument("--shard", action="store_true", help="N > 1: ONE recording sharded over all ranks (strong scaling) instead of one recording per rank")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the extra strong_4h measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profiling", action="store_true", help="allow < 3 warm-up steps and skip the extras (only for runs under ncu; never a bench value)")
     args = ap.parse_args()

@@ -110,35 +110,50 @@ class OracleClusteringDiarizer:
             self.subseg_manifests[scale_idx] = path
 
     # -- timed: waveform in RAM -> labels in RAM ----------------------------------------------
-    def _extract_embeddings(self, manifest_file):
-        entries = [json.loads(l) for l in open(manifest_file) if l.strip()]
-        sigs = []
-        for dic in entries:
-            uniq = su.get_uniqname_from_filepath(dic["audio_filepath"])
-            start = int(dic["offset"] * self.sample_rate)
-            n = int(dic["duration"] * self.sample_rate)
-            sigs.append(torch.from_numpy(self.wavs[uniq][start : start + n]))
-        all_embs = []
-        for b0 in range(0, len(sigs), self.batch_size):
-            audio, lens = collate(sigs[b0 : b0 + self.batch_size])
-            _, embs = self.model(audio, lens)
-            all_embs.append(embs)
-        all_embs = torch.cat(all_embs) if all_embs else torch.empty([0])
-        embeddings, time_stamps = {}, {}
-        for i, dic in enumerate(entries):
-            uniq = su.get_uniqname_from_filepath(dic["audio_filepath"])
-            embeddings.setdefault(uniq, []).append(all_embs[i].view(1, -1))
-            start = dic["offset"]
-            time_stamps.setdefault(uniq, []).append([start, start + dic["duration"]])
-        embeddings = {u: torch.cat(v) for u, v in embeddings.items()}
-        return embeddings, time_stamps
+    def plan_batches(self):
+        """Dataloader batches of the whole job, in upstream's order (scale by scale, `batch_size` windows each):
+        [(scale_idx, first window, one past last window)].  `embed()` is `embed_batch` over this list + `finish_embed()`;
+        bench.py's reference arm walks the same list in slices to time a bounded part of the pass per step."""
+        self._entries, self._sigs, self._embs = {}, {}, {}
+        plan = []
+        for scale_idx in self.multiscale_args_dict["scale_dict"]:
+            entries = [json.loads(l) for l in open(self.subseg_manifests[scale_idx]) if l.strip()]
+            sigs = []
+            for dic in entries:
+                uniq = su.get_uniqname_from_filepath(dic["audio_filepath"])
+                start = int(dic["offset"] * self.sample_rate)
+                n = int(dic["duration"] * self.sample_rate)
+                sigs.append(torch.from_numpy(self.wavs[uniq][start : start + n]))
+            self._entries[scale_idx], self._sigs[scale_idx], self._embs[scale_idx] = entries, sigs, {}
+            plan.extend((scale_idx, b0, min(b0 + self.batch_size, len(sigs))) for b0 in range(0, len(sigs), self.batch_size))
+        return plan
+
+    def embed_batch(self, item):
+        scale_idx, b0, b1 = item
+        audio, lens = collate(self._sigs[scale_idx][b0:b1])
+        _, embs = self.model(audio, lens)
+        self._embs[scale_idx][b0] = embs
+
+    def finish_embed(self):
+        self.multiscale_embeddings_and_timestamps = {}
+        for scale_idx, entries in self._entries.items():
+            parts = [self._embs[scale_idx][b0] for b0 in sorted(self._embs[scale_idx])]
+            all_embs = torch.cat(parts) if parts else torch.empty([0])
+            embeddings, time_stamps = {}, {}
+            for i, dic in enumerate(entries):
+                uniq = su.get_uniqname_from_filepath(dic["audio_filepath"])
+                embeddings.setdefault(uniq, []).append(all_embs[i].view(1, -1))
+                start = dic["offset"]
+                time_stamps.setdefault(uniq, []).append([start, start + dic["duration"]])
+            self.multiscale_embeddings_and_timestamps[scale_idx] = ({u: torch.cat(v) for u, v in embeddings.items()}, time_stamps)
+        self.embs_and_timestamps = su.get_embs_and_timestamps(self.multiscale_embeddings_and_timestamps, self.multiscale_args_dict)
+        self._sigs, self._embs = {}, {}
 
     def embed(self):
         t0 = time.perf_counter()
-        self.multiscale_embeddings_and_timestamps = {}
-        for scale_idx in self.multiscale_args_dict["scale_dict"]:
-            self.multiscale_embeddings_and_timestamps[scale_idx] = self._extract_embeddings(self.subseg_manifests[scale_idx])
-        self.embs_and_timestamps = su.get_embs_and_timestamps(self.multiscale_embeddings_and_timestamps, self.multiscale_args_dict)
+        for item in self.plan_batches():
+            self.embed_batch(item)
+        self.finish_embed()
         self.stage_seconds["embed"] = time.perf_counter() - t0
 
     def cluster(self):

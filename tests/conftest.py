@@ -24,10 +24,11 @@ def dev():
 
 @pytest.fixture(scope="session")
 def weights(dev):
-    """The product's fixed-seed random-init TitaNet-L (calibrated on the GPU), shared with the oracle."""
+    """The fixed-seed random-init TitaNet-L of the benchmark (embedding-BN statistics from the committed CPU-oracle
+    fixture), shared by the product and the oracle."""
     from whisper_nemo_b200 import checkpoint
 
-    return checkpoint.calibrated(dev)
+    return checkpoint.seeded()
 
 
 @pytest.fixture(scope="session")

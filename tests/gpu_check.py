@@ -84,7 +84,7 @@ def _oracle_model():
 
 
 def check_feat(model=None):
-    from whisper_nemo_b200 import synth
+    from tools import workload as synth
 
     model = model or _oracle_model()
     wav, _ = synth.synth_recording(30.0, 2, seed=5)
@@ -111,7 +111,7 @@ def check_feat(model=None):
 
 def check_titanet(model=None):
     from oracle.clustering_diarizer import collate
-    from whisper_nemo_b200 import synth
+    from tools import workload as synth
 
     model = model or _oracle_model()
     wav, _ = synth.synth_recording(40.0, 3, seed=7)

@@ -12,7 +12,8 @@ from oracle import offline_clustering as oc
 from oracle import speaker_utils as osu
 from tests.util import synthetic_multiscale_embeddings
 from whisper_nemo_b200 import clustering as cl
-from whisper_nemo_b200 import config, longform as lf, sharding, synth
+from tools import workload as synth
+from whisper_nemo_b200 import config, longform as lf, sharding
 from whisper_nemo_b200 import speaker_utils as su
 
 SCALES = [(1.5, .75), (1.25, .625), (1.0, .5), (.75, .375), (.5, .25), (3.0, 1.5), (1.9, .95), (1.2, .6)]

@@ -36,7 +36,7 @@ def _featurizer_variant(monkeypatch, variant):
                                             (30400, [30400, 30400, 12345])])
 def test_featurizer_matches_oracle(dev, oracle_model, weights, fixed_len, lens, variant, monkeypatch):
     from oracle.clustering_diarizer import collate
-    from whisper_nemo_b200 import synth
+    from tools import workload as synth
     from whisper_nemo_b200 import titanet as tn
 
     _featurizer_variant(monkeypatch, variant)
@@ -62,7 +62,7 @@ def test_featurizer_matches_oracle(dev, oracle_model, weights, fixed_len, lens, 
 @pytest.mark.parametrize("fixed_len,n", [(24000, 12), (8000, 40), (48000, 5), (20000, 7)])
 def test_titanet_embeddings_match_oracle(dev, oracle_model, weights, fixed_len, n, variant, monkeypatch):
     from oracle.clustering_diarizer import collate
-    from whisper_nemo_b200 import synth
+    from tools import workload as synth
     from whisper_nemo_b200 import titanet as tn
 
     _featurizer_variant(monkeypatch, variant)
@@ -287,7 +287,8 @@ def test_multi_recording_manifest_matches_oracle(dev, oracle_model, weights, tmp
     """A manifest with several recordings (BASELINE config #4 in miniature): the dataloader batches of 64 windows run across
     recording boundaries (fixed_seq collate), each recording is clustered on its own."""
     from oracle.clustering_diarizer import OracleClusteringDiarizer
-    from whisper_nemo_b200 import ClusteringDiarizer, config, synth
+    from tools import workload as synth
+    from whisper_nemo_b200 import ClusteringDiarizer, config
 
     def build(root):
         entries = []

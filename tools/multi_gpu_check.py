@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from tests.util import make_session_cfg
+from tools.workload import make_session_cfg
 from whisper_nemo_b200 import ClusteringDiarizer, checkpoint
 
 
@@ -25,7 +25,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 1200.0
     domain = sys.argv[2] if len(sys.argv) > 2 else "telephonic"
-    weights = checkpoint.calibrated(dev)
+    weights = checkpoint.seeded()
     work = os.path.join(tempfile.gettempdir(), f"b200d_mgpu_r{rank}")
     cfg, _, _ = make_session_cfg(work, domain, seconds, 4 if seconds < 3000 else 8, seed=7)
     results = {}

@@ -9,14 +9,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 faulthandler.enable()
 import torch
 
-from tests.util import make_session_cfg
+from tools.workload import make_session_cfg
 from whisper_nemo_b200 import ClusteringDiarizer, checkpoint
 
 domain, seconds, reps = sys.argv[1], float(sys.argv[2]), int(sys.argv[3])
 dev = torch.device("cuda", 0)
-weights = checkpoint.calibrated(dev)
+weights = checkpoint.seeded()
 if domain.startswith("batch"):  # batchN: N recordings in one manifest (general YAML)
-    from whisper_nemo_b200 import config, synth
+    from tools import workload as synth
+    from whisper_nemo_b200 import config
 
     root = tempfile.mkdtemp()
     entries = []

@@ -1,4 +1,7 @@
-"""Seeded synthetic multi-speaker 16 kHz audio + ground-truth RTTM.
+"""Benchmark / test WORKLOADS: seeded synthetic multi-speaker 16 kHz audio + ground-truth RTTM, the session
+(manifest + config) builders around it and the label / RTTM comparison metrics.  Shared by tests/, bench.py (both arms)
+and __graft_entry__.smoke(); it imports neither the product package nor the oracle, so the reference arm of the
+benchmark can build its inputs without loading libb200d.so.
 
 There is no network for datasets and the reference's only clip
 (/root/reference/tests/assets/test.opus, 22.58 s stereo 48 kHz Opus) cannot be
@@ -148,3 +151,98 @@ def make_session(work_dir: str, name: str, duration_s: float, n_speakers: int, s
     write_wav(wav_path, wav, pcm16=pcm16)
     write_rttm(rttm_path, name, turns)
     return wav_path, rttm_path, wav, turns
+
+
+# ------------------------------------------------------------------------------------------ sessions
+class AttrDict(dict):
+    """Minimal OmegaConf-DictConfig stand-in (attribute access on nested dicts); the product's `config.as_config` and the
+    oracle's `_get` both accept it."""
+
+    def __init__(self, data=None):
+        super().__init__()
+        for k, v in dict(data or {}).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, AttrDict(v) if isinstance(v, dict) and not isinstance(v, AttrDict) else v)
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+CONF_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "whisper_nemo_b200", "conf")
+
+
+def load_domain_config(domain: str) -> AttrDict:
+    """diar_infer_<domain>.yaml (the reference's nemo_msdd_configs/*.yaml schema, bundled with the product as data)."""
+    import yaml
+
+    with open(os.path.join(CONF_DIR, f"diar_infer_{domain}.yaml")) as f:
+        return AttrDict(yaml.safe_load(f))
+
+
+def make_session_cfg(tmp_dir, domain, duration_s, n_speakers, seed, name="mono_file", pcm16=False, **overrides):
+    """Synthetic recording + manifest + config (oracle VAD from the ground-truth RTTM).  Returns (cfg, waveform, turns)."""
+    wav_path, rttm_path, wav, turns = make_session(str(tmp_dir), name, duration_s, n_speakers, seed, pcm16=pcm16)
+    cfg = load_domain_config(domain)
+    man = os.path.join(str(tmp_dir), "input_manifest.json")
+    write_manifest(man, [{"audio_filepath": wav_path, "rttm_filepath": rttm_path}])
+    cfg.diarizer.manifest_filepath = man
+    cfg.diarizer.out_dir = str(tmp_dir)
+    cfg.diarizer.oracle_vad = True
+    for k, v in overrides.items():
+        cfg.diarizer.clustering.parameters[k] = v
+    return cfg, wav, turns
+
+
+# ------------------------------------------------------------------------------------------ metrics
+def best_permutation_agreement(a, b) -> float:
+    """Fraction of items on which labelings a and b agree under the best one-to-one label mapping."""
+    from scipy.optimize import linear_sum_assignment
+
+    a, b = np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64)
+    assert a.shape == b.shape
+    k = max(int(a.max()) + 1, int(b.max()) + 1)
+    cont = np.zeros((k, k), dtype=np.int64)
+    np.add.at(cont, (a, b), 1)
+    r, c = linear_sum_assignment(-cont)
+    return cont[r, c].sum() / len(a)
+
+
+def rttm_frames(path, step=0.01):
+    """RTTM -> {speaker: set of 10 ms frame indices} for a permutation-invariant comparison of two RTTMs."""
+    out = {}
+    with open(path) as f:
+        for line in f:
+            fld = line.split()
+            if not fld:
+                continue
+            st, du, spk = float(fld[3]), float(fld[4]), fld[7]
+            out.setdefault(spk, set()).update(range(int(round(st / step)), int(round((st + du) / step))))
+    return out
+
+
+def rttm_der_between(path_a, path_b) -> float:
+    """Speaker-confusion + miss + false-alarm time between two RTTMs over their union, best label mapping
+    (a small permutation-invariant DER; 0.0 means identical turns up to speaker renaming)."""
+    from scipy.optimize import linear_sum_assignment
+
+    fa, fb = rttm_frames(path_a), rttm_frames(path_b)
+    ka, kb = sorted(fa), sorted(fb)
+    k = max(len(ka), len(kb))
+    overlap = np.zeros((k, k))
+    for i, sa in enumerate(ka):
+        for j, sb in enumerate(kb):
+            overlap[i, j] = len(fa[sa] & fb[sb])
+    r, c = linear_sum_assignment(-overlap)
+    matched = overlap[r, c].sum()
+    total = max(sum(len(v) for v in fa.values()), sum(len(v) for v in fb.values()))
+    return 1.0 - matched / max(total, 1)

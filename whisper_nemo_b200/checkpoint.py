@@ -15,10 +15,12 @@ the running statistics are not an identity (BN folding is exercised).  One Batch
 drawn blindly: the one in front of the 6144 -> 192 embedding projection sees pooled statistics
 whose per-channel offsets are ~10x larger than their variation between speakers, and a random
 guess of its running mean would bury the speaker information under a constant vector.
-`calibrated()` therefore sets that layer's running statistics from one pass of seeded synthetic
-speech through the B200 encoder itself (this package's own kernels; a trained checkpoint carries
-the equivalent numbers from training).  Parity tests load the resulting state_dict into the CPU
-oracle, so neither the init distribution nor the calibration enters any parity claim.
+Its running statistics are therefore a committed fixture (`data/titanet_large_random_seed<seed>_embbn.pt`,
+two 6144-vectors) measured once by `tools/make_embbn_fixture.py`, which pushes seeded synthetic
+speech through the CPU oracle's fp32 encoder (a trained checkpoint carries the equivalent numbers
+from training).  The weights are thus reproducible without a GPU and identical for the product, the
+oracle and the benchmark's reference arm; neither the init distribution nor the calibration enters
+any parity claim.  This module is pure Python / CPU torch: importing it never loads libb200d.so.
 """
 import os
 from typing import Dict
@@ -90,65 +92,90 @@ def random_init_titanet_large(seed: int = DEFAULT_SEED) -> Dict[str, torch.Tenso
 
 
 _CACHE: Dict[str, Dict[str, torch.Tensor]] = {}
+_DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
-def calibration_windows(seed: int = DEFAULT_SEED, n_speakers: int = 8, duration_s: float = 64.0, window_s: float = 1.5):
-    """Seeded synthetic speech cut into 1.5 s windows (inside speaker turns): (waveform float32, starts, length)."""
-    from . import synth
-
-    wav, turns = synth.synth_recording(duration_s, n_speakers, seed=seed + 77)
-    n = int(window_s * synth.SR)
-    starts = []
-    for a, b, _ in turns:
-        t = a
-        while t + window_s <= b:
-            starts.append(int(t * synth.SR))
-            t += window_s
-    return wav, starts, n
+def embbn_fixture_path(seed: int = DEFAULT_SEED) -> str:
+    return os.path.join(_DATA_DIR, f"titanet_large_random_seed{seed}_embbn.pt")
 
 
-def calibrate_embedding_bn(state_dict: Dict[str, torch.Tensor], device, seed: int = DEFAULT_SEED) -> Dict[str, torch.Tensor]:
-    """Return a copy of `state_dict` whose `decoder.emb_layers.0.0.running_{mean,var}` are the statistics of the
-    attentive-pooling output over seeded synthetic speech, measured by running the B200 encoder (TitaNetB200)."""
-    from .titanet import TitaNetB200
-
-    wav, starts, n = calibration_windows(seed)
-    net = TitaNetB200(state_dict, device, max_frames=8192)
-    wav_d = torch.from_numpy(wav).to(net.device)
-    st = torch.tensor(starts, dtype=torch.int32, device=net.device)
-    ln = torch.full((len(starts),), n, dtype=torch.int32, device=net.device)
-    pools = []
-    step = max(1, net.max_frames // (n // 160 + 1))  # an upper bound on the frames per window in either featurizer variant
-    for c0 in range(0, len(starts), step):
-        taps = {}
-        net.embed_segments(wav_d, st[c0 : c0 + step], ln[c0 : c0 + step], n, taps=taps)
-        pools.append(taps["pool"].float())
-    pool = torch.cat(pools)
-    out = dict(state_dict)
-    out["decoder.emb_layers.0.0.running_mean"] = pool.mean(dim=0).cpu()
-    out["decoder.emb_layers.0.0.running_var"] = pool.var(dim=0, unbiased=False).cpu()
-    return out
-
-
-def calibrated(device, seed: int = None) -> Dict[str, torch.Tensor]:
-    """The fixed-seed random-init TitaNet-L the diarizer uses for `model_path: titanet_large`."""
+def seeded(seed: int = None) -> Dict[str, torch.Tensor]:
+    """The fixed-seed random-init TitaNet-L (`model_path: titanet_large_random`): `random_init_titanet_large(seed)` with
+    the embedding BatchNorm's running statistics taken from the committed fixture of that seed."""
     if seed is None:
         seed = int(os.environ.get("B200D_TITANET_SEED", DEFAULT_SEED))
-    key = f"cal{seed}"
+    key = f"seeded{seed}"
     if key not in _CACHE:
-        _CACHE[key] = calibrate_embedding_bn(random_init_titanet_large(seed), device, seed)
+        path = embbn_fixture_path(seed)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not found: generate it with `python tools/make_embbn_fixture.py --seed {seed}` (CPU, ~1 min)")
+        fix = torch.load(path, map_location="cpu", weights_only=True)
+        sd = random_init_titanet_large(seed)
+        sd["decoder.emb_layers.0.0.running_mean"] = fix["running_mean"].float().clone()
+        sd["decoder.emb_layers.0.0.running_var"] = fix["running_var"].float().clone()
+        _CACHE[key] = sd
     return _CACHE[key]
 
 
+def calibrated(device=None, seed: int = None) -> Dict[str, torch.Tensor]:
+    """Round-1 name of `seeded` (the calibration ran on the GPU then; `device` is ignored now)."""
+    return seeded(seed)
+
+
+def _load_nemo_archive(path: str) -> Dict[str, torch.Tensor]:
+    """A `.nemo` file is a (possibly gzipped) tar holding `model_weights.ckpt` (torch.save of the state_dict) next to
+    `model_config.yaml` -- NeMo's normal `model_path` format (SaveRestoreConnector)."""
+    import io
+    import tarfile
+
+    with tarfile.open(path, "r:*") as tar:
+        member = next((m for m in tar.getmembers() if os.path.basename(m.name) == "model_weights.ckpt"), None)
+        if member is None:
+            raise ValueError(f"{path}: no model_weights.ckpt inside the .nemo archive")
+        data = tar.extractfile(member).read()
+    return torch.load(io.BytesIO(data), map_location="cpu", weights_only=True)
+
+
+def _find_local_titanet() -> str:
+    """A TitaNet-L checkpoint already on this machine: $B200D_TITANET_CKPT, or what NeMo's `from_pretrained` left in its
+    cache (~/.cache/torch/NeMo/**/titanet-l*.nemo)."""
+    env = os.environ.get("B200D_TITANET_CKPT")
+    if env:
+        return env
+    import glob
+
+    hits = sorted(glob.glob(os.path.join(os.path.expanduser("~"), ".cache", "torch", "NeMo", "**", "titanet-l*.nemo"), recursive=True))
+    return hits[-1] if hits else ""
+
+
 def resolve(model_path, device=None) -> Dict[str, torch.Tensor]:
-    """`diarizer.speaker_embeddings.model_path` -> TitaNet-L state_dict.  A local file is loaded
-    (`torch.load`, a state_dict or {'state_dict': ...}); `titanet_large` / None gives the fixed-seed
-    random init (seed overridable through B200D_TITANET_SEED), calibrated on `device`."""
+    """`diarizer.speaker_embeddings.model_path` -> TitaNet-L state_dict.
+      * a local file: a `.nemo` archive, or a `torch.save`d state_dict / {'state_dict': ...};
+      * `titanet_large_random`: the fixed-seed random init (BASELINE.json's benchmark weights; seed via B200D_TITANET_SEED);
+      * `titanet_large` / None (what the reference's create_config sets, helpers.py:281,290 -- an NGC download upstream):
+        $B200D_TITANET_CKPT or NeMo's local download cache when one exists; otherwise, because there is no network here,
+        the random init WITH A WARNING (speaker labels from untrained weights are meaningless), or an error when
+        B200D_STRICT_WEIGHTS=1."""
     if model_path and os.path.exists(str(model_path)):
-        obj = torch.load(str(model_path), map_location="cpu", weights_only=True)
+        path = str(model_path)
+        if path.endswith(".nemo"):
+            return _load_nemo_archive(path)
+        obj = torch.load(path, map_location="cpu", weights_only=True)
         return obj.get("state_dict", obj) if isinstance(obj, dict) and "state_dict" in obj else obj
-    if model_path in (None, "titanet_large", "titanet_large_random"):
-        if device is None:
-            raise ValueError("the random-init TitaNet-L is calibrated on the GPU: pass the device")
-        return calibrated(device)
+    if model_path == "titanet_large_random":
+        return seeded()
+    if model_path in (None, "titanet_large"):
+        local = _find_local_titanet()
+        if local:
+            return resolve(local, device)
+        if os.environ.get("B200D_STRICT_WEIGHTS") == "1":
+            raise FileNotFoundError("speaker_embeddings.model_path='titanet_large': no local checkpoint ($B200D_TITANET_CKPT / NeMo cache) and "
+                                    "no network for the NGC download")
+        import warnings
+
+        warnings.warn("speaker_embeddings.model_path='titanet_large' could not be resolved to a checkpoint (no $B200D_TITANET_CKPT, nothing in "
+                      "~/.cache/torch/NeMo, no network): using the RANDOM-INIT fixed-seed TitaNet-L of the benchmark.  Speaker labels from "
+                      "untrained weights are NOT meaningful; point model_path at a .nemo / state_dict file for real diarization "
+                      "(B200D_STRICT_WEIGHTS=1 turns this warning into an error).", RuntimeWarning, stacklevel=2)
+        return seeded()
     raise FileNotFoundError(f"speaker_embeddings.model_path={model_path!r}: not a local checkpoint and there is no network for NGC models")
