@@ -81,6 +81,7 @@ class OracleClusteringDiarizer:
         self.clus = _get(cfg, "diarizer.clustering.parameters")
         self.stage_seconds: Dict[str, float] = {}
         self.results: Dict[str, dict] = {}
+        self.clusterers: Dict[str, LongFormSpeakerClustering] = {}
 
     # -- untimed preparation: manifests, VAD, WAV decode ------------------------------------
     def prepare(self):
@@ -171,6 +172,7 @@ class OracleClusteringDiarizer:
             else:
                 num_speakers = -1
             sc = LongFormSpeakerClustering()
+            self.clusterers[uniq_id] = sc
             labels = sc.forward_infer(
                 embeddings_in_scales=e["embeddings"],
                 timestamps_in_scales=e["timestamps"],

@@ -139,6 +139,7 @@ class LongFormSpeakerClustering:
         self.speaker_clustering = SpeakerClustering()
         self.embeddings_in_scales: List[torch.Tensor] = []
         self.timestamps_in_scales: List[torch.Tensor] = []
+        self.chunk_labels = {}  # long-form path: chunk index -> (first window, over-clustering labels); read by the parity tests
 
     @staticmethod
     def get_div_ceil_count(numer: int, denomin: int) -> int:
@@ -237,6 +238,7 @@ class LongFormSpeakerClustering:
                     max_num_speakers=chunk_cluster_count,
                     sparse_search_volume=sparse_search_volume,
                 )
+            self.chunk_labels[win_index] = (int(offset_index), Y_part.clone())
             num_to_be_merged = int(min(embeddings_per_chunk, emb_part.shape[0]) - chunk_cluster_count)
             min_count_per_cluster = self.get_div_ceil_count(numer=chunk_cluster_count, denomin=len(torch.unique(Y_part)))
             class_target_vol = get_merge_quantity(num_to_be_removed=num_to_be_merged, pre_clus_labels=Y_part, min_count_per_cluster=min_count_per_cluster)

@@ -254,7 +254,10 @@ class SpectralClustering:
 
     def getSpectralEmbeddings(self, affinity_mat: torch.Tensor) -> torch.Tensor:
         laplacian = getLaplacian(affinity_mat)
-        _, diffusion_map_ = eigDecompose(laplacian)
+        if switches.SPECTRAL_EIGH_FP64:  # test probe (off = upstream): how far do the LABELS depend on eigh's fp32 rounding?
+            diffusion_map_ = torch.linalg.eigh(laplacian.double())[1].float()
+        else:
+            _, diffusion_map_ = eigDecompose(laplacian)
         diffusion_map = diffusion_map_[:, : self.n_clusters]
         inv_idx = torch.arange(diffusion_map.size(1) - 1, -1, -1).long()
         embedding = diffusion_map.T[inv_idx, :]

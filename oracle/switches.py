@@ -51,3 +51,10 @@ ENHANCED_COUNT_THRES = 80
 # p-th position is unspecified.  The restatement pins it to the stable order (lower column first), which
 # is also what the CUDA path implements; set False to get torch's native (unspecified) tie order.
 ARGSORT_STABLE = True
+
+# TEST PROBE, not an upstream behaviour: run the eigh of SpectralClustering.getSpectralEmbeddings in float64 (result cast
+# back to float32).  Upstream's is fp32; where the k lowest eigenvalues have no gap to the next ones (the long-form
+# path over-clusters 10 000 windows into 50), fp32 LAPACK rounding decides which way near-degenerate eigenvectors mix, and
+# a handful of k-means assignments with it.  Tests flip this to measure how many labels of the ORACLE ITSELF hang on that
+# rounding (the yardstick for label differences between the CPU and the B200 path at that size).
+SPECTRAL_EIGH_FP64 = False

@@ -13,6 +13,28 @@ from tests.util import best_permutation_agreement, make_session_cfg, rttm_der_be
 pytestmark = pytest.mark.gpu
 
 
+def _clus_kwargs(cfg):
+    clus = cfg.diarizer.clustering.parameters
+    return dict(max_num_speakers=int(clus.max_num_speakers), max_rp_threshold=float(clus.max_rp_threshold),
+                sparse_search_volume=int(clus.sparse_search_volume), chunk_cluster_count=clus.chunk_cluster_count,
+                embeddings_per_chunk=clus.embeddings_per_chunk)
+
+
+def _oracle_is_decisive(e, kw, labels, rel=3e-3, seed=0):
+    """End to end the discrete decisions can only be required to agree where the oracle's own decision is not a near-tie:
+    re-run the ORACLE's clustering on its embeddings perturbed at the size of the fp16 embedding error (relative 3e-3);
+    decisive = same speaker count and identical labels up to permutation."""
+    from oracle.longform_clustering import LongFormSpeakerClustering as OracleLF
+
+    gen = torch.Generator().manual_seed(seed)
+    emb = e["embeddings"]
+    pert = emb * (1.0 + rel * torch.randn(emb.shape, generator=gen))
+    state = torch.get_rng_state()
+    relabel = OracleLF().forward_infer(pert, e["timestamps"], e["multiscale_segment_counts"], e["multiscale_weights"], **kw)
+    torch.set_rng_state(state)
+    return len(set(relabel.tolist())) == len(set(np.asarray(labels).tolist())) and best_permutation_agreement(relabel.numpy(), labels) == 1.0
+
+
 def _windows(wav, fixed_len, lens, step=3000, first=1000):
     starts = [first + step * i for i in range(len(lens))]
     return starts, lens
@@ -102,6 +124,7 @@ def test_speaker_clustering_matches_oracle(dev, duration, scales, k, seed):
     want = osc.forward_infer(embs, stamps, counts, w, max_num_speakers=8, max_rp_threshold=0.25, sparse_search_volume=30)
     torch.set_rng_state(state)
     gsc = cl.SpeakerClustering()
+    gsc.keep_affinity = True
     got = gsc.forward_infer(embs.to(dev), stamps, counts, w, max_num_speakers=8, max_rp_threshold=0.25, sparse_search_volume=30).cpu()
     err = (gsc.fused_affinity.cpu() - osc.fused_affinity).abs().max().item()
     print(f"N={counts[-1].item()} oracle {osc.debug['est_num_of_spk']} spk p_hat {osc.debug['p_hat']} | b200 {gsc.debug['est_num_of_spk']} spk "
@@ -150,6 +173,7 @@ def test_diarize_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path,
     oracle.diarize()
     torch.set_rng_state(state)
     diar = ClusteringDiarizer(cfg=cfg_g, speaker_model=weights).to("cuda")
+    diar.keep_affinity = True
     assert diar.diarize() is None
     ro, rg = oracle.results["mono_file"], diar.results["mono_file"]
     # embeddings (all scales) within 1e-3 cosine
@@ -177,25 +201,13 @@ def test_diarize_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path,
     # stage parity of the clustering: the oracle's embeddings through the B200 clustering give the oracle's labels exactly
     from whisper_nemo_b200.longform import LongFormSpeakerClustering
 
-    clus = cfg_g.diarizer.clustering.parameters
-    kw = dict(max_num_speakers=int(clus.max_num_speakers), max_rp_threshold=float(clus.max_rp_threshold),
-              sparse_search_volume=int(clus.sparse_search_volume), chunk_cluster_count=clus.chunk_cluster_count,
-              embeddings_per_chunk=clus.embeddings_per_chunk)
+    kw = _clus_kwargs(cfg_g)
     stage_sc = LongFormSpeakerClustering()
     stage_labels = stage_sc.forward_infer(eo.to(dev), eo_all["timestamps"], eo_all["multiscale_segment_counts"], eo_all["multiscale_weights"], **kw).cpu()
     assert stage_sc.speaker_clustering.debug["n_clusters"] == ro["debug"]["n_clusters"]
     assert stage_sc.speaker_clustering.debug["p_hat"] == ro["debug"]["p_hat"]
     assert best_permutation_agreement(stage_labels.numpy(), ro["labels"]) == 1.0
-    # end to end the discrete decisions can only be required to agree where the oracle's own decision is not a near-tie:
-    # re-run the ORACLE on its embeddings perturbed at the size of the fp16 embedding error (relative 3e-3)
-    from oracle.longform_clustering import LongFormSpeakerClustering as OracleLF
-
-    gen = torch.Generator().manual_seed(0)
-    pert = eo * (1.0 + 3e-3 * torch.randn(eo.shape, generator=gen))
-    state = torch.get_rng_state()
-    relabel = OracleLF().forward_infer(pert, eo_all["timestamps"], eo_all["multiscale_segment_counts"], eo_all["multiscale_weights"], **kw)
-    torch.set_rng_state(state)
-    decisive = len(set(relabel.tolist())) == ro["debug"]["n_clusters"] and best_permutation_agreement(relabel.numpy(), ro["labels"]) == 1.0
+    decisive = _oracle_is_decisive(eo_all, kw, ro["labels"])
     agree = best_permutation_agreement(rg["labels"], ro["labels"]) if len(rg["labels"]) == len(ro["labels"]) else 0.0
     der = rttm_der_between(str(d_o / "pred_rttms" / "mono_file.rttm"), str(d_g / "pred_rttms" / "mono_file.rttm"))
     print(f"   oracle decision {'decisive' if decisive else 'NEAR-TIE (oracle changes its own labels under a 3e-3 perturbation)'}; "
@@ -213,74 +225,71 @@ def test_diarize_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path,
     assert os.path.exists(d_g / "speaker_outputs" / f"subsegments_scale{rg['base_scale_idx']}_cluster.label")
 
 
-def test_ten_minute_telephonic_properties(dev, weights, tmp_path):
-    """BASELINE config #2 at full size (10 min, 2 speakers, telephonic): properties that need no CPU oracle run --
-    two speakers found, windows labelled consistently with the ground-truth turns, and a second run is identical."""
-    from whisper_nemo_b200 import ClusteringDiarizer
-
-    cfg, wav, turns = make_session_cfg(tmp_path, "telephonic", 600.0, 2, seed=2)
-    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights)
-    diar.diarize()
-    r = diar.results["mono_file"]
-    lab1 = r["labels"].copy()
-    ts = r["timestamps"].numpy()
-    mid = ts.mean(1)
+def _truth_labels(timestamps, turns):
+    mid = timestamps.numpy().mean(1)
     truth = np.full(len(mid), -1)
     for a, b, k in turns:
         truth[(mid >= a) & (mid <= b)] = k
-    ok = truth >= 0
-    purity = best_permutation_agreement(lab1[ok], truth[ok])
-    print(f"10 min telephonic: N={len(lab1)} speakers {r['debug']['n_clusters']} p_hat {r['debug']['p_hat']} purity {purity:.4f} stages {diar.stage_ms}")
-    assert r["debug"]["n_clusters"] == 2
-    assert purity >= 0.99
-    diar.run_device()
-    assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
+    return truth
 
 
-def test_one_hour_meeting_properties(dev, weights, tmp_path):
-    """BASELINE config #3 at full size (1 hour, 8 speakers, meeting YAML, default knobs -> long-form path): size-independent
-    properties -- every window labelled, 2..8 speakers, turns sorted and non-overlapping, second run identical."""
+def _end_to_end_pair(tmp_path, oracle_model, weights, domain, duration, n_speakers, seed):
+    """The same synthetic session through the CPU oracle and through the B200 path.  Returns (oracle, diarizer, cfg, turns, dirs)."""
+    from oracle.clustering_diarizer import OracleClusteringDiarizer
     from whisper_nemo_b200 import ClusteringDiarizer
-    from whisper_nemo_b200 import speaker_utils as su
 
-    cfg, wav, turns = make_session_cfg(tmp_path, "meeting", 3600.0, 8, seed=100)
-    diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights)
-    diar.diarize()
-    r = diar.results["mono_file"]
-    lab1 = r["labels"].copy()
-    assert len(lab1) > 10000 and r["fused_affinity"] is None  # long-form: no N x N fused matrix was built
-    k = len(set(lab1.tolist()))
-    ts = r["timestamps"].numpy()
-    mid = ts.mean(1)
-    truth = np.full(len(mid), -1)
-    for a, b, s in turns:
-        truth[(mid >= a) & (mid <= b)] = s
-    ok = truth >= 0
-    agree = best_permutation_agreement(lab1[ok], truth[ok])
-    print(f"1 h meeting: N={len(lab1)} speakers {k} agreement with the 8 true speakers {agree:.4f} stages {diar.stage_ms}")
-    assert 2 <= k <= 8
-    rttm = su.rttm_to_turns(str(tmp_path / "pred_rttms" / "mono_file.rttm"))
-    assert all(e > s for s, e, _ in rttm)
-    assert all(b[0] >= a[1] - 1e-3 for a, b in zip(rttm, rttm[1:]))
-    diar.run_device()
-    assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
-    # stage parity at FULL size: the same (GPU) embeddings through the CPU oracle's long-form clustering -- two dense
-    # eigh(10 000 x 10 000) + k-means(50) on the host, about a minute -- must give the labels of the device path
-    from oracle.longform_clustering import LongFormSpeakerClustering as OracleLF
-
-    e = diar.embs_and_timestamps["mono_file"]
-    clus = cfg.diarizer.clustering.parameters
+    d_o, d_g = tmp_path / "oracle", tmp_path / "b200"
+    cfg_o, _, _ = make_session_cfg(d_o, domain, duration, n_speakers, seed)
+    cfg_g, _, turns = make_session_cfg(d_g, domain, duration, n_speakers, seed)
     torch.set_num_threads(os.cpu_count() or 8)
     state = torch.get_rng_state()
-    want = OracleLF().forward_infer(e["embeddings"].cpu(), e["timestamps"], e["multiscale_segment_counts"], e["multiscale_weights"],
-                                    max_num_speakers=int(clus.max_num_speakers), max_rp_threshold=float(clus.max_rp_threshold),
-                                    sparse_search_volume=int(clus.sparse_search_volume), chunk_cluster_count=clus.chunk_cluster_count,
-                                    embeddings_per_chunk=clus.embeddings_per_chunk)
+    oracle = OracleClusteringDiarizer(cfg_o, oracle_model)
+    oracle.diarize()
     torch.set_rng_state(state)
-    stage_agree = best_permutation_agreement(lab1, want.numpy())
-    print(f"   oracle long-form clustering on the same embeddings: {len(set(want.tolist()))} speakers, label agreement {stage_agree:.5f}")
-    assert len(set(want.tolist())) == k
-    assert stage_agree >= 0.999
+    diar = ClusteringDiarizer(cfg=cfg_g, speaker_model=weights)
+    diar.diarize()
+    return oracle, diar, cfg_g, turns, (d_o, d_g)
+
+
+@pytest.mark.parametrize("name,domain,duration,n_speakers,seed", [
+    ("config #2: 10 min telephonic", "telephonic", 600.0, 2, 2),
+    ("config #4: one 10 min recording of the general batch", "general", 600.0, 3, 1000),
+], ids=["config2_telephonic_10min", "config4_general_10min"])
+def test_fullsize_ten_minutes_matches_oracle(dev, oracle_model, weights, tmp_path, name, domain, duration, n_speakers, seed):
+    """BASELINE configs #2 and #4 (one recording of the batch) at FULL size against the CPU oracle end to end: every window's
+    embedding within 1e-3 cosine, identical speaker count and p-hat, identical labels, 0.00 DER between the two RTTMs."""
+    oracle, diar, cfg, turns, (d_o, d_g) = _end_to_end_pair(tmp_path, oracle_model, weights, domain, duration, n_speakers, seed)
+    eo_all, eg_all = oracle.embs_and_timestamps["mono_file"], diar.embs_and_timestamps["mono_file"]
+    ro, rg = oracle.results["mono_file"], diar.results["mono_file"]
+    assert torch.equal(eo_all["timestamps"], eg_all["timestamps"]) and torch.equal(eo_all["multiscale_segment_counts"], eg_all["multiscale_segment_counts"])
+    cos = torch.nn.functional.cosine_similarity(eo_all["embeddings"], eg_all["embeddings"].cpu(), dim=1)
+    agree = best_permutation_agreement(rg["labels"], ro["labels"])
+    der = rttm_der_between(str(d_o / "pred_rttms" / "mono_file.rttm"), str(d_g / "pred_rttms" / "mono_file.rttm"))
+    truth = _truth_labels(rg["timestamps"], turns)
+    purity = best_permutation_agreement(rg["labels"][truth >= 0], truth[truth >= 0])
+    decisive = _oracle_is_decisive(eo_all, _clus_kwargs(cfg), ro["labels"])
+    print(f"{name}: {len(cos)} windows max(1-cos) {(1 - cos).max().item():.2e}; N={len(ro['labels'])} oracle k {ro['debug']['n_clusters']} p_hat "
+          f"{ro['debug']['p_hat']} | b200 k {rg['debug']['n_clusters']} p_hat {rg['debug']['p_hat']}; label agreement {agree:.5f} DER {der:.5f} "
+          f"purity vs truth {purity:.4f}; oracle {'decisive' if decisive else 'NEAR-TIE'}; oracle CPU s {oracle.stage_seconds} device ms {diar.stage_ms}")
+    assert (1 - cos).max().item() <= 1e-3
+    # stage parity: the oracle's embeddings through the B200 clustering give the oracle's decisions exactly
+    from whisper_nemo_b200.longform import LongFormSpeakerClustering
+
+    stage_sc = LongFormSpeakerClustering()
+    stage = stage_sc.forward_infer(eo_all["embeddings"].to(dev), eo_all["timestamps"], eo_all["multiscale_segment_counts"],
+                                   eo_all["multiscale_weights"], **_clus_kwargs(cfg)).cpu()
+    assert stage_sc.speaker_clustering.debug["n_clusters"] == ro["debug"]["n_clusters"]
+    assert stage_sc.speaker_clustering.debug["p_hat"] == ro["debug"]["p_hat"]
+    assert best_permutation_agreement(stage.numpy(), ro["labels"]) == 1.0
+    if decisive:
+        assert rg["debug"]["n_clusters"] == ro["debug"]["n_clusters"]
+        assert rg["debug"]["p_hat"] == ro["debug"]["p_hat"]
+        assert agree == 1.0
+        assert der == 0.0
+    # a second pass over the same recording is bit-identical
+    lab1 = rg["labels"].copy()
+    diar.run_device()
+    assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
 
 
 def test_multi_recording_manifest_matches_oracle(dev, oracle_model, weights, tmp_path):
@@ -315,8 +324,13 @@ def test_multi_recording_manifest_matches_oracle(dev, oracle_model, weights, tmp
         assert (1 - cos).max().item() <= 1e-3
         assert torch.equal(oracle.embs_and_timestamps[u]["timestamps"], diar.embs_and_timestamps[u]["timestamps"])
         agree = best_permutation_agreement(diar.results[u]["labels"], oracle.results[u]["labels"])
-        print(f"{u}: N={len(oracle.results[u]['labels'])} k oracle {oracle.results[u]['debug']['n_clusters']} b200 {diar.results[u]['debug']['n_clusters']} agreement {agree:.4f}")
-        assert os.path.exists(tmp_path / "b200" / "pred_rttms" / f"{u}.rttm")
+        decisive = _oracle_is_decisive(oracle.embs_and_timestamps[u], _clus_kwargs(diar.cfg), oracle.results[u]["labels"])
+        der = rttm_der_between(str(tmp_path / "oracle" / "pred_rttms" / f"{u}.rttm"), str(tmp_path / "b200" / "pred_rttms" / f"{u}.rttm"))
+        print(f"{u}: N={len(oracle.results[u]['labels'])} k oracle {oracle.results[u]['debug']['n_clusters']} b200 {diar.results[u]['debug']['n_clusters']} "
+              f"agreement {agree:.4f} DER {der:.4f} oracle {'decisive' if decisive else 'NEAR-TIE'}")
+        if decisive:
+            assert diar.results[u]["debug"]["n_clusters"] == oracle.results[u]["debug"]["n_clusters"]
+            assert agree == 1.0 and der == 0.0
 
 
 def test_boundary_errors(dev, weights, tmp_path):
@@ -392,6 +406,9 @@ def test_short_and_ragged_speech_regions_match_oracle(dev, oracle_model, weights
         embeddings_per_chunk=clus.embeddings_per_chunk).cpu()
     assert best_permutation_agreement(got.numpy(), ro["labels"]) == 1.0
     assert os.path.exists(tmp_path / "b200" / "pred_rttms" / "mono_file.rttm")
+    # end to end: asserted where the oracle's own decision survives a perturbation of the size of the fp16 embedding error
+    if len(ro["labels"]) > 1 and _oracle_is_decisive(eo, _clus_kwargs(diar.cfg), ro["labels"]):
+        assert best_permutation_agreement(rg["labels"], ro["labels"]) == 1.0
 
 
 def test_two_hour_recording_longform_properties(dev, weights, tmp_path):
@@ -413,7 +430,7 @@ def test_two_hour_recording_longform_properties(dev, weights, tmp_path):
     ok = truth >= 0
     agree = best_permutation_agreement(lab1[ok], truth[ok])
     print(f"2 h telephonic: N={len(lab1)} speakers {k} agreement with the 6 true speakers {agree:.4f} stages {diar.stage_ms}")
-    assert len(lab1) > 20000 and r["fused_affinity"] is None
+    assert len(lab1) > 20000 and len(diar._last_clusterers["mono_file"].chunk_labels) == 3
     assert 2 <= k <= 8
     assert set(np.unique(lab1).tolist()) == set(range(k))
     diar.run_device()
@@ -436,7 +453,7 @@ def test_longform_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path
     diar = ClusteringDiarizer(cfg=cfg_g, speaker_model=weights)
     diar.diarize()
     ro, rg = oracle.results["mono_file"], diar.results["mono_file"]
-    assert ro["fused_affinity"] is None and rg["fused_affinity"] is None  # both took the long-form branch
+    assert len(oracle.clusterers["mono_file"].chunk_labels) == 3 and len(diar._last_clusterers["mono_file"].chunk_labels) == 3  # both took the long-form branch
     eo = oracle.embs_and_timestamps["mono_file"]
     # stage parity: the oracle's embeddings through the B200 long-form clustering
     from whisper_nemo_b200.longform import LongFormSpeakerClustering
@@ -451,7 +468,10 @@ def test_longform_end_to_end_matches_oracle(dev, oracle_model, weights, tmp_path
     print(f"long-form 5 min: N={len(ro['labels'])} speakers oracle {len(set(ro['labels'].tolist()))} stage {len(set(stage.tolist()))} "
           f"e2e {len(set(rg['labels'].tolist()))}; agreement stage {stage_agree:.4f} end-to-end {e2e_agree:.4f}")
     assert len(set(stage.tolist())) == len(set(ro["labels"].tolist()))
-    assert stage_agree >= 0.999
+    assert stage_agree == 1.0
+    if _oracle_is_decisive(eo, args, ro["labels"]):
+        assert len(set(rg["labels"].tolist())) == len(set(ro["labels"].tolist()))
+        assert e2e_agree == 1.0
 
 
 def test_in_memory_waveform_api_matches_file_path(dev, weights, tmp_path):
@@ -472,3 +492,105 @@ def test_in_memory_waveform_api_matches_file_path(dev, weights, tmp_path):
     for source in (torch.from_numpy(wav), torch.from_numpy(wav).to(dev)):
         mem_ts = ClusteringDiarizer(cfg=cfg, speaker_model=weights).diarize_waveform(source, regions)
         assert mem_ts == file_ts
+
+
+def test_fullsize_meeting_one_hour_matches_oracle(dev, oracle_model, weights, tmp_path):
+    """BASELINE config #3 -- the headline configuration -- at FULL size against the CPU oracle END TO END (about five minutes
+    of host time: 30 355 windows through the fp32 TitaNet-L, two dense eigh(10 000 x 10 000), k-means(50); kept last in the file):
+    1 hour, 8 speakers, diar_infer_meeting.yaml, default knobs -> long-form path (2 chunks of 10 000 over-clustered to 50).
+
+      * every window's embedding within 1e-3 cosine, identical timestamps;
+      * stage parity of the clustering on the ORACLE's embeddings, and end-to-end labels / RTTM against the oracle's;
+      * where labels differ, the yardstick is the oracle itself: its own labels with the spectral eigh done in float64
+        instead of float32 (oracle.switches.SPECTRAL_EIGH_FP64).  The 50-cluster subspace of a chunk has no eigengap, so
+        LAPACK's fp32 rounding decides a handful of k-means assignments; a difference between the two paths counts as a
+        near-tie only if it is of that size, and the RTTM DER must stay <= 1e-3 either way.
+    Set B200D_SKIP_FULLSIZE_1H=1 to skip (development runs)."""
+    if os.environ.get("B200D_SKIP_FULLSIZE_1H") == "1":
+        pytest.skip("B200D_SKIP_FULLSIZE_1H=1")
+    import time
+
+    from oracle import switches
+    from oracle.longform_clustering import LongFormSpeakerClustering as OracleLF
+    from whisper_nemo_b200 import speaker_utils as su
+    from whisper_nemo_b200.longform import LongFormSpeakerClustering
+
+    oracle, diar, cfg, turns, (d_o, d_g) = _end_to_end_pair(tmp_path, oracle_model, weights, "meeting", 3600.0, 8, seed=100)
+    eo_all, eg_all = oracle.embs_and_timestamps["mono_file"], diar.embs_and_timestamps["mono_file"]
+    ro, rg = oracle.results["mono_file"], diar.results["mono_file"]
+    kw = _clus_kwargs(cfg)
+    n = len(ro["labels"])
+    assert torch.equal(eo_all["timestamps"], eg_all["timestamps"]) and torch.equal(eo_all["multiscale_segment_counts"], eg_all["multiscale_segment_counts"])
+    cos = torch.nn.functional.cosine_similarity(eo_all["embeddings"], eg_all["embeddings"].cpu(), dim=1)
+    print(f"1 h meeting: {len(cos)} windows of 6 scales, max(1-cos) {(1 - cos).max().item():.2e} mean {(1 - cos).mean().item():.2e}; "
+          f"N={n}; oracle CPU seconds {oracle.stage_seconds}; device ms {diar.stage_ms}")
+    assert (1 - cos).max().item() <= 1e-3
+    lf_o, lf_g = oracle.clusterers["mono_file"], diar._last_clusterers["mono_file"]
+    assert len(lf_o.chunk_labels) == 2 and len(lf_g.chunk_labels) == 2  # both took the long-form branch
+    # ---- size-independent properties of the product's output
+    k_o, k_g = len(set(ro["labels"].tolist())), len(set(rg["labels"].tolist()))
+    truth = _truth_labels(rg["timestamps"], turns)
+    purity = best_permutation_agreement(rg["labels"][truth >= 0], truth[truth >= 0])
+    rttm = su.rttm_to_turns(str(d_g / "pred_rttms" / "mono_file.rttm"))
+    assert all(e > s for s, e, _ in rttm) and all(b[0] >= a[1] - 1e-3 for a, b in zip(rttm, rttm[1:]))
+    assert set(np.unique(rg["labels"]).tolist()) == set(range(k_g)) and 2 <= k_g <= 8
+    lab1 = rg["labels"].copy()
+    diar.run_device()
+    assert np.array_equal(diar.results["mono_file"]["labels"], lab1)
+    # ---- the yardstick: the oracle against itself with the spectral eigh in float64
+    t0 = time.perf_counter()
+    switches.SPECTRAL_EIGH_FP64 = True
+    try:
+        state = torch.get_rng_state()
+        probe_lf = OracleLF()
+        probe = probe_lf.forward_infer(eo_all["embeddings"], eo_all["timestamps"], eo_all["multiscale_segment_counts"], eo_all["multiscale_weights"], **kw)
+        torch.set_rng_state(state)
+    finally:
+        switches.SPECTRAL_EIGH_FP64 = False
+    probe_diff = int(round((1.0 - best_permutation_agreement(probe.numpy(), ro["labels"])) * n))
+    probe_chunk = [int(round((1.0 - best_permutation_agreement(probe_lf.chunk_labels[w][1].numpy(), lf_o.chunk_labels[w][1].numpy())) * len(lf_o.chunk_labels[w][1])))
+                   for w in sorted(lf_o.chunk_labels)]
+    print(f"   oracle vs ITSELF with float64 eigh: {probe_diff} of {n} final labels differ; per-chunk over-clustering labels differing {probe_chunk} "
+          f"({time.perf_counter() - t0:.0f} s)")
+    # ---- stage parity: the oracle's embeddings through the B200 long-form clustering
+    stage_lf = LongFormSpeakerClustering()
+    stage = stage_lf.forward_infer(eo_all["embeddings"].to(dev), eo_all["timestamps"], eo_all["multiscale_segment_counts"],
+                                   eo_all["multiscale_weights"], **kw).cpu().numpy()
+    stage_chunk = [int(round((1.0 - best_permutation_agreement(stage_lf.chunk_labels[w][1].numpy(), lf_o.chunk_labels[w][1].numpy())) * len(lf_o.chunk_labels[w][1])))
+                   for w in sorted(lf_o.chunk_labels)]
+    stage_diff_idx = _differing(stage, ro["labels"])
+    e2e_diff_idx = _differing(rg["labels"], ro["labels"])
+    der = rttm_der_between(str(d_o / "pred_rttms" / "mono_file.rttm"), str(d_g / "pred_rttms" / "mono_file.rttm"))
+    print(f"   stage (oracle embeddings -> B200 clustering): {len(stage_diff_idx)} of {n} labels differ {stage_diff_idx[:20].tolist()}; per-chunk {stage_chunk}")
+    print(f"   end to end: speakers oracle {k_o} b200 {k_g}; {len(e2e_diff_idx)} of {n} labels differ {e2e_diff_idx[:20].tolist()}; DER between the RTTMs {der:.6f}; "
+          f"purity vs the 8 true speakers {purity:.4f}")
+    dump = os.environ.get("B200D_DUMP_DIR")
+    if dump:
+        os.makedirs(dump, exist_ok=True)
+        eo = eo_all["embeddings"].numpy()
+        np.savez_compressed(os.path.join(dump, "meeting_1h_parity.npz"), oracle_embeddings=eo,
+                            gpu_minus_oracle_f16=(eg_all["embeddings"].cpu().numpy() - eo).astype(np.float16), timestamps=eo_all["timestamps"].numpy(),
+                            counts=eo_all["multiscale_segment_counts"].numpy(), weights=eo_all["multiscale_weights"].numpy(),
+                            oracle_labels=ro["labels"], gpu_labels=rg["labels"], stage_labels=stage, probe_labels=probe.numpy(),
+                            **{f"oracle_chunk{w}": lf_o.chunk_labels[w][1].numpy() for w in lf_o.chunk_labels},
+                            **{f"gpu_chunk{w}": lf_g.chunk_labels[w][1].numpy() for w in lf_g.chunk_labels},
+                            **{f"stage_chunk{w}": stage_lf.chunk_labels[w][1].numpy() for w in stage_lf.chunk_labels})
+    assert len(set(stage.tolist())) == k_o and k_g == k_o
+    near_tie_budget = max(3 * probe_diff, 2)  # what fp32-vs-fp64 rounding moves inside the oracle itself (times a small factor), at least two windows
+    assert len(stage_diff_idx) <= near_tie_budget, (len(stage_diff_idx), probe_diff)
+    assert len(e2e_diff_idx) <= max(near_tie_budget, int(1e-3 * n))
+    assert der <= 1e-3
+
+
+def _differing(a, b):
+    """Indices where labeling a differs from b under the best one-to-one mapping of a's labels onto b's."""
+    from scipy.optimize import linear_sum_assignment
+
+    a, b = np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64)
+    k = max(int(a.max()), int(b.max())) + 1
+    cont = np.zeros((k, k), dtype=np.int64)
+    np.add.at(cont, (a, b), 1)
+    r, c = linear_sum_assignment(-cont)
+    mapping = np.zeros(k, dtype=np.int64)
+    mapping[r] = c
+    return np.nonzero(mapping[a] != b)[0]

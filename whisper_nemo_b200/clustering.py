@@ -574,6 +574,7 @@ class SpeakerClustering:
         self.embeddings_in_scales: List[torch.Tensor] = []
         self.timestamps_in_scales: List[torch.Tensor] = []
         self.debug = {}
+        self.keep_affinity = False  # parity tests set this to read the fused N x N matrix back (13 GB for a 4-hour recording)
         self.fused_affinity: Optional[torch.Tensor] = None
 
     def forward_unit_infer(self, mat: torch.Tensor, oracle_num_speakers: int = -1, max_num_speakers: int = 8,
@@ -616,7 +617,7 @@ class SpeakerClustering:
         if oracle_num_speakers > 0:
             max_num_speakers = oracle_num_speakers
         mat = getMultiScaleCosAffinityMatrix(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales, scale_mapping)
-        self.fused_affinity = mat
+        self.fused_affinity = mat if self.keep_affinity else None
         return self.forward_unit_infer(mat=mat, oracle_num_speakers=oracle_num_speakers, max_rp_threshold=max_rp_threshold,
                                        max_num_speakers=max_num_speakers, sparse_search_volume=sparse_search_volume,
                                        est_num_of_spk_enhanced=est_num_of_spk_enhanced, fixed_thres=fixed_thres)

@@ -93,6 +93,8 @@ class ClusteringDiarizer:
         self._embed_streams: List[torch.cuda.Stream] = []
         self._cluster_streams: List[torch.cuda.Stream] = []
         self._speaker_model = self._init_speaker_model(speaker_model)
+        self.keep_affinity = bool(int(os.environ.get("B200D_KEEP_AFFINITY", "0")))  # results[...]["fused_affinity"] (debug / parity tests)
+        self._last_clusterers: Dict[str, object] = {}
         self.stage_ms: Dict[str, float] = {}
         self.results: Dict[str, dict] = {}
         self.embs_and_timestamps: Dict[str, dict] = {}
@@ -275,6 +277,7 @@ class ClusteringDiarizer:
         else:
             num_speakers = -1
         sc = LongFormSpeakerClustering(shard_chunks=self.shard_windows, chunk_streams=chunk_streams)
+        sc.speaker_clustering.keep_affinity = self.keep_affinity
         labels = sc.forward_infer(
             embeddings_in_scales=e["embeddings"],
             timestamps_in_scales=e["timestamps"],
@@ -357,6 +360,7 @@ class ClusteringDiarizer:
             lab = labels.cpu().numpy()
             labels_host[uniq_id] = lab
             base_scale_idx = int(self.embs_and_timestamps[uniq_id]["multiscale_segment_counts"].shape[0]) - 1
+            self._last_clusterers[uniq_id] = sc
             self.results[uniq_id] = {"labels": lab, "timestamps": sc.timestamps_in_scales[base_scale_idx], "base_scale_idx": base_scale_idx,
                                      "debug": dict(sc.speaker_clustering.debug), "fused_affinity": sc.speaker_clustering.fused_affinity}
         if timers:

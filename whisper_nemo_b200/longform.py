@@ -138,6 +138,7 @@ class LongFormSpeakerClustering:
         self.speaker_clustering = SpeakerClustering()
         self.embeddings_in_scales: List[torch.Tensor] = []
         self.timestamps_in_scales: List[torch.Tensor] = []
+        self.chunk_labels = {}  # long-form path: chunk index -> (first window, int64 over-clustering labels on the host)
 
     @staticmethod
     def get_div_ceil_count(numer: int, denomin: int) -> int:
@@ -239,6 +240,7 @@ class LongFormSpeakerClustering:
             y_host = Y_part.cpu()
             min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
             class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
+            self.chunk_labels[win_index] = (offset_index, y_host)
             return self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index, y_host)
 
         mine = [w for w in range(n_chunks) if w % world == rank]
