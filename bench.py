@@ -264,9 +264,9 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _cabi.launch_count
+    launches0 = _cabi.total_launches()
     dev_ms, e2e_ms = _time_steps(diar, wav_dev, args.steps, barrier, torch)
-    launches = (_cabi.launch_count - launches0) // 2  # the two timed loops run the same launches
+    launches = (_cabi.total_launches() - launches0) // 2  # the two timed loops run the same launches
     clocks = sampler.stop() if rank == 0 else None
     dev_ms, e2e_ms = all_max([dev_ms, e2e_ms])
     labels_main = {u: r["labels"].copy() for u, r in diar.results.items()}

@@ -69,6 +69,28 @@ int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, c
                     const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant,
                     void* out_f16, int32_t ldo, float* out_f32, void* stream);
 
+/* The same featurizer with every 10-ms frame computed ONCE per recording instead of once per window (windows of all scales
+ * overlap: upstream recomputes each STFT frame ~10 times).  A frame in the interior of a window depends only on where its 400
+ * samples lie, not on the window, so:
+ *   b200d_mel_stream         log(mel + 2^-24) of the frames of `n_streams` STREAMS: stream s holds the frames centred on samples
+ *                            stream_start[s] + g * 160, g = 0 .. stream_off[s+1] - stream_off[s] - 1, as rows stream_off[s] + g of
+ *                            logmel float32 [total_rows][80].  stream_off[] are multiples of 32 (pad each stream's frame count;
+ *                            padding rows are computed from whatever samples lie there and never used).  Samples outside
+ *                            [0, n_wav) read as 0.  stream_start int64 [n_streams], stream_off int32 [n_streams + 1] (device).
+ *   b200d_featurize_windows  b200d_featurize with seg_row0 int32 [n_seg]: the row in `logmel` of the stream frame centred on the
+ *                            segment's first sample (the host plans streams so that every full-length window starts on a frame of
+ *                            one), or < 0.  Segments with seg_row0 >= 0 and seg_len == fixed_len copy their interior frames
+ *                            (t*160 - 201 >= 0 and t*160 + 200 <= fixed_len) from the stream and compute only the two frames at
+ *                            each end (reflect / zero padding, first-sample pre-emphasis); all others compute every frame.
+ *                            logmel == NULL and seg_row0 == NULL together: every segment takes the generic path (== b200d_featurize). */
+int b200d_mel_stream(const float* wav, int64_t n_wav, const int64_t* stream_start, const int32_t* stream_off, int32_t n_streams,
+                     int32_t total_rows, const int32_t* fb_start, const int32_t* fb_off, const float* fb_w, int32_t fb_nnz,
+                     const float* window, float* logmel, void* stream);
+int b200d_featurize_windows(const float* wav, int64_t n_wav, const float* logmel, const int32_t* seg_start, const int32_t* seg_len,
+                            const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off,
+                            const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant, void* out_f16, int32_t ldo,
+                            float* out_f32, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * TitaNet-L building blocks (nemo/collections/asr/parts/submodules/jasper.py JasperBlock,
  * MaskedConv1d, SqueezeExcite; modules/conv_asr.py ConvASREncoder, SpeakerDecoder;
@@ -122,16 +144,17 @@ typedef struct b200d_gemm_epilogue {
   int32_t ldx;
   void* vt;               /* __nv_bfloat16 [N][ldvt] */
   int32_t ldvt;
+  int32_t flags;          /* B200D_GEMM_* bits, 0 = default kernel choice */
 } b200d_gemm_epilogue;
+
+/* Kernel choice is a PER-CALL property (no process-wide state): large GEMMs run on a cluster-launched CTA-pair kernel
+ * (tcgen05 cta_group::2).  On B200 / driver 580.159 that kernel deadlocked the device when it shared the GPU with a
+ * register-heavy kernel of ANOTHER stream (tools/concurrency_check.py), so a caller that keeps several streams busy at
+ * once passes B200D_GEMM_NO_PAIR on the calls made inside that region and every such GEMM takes the 1-CTA kernel. */
+#define B200D_GEMM_NO_PAIR 1
 
 int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K,
                    void* out, int32_t ldo, const b200d_gemm_epilogue* epi, void* stream);
-/* Large GEMMs run on a cluster-launched CTA-pair kernel (tcgen05 cta_group::2) that must not share the device with
- * kernels of other streams (observed device deadlock against a register-heavy kernel on B200 / driver 580.159).  A host
- * that is about to use several streams calls this with 0 (every GEMM then takes the 1-CTA kernel) and restores the
- * returned previous value afterwards.  Process-wide; returns the previous setting.                                */
-int b200d_gemm_set_pair_kernel(int32_t enable);
-
 /* SqueezeExcite = b200d_time_stats(with_std=0) -> b200d_gemm_f16(fc.0, BIAS_RELU with zero bias)
  * -> b200d_gemm_f16(fc.2, SIGMOID_F32) -> gate float32 [n_seg][C].                                 */
 
@@ -151,6 +174,62 @@ int b200d_time_stats(const void* x, int32_t n_seg, int32_t T, int32_t C, int32_t
 /* Attentive statistics pooling: alpha = softmax_t(e), mu = sum alpha x, sg = sqrt(clamp(sum alpha (x-mu)^2, 1e-10)).
  *  x, e __half [n_seg*T][C];  out16 __half [n_seg][2*C] = [mu | sg]                              */
 int b200d_attn_pool(const void* x, const void* e, int32_t n_seg, int32_t T, int32_t C, void* out16, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * TitaNet-L as two composite calls (label_models.EncDecSpeakerLabelModel.forward: preprocessor -> ConvASREncoder ->
+ * SpeakerDecoder; upstream's `_extract_embeddings` dataloader loop calls it once per batch of 64 windows).
+ *
+ * b200d_titanet_pack_weights (HOST, one-time): upstream's state_dict as parallel arrays -- names[i] (NeMo's keys:
+ *   `encoder.encoder.<b>.mconv.<j>.conv.weight`, `...mconv.<j>.{weight,bias,running_mean,running_var}`, `...mconv.<j>.fc.{0,2}.weight`,
+ *   `encoder.encoder.<b>.res.0.{0.conv.weight,1.*}`, `decoder._pooling.attention_layer.{0.conv_layer.*,0.bn.*,2.*}`,
+ *   `decoder.emb_layers.0.{0.*,1.*}`; optional `preprocessor.featurizer.{fb,window}`, computed when absent), data_host[i] float32
+ *   host arrays in upstream's layouts, numel[i] their element counts (all shapes follow from them).  Writes the folded /
+ *   padded / fp16 operands into packed_host (position independent: copy it to the device as is, 256-byte aligned) and the
+ *   byte offset of every operand into *desc.  packed_host == NULL: only fills *desc (desc->packed_bytes is the size needed).
+ * b200d_titanet_forward: embeddings of n_seg windows that all share fixed_len (see b200d_featurize for wav / seg_* / variant,
+ *   b200d_featurize_windows for logmel / seg_row0, both may be NULL).  Windows are processed in groups that fit `ws`
+ *   (b200d_titanet_workspace_bytes(desc, max_frames, max_segs) holds groups of max_segs windows / max_frames frames; any
+ *   size that holds one window works).  emb_out float32 [n_seg][ld_emb], first desc->emb columns written.  flags: B200D_GEMM_*.
+ * b200d_titanet_mel_stream: b200d_mel_stream with the filterbank / window tables of the packed blob.
+ * ------------------------------------------------------------------------------------------ */
+#define B200D_TITANET_MAX_BLOCKS 8
+typedef struct b200d_titanet_desc {
+  int32_t n_blocks, feat_in, feat_pad, enc_out, attn, emb, emb_pad, fb_nnz;
+  struct {
+    int32_t cin, cin_pad, cout, repeat, ksize, residual, se_hidden, pad_;
+    int64_t dw[3];    /* float32 [ksize][cin_pad] tap-major, -1 when ksize == 1 (folded into w) */
+    int64_t w[3];     /* __half [cout][cin_pad], BatchNorm scale folded in */
+    int64_t bias[3];  /* float32 [cout], BatchNorm shift */
+    int64_t se_w1, se_w2, res_w, res_bias;
+  } block[B200D_TITANET_MAX_BLOCKS];
+  int64_t tdnn_wx, tdnn_wctx, tdnn_b, tdnn_scale, tdnn_shift, attn_w2, attn_b2, emb_w, emb_b, zeros;
+  int64_t fb_start, fb_off, fb_w, window;
+  int64_t packed_bytes;
+} b200d_titanet_desc;
+
+int b200d_titanet_pack_weights(int32_t n_tensors, const char* const* names, const float* const* data_host, const int64_t* numel,
+                               b200d_titanet_desc* desc, void* packed_host, size_t packed_bytes);
+size_t b200d_titanet_workspace_bytes(const b200d_titanet_desc* desc, int32_t max_frames, int32_t max_segs);
+int b200d_titanet_forward(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav, const float* logmel,
+                          const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len,
+                          int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes, void* stream);
+int b200d_titanet_mel_stream(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav,
+                             const int64_t* stream_start, const int32_t* stream_off, int32_t n_streams, int32_t total_rows, float* logmel,
+                             void* stream);
+
+/* Per-kernel device time INSIDE the composite entry points (b200d_titanet_forward, b200d_eig_bottomk): between start and stop
+ * every kernel they launch is bracketed by a cudaEvent pair on the caller's stream.  A measurement aid (bench.py's roofline
+ * leg); adds event overhead, never active in a timed region.  stop synchronises the device, fills up to `capacity` spans and
+ * sets *n_spans to the number recorded.  work = 2 M N K for GEMM launches, else 0.                                          */
+typedef struct b200d_profile_span {
+  char name[48];
+  float ms;
+  double work;
+} b200d_profile_span;
+/* Kernels launched so far from inside composite entry points (process-wide counter; callers count their own fine-grained calls). */
+int64_t b200d_launch_count(void);
+int b200d_profile_start(void);
+int b200d_profile_stop(b200d_profile_span* spans, int32_t capacity, int32_t* n_spans);
 
 /* ------------------------------------------------------------------------------------------
  * Affinity (nemo/collections/asr/parts/utils/offline_clustering.py):
@@ -253,6 +332,33 @@ int b200d_spmm_cheb(const int32_t* rowptr, const uint32_t* colw, int32_t n, int3
  * ws: at least ceil(n / 256) * 64 floats (b200d_gram_workspace_bytes(n, b) is always enough).              */
 int b200d_resid_norms(const float* w, const float* x, const float* theta, int32_t n, int32_t b, int32_t ld, float* out,
                       void* ws, size_t ws_bytes, void* stream);
+
+/* The whole solver as ONE call (SpectralClustering.getSpectralEmbeddings: upstream's eigh(N x N) + k columns kept): the k lowest
+ * eigenvectors of L = diag(deg) - A for A = b200d_topp_binarize's output, by Chebyshev-filtered subspace iteration over the
+ * kernels above (B200D_EPI_CHEB GEMMs, or b200d_spmm_cheb when the graph was built from p neighbours with 2 p <=
+ * sparse_max_row_nnz or 2 p <= sparse_max_density * n; p <= 0: always dense).
+ *  x     float32 [n][b], b = b200d_eig_bottomk_block(k) (32 for k <= 24, 64 for k <= 56): IN a random start block (the caller's
+ *        RNG, e.g. torch.randn under a fixed seed), OUT orthonormal Ritz vectors, ascending; columns 0..k-1 span the answer.
+ *  n >= 2 b.  Synchronises `stream` once per outer iteration (the polynomial degree and the stopping test are host decisions
+ *  on 2 b floats read back).  opt == NULL: defaults; stats may be NULL.                                                     */
+#define B200D_EIG_HISTORY 40
+typedef struct b200d_eig_options {
+  double tol;                /* stop when max_j<k ||L x_j - theta_j x_j|| <= tol * (2 max deg); default 2e-6 */
+  int32_t max_outer;         /* default 40 */
+  int32_t gemm_flags;        /* B200D_GEMM_* for the products */
+  int32_t sparse_max_row_nnz;   /* default 32 */
+  int32_t pad_;
+  double sparse_max_density;    /* default 1/64 */
+} b200d_eig_options;
+typedef struct b200d_eig_stats {
+  int32_t block, outer, gemms, converged, sparse;
+  float max_resid;
+  float history[B200D_EIG_HISTORY];  /* relative residual after each outer iteration */
+} b200d_eig_stats;
+int32_t b200d_eig_bottomk_block(int32_t k);
+size_t b200d_eig_bottomk_workspace_bytes(int32_t n, int32_t k, int32_t p, const b200d_eig_options* opt);
+int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* deg, int32_t n, int32_t k, int32_t p, float* x, int32_t ldx,
+                      const b200d_eig_options* opt, b200d_eig_stats* stats, void* ws, size_t ws_bytes, void* stream);
 
 /* k-means of kmeans_torch / kmeans_plusplus_torch with the RNG draws supplied by the host
  * (torch.manual_seed(0) stream: first-centre index, rand(30) per further centre, fallback randints).

@@ -93,3 +93,81 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_titanet_pack_weights_is_a_host_function_and_matches_the_python_packing():
+    """b200d_titanet_pack_weights (C++, host) against titanet.pack_weights (the per-operand Python packing the step-by-step
+    reference orchestration uses): every folded / padded / fp16-converted operand bit for bit -- except the embedding bias,
+    whose 6144-term double-precision dot product is summed in a different order (compared to 1e-6 relative)."""
+    import numpy as np
+    import torch
+
+    from whisper_nemo_b200 import checkpoint
+    from whisper_nemo_b200 import titanet as tn
+
+    sd = checkpoint.seeded()
+    desc, blob = tn.pack_weights_cabi(sd, device="cpu")
+    pk = tn.pack_weights(sd, device="cpu")
+    raw = blob.numpy()
+
+    def region(off, like):
+        n = like.numel() * like.element_size()
+        return torch.from_numpy(raw[off : off + n].copy()).view(like.dtype).view(like.shape)
+
+    assert desc.n_blocks == 5 and desc.feat_in == 80 and desc.feat_pad == 128 and desc.enc_out == 3072 and desc.attn == 128 and desc.emb == 192
+    assert [desc.block[i].ksize for i in range(5)] == [3, 7, 11, 15, 1] and [desc.block[i].repeat for i in range(5)] == [1, 3, 3, 3, 1]
+    for i, blk in enumerate(pk.blocks):
+        d = desc.block[i]
+        for r, sb in enumerate(blk.subs):
+            if sb.dw is None:
+                assert d.dw[r] == -1
+            else:
+                assert torch.equal(region(d.dw[r], sb.dw), sb.dw), (i, r, "dw")
+            assert torch.equal(region(d.w[r], sb.w).view(torch.int16), sb.w.view(torch.int16)), (i, r, "w")
+            assert torch.equal(region(d.bias[r], sb.bias), sb.bias), (i, r, "bias")
+        assert torch.equal(region(d.se_w1, blk.se_w1).view(torch.int16), blk.se_w1.view(torch.int16))
+        assert torch.equal(region(d.se_w2, blk.se_w2).view(torch.int16), blk.se_w2.view(torch.int16))
+        if blk.res_w is not None:
+            assert torch.equal(region(d.res_w, blk.res_w).view(torch.int16), blk.res_w.view(torch.int16))
+            assert torch.equal(region(d.res_bias, blk.res_bias), blk.res_bias)
+        else:
+            assert d.residual == 0
+    for name in ("tdnn_wx", "tdnn_wctx", "attn_w2", "emb_w"):
+        a, b = region(getattr(desc, name), getattr(pk, name)), getattr(pk, name)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), name
+    for name in ("tdnn_b", "tdnn_scale", "tdnn_shift", "attn_b2", "fb_start", "fb_off", "window"):
+        assert torch.equal(region(getattr(desc, name), getattr(pk, name)), getattr(pk, name)), name
+    assert torch.equal(region(desc.fb_w, pk.fb_w), pk.fb_w) and desc.fb_nnz == pk.fb_w.numel()
+    eb = region(desc.emb_b, pk.emb_b)
+    assert torch.allclose(eb, pk.emb_b, rtol=1e-6, atol=1e-9) and (eb != pk.emb_b).float().mean().item() < 0.2
+    # without the preprocessor buffers in the state_dict the library computes the slaney filterbank / hann window itself
+    lib = tn._cabi.load()
+    names = [k for k in sd if sd[k].dtype.is_floating_point]
+    keep = [sd[k].float().contiguous() for k in names]
+    c_names = (ctypes.c_char_p * len(names))(*[k.encode() for k in names])
+    c_data = (ctypes.c_void_p * len(names))(*[t.data_ptr() for t in keep])
+    c_numel = (ctypes.c_int64 * len(names))(*[t.numel() for t in keep])
+    d2 = tn._cabi.TitaNetDesc()
+    assert lib.b200d_titanet_pack_weights(len(names), c_names, c_data, c_numel, ctypes.byref(d2), None, 0) == 0
+    blob2 = torch.empty(int(d2.packed_bytes), dtype=torch.uint8)
+    assert lib.b200d_titanet_pack_weights(len(names), c_names, c_data, c_numel, ctypes.byref(d2), blob2.data_ptr(), blob2.numel()) == 0
+    raw2 = blob2.numpy()
+    own_fb = np.frombuffer(raw2[d2.fb_w : d2.fb_w + 4 * d2.fb_nnz].tobytes(), dtype=np.float32)
+    own_win = np.frombuffer(raw2[d2.window : d2.window + 1600].tobytes(), dtype=np.float32)
+    assert d2.fb_nnz == desc.fb_nnz
+    assert np.abs(own_fb - pk.fb_w.numpy()).max() <= 2e-9 and np.abs(own_win - pk.window.numpy()).max() <= 1e-7
+    assert lib.b200d_titanet_workspace_bytes(ctypes.byref(desc), 131072, 4096) > 131072 * 20000
+    # errors: a truncated state_dict is refused with a message
+    assert lib.b200d_titanet_pack_weights(3, c_names, c_data, c_numel, ctypes.byref(d2), None, 0) < 0
+    assert b"b200d_titanet_pack_weights" in lib.b200d_last_error()
+
+
+def test_eig_bottomk_queries():
+    from whisper_nemo_b200 import _cabi
+
+    lib = _cabi.load()
+    assert [lib.b200d_eig_bottomk_block(k) for k in (1, 8, 24, 25, 50, 56, 57)] == [32, 32, 32, 64, 64, 64, 0]
+    dense = lib.b200d_eig_bottomk_workspace_bytes(10000, 50, 684, None)
+    sparse = lib.b200d_eig_bottomk_workspace_bytes(10000, 50, 11, None)
+    assert dense > 4 * 10000 * 64 * 4 + 2 * 192 * 10000 * 2 and 4 * 10000 * 64 * 4 < sparse < dense  # CSR lists (22 per row) instead of two bf16 operand buffers
+    assert lib.b200d_eig_bottomk_workspace_bytes(10000, 60, 0, None) == 0

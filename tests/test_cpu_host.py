@@ -255,3 +255,69 @@ def test_window_sharding_all_gather_gloo_world2(tmp_path):
 
     mp.spawn(_gloo_worker, args=(2, 29517, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def _random_regions(rng, n=300, path="/x/rec a.wav", uniq="rec a"):
+    regs, t = [], 0.0
+    for _ in range(n):
+        d = float(round(rng.uniform(0.03, 9), 5))
+        t = float(round(t + rng.uniform(0, 1), 5))
+        regs.append({"audio_filepath": path, "offset": t, "duration": d, "label": "UNK", "uniq_id": uniq})
+        t += d
+    return regs
+
+
+def test_vectorised_subsegments_equal_the_loop(tmp_path):
+    """subsegment_arrays / write_subsegments_manifest (the product's prepare path) against the per-region loop that mirrors
+    upstream: identical float64 starts and durations, byte-identical subsegments_scale<k>.json."""
+    regs = _random_regions(np.random.default_rng(1))
+    man = tmp_path / "seg.json"
+    man.write_text("".join(json.dumps(r) + "\n" for r in regs))
+    for w, s in SCALES:
+        ref = su.segments_manifest_to_subsegments_manifest(str(man), str(tmp_path / "a.json"), w, s)
+        region, start, dur = su.subsegment_arrays([r["offset"] for r in regs], [r["duration"] for r in regs], w, s)
+        su.write_subsegments_manifest(str(tmp_path / "b.json"), regs, region, start, dur)
+        assert (tmp_path / "a.json").read_text() == (tmp_path / "b.json").read_text()
+        assert [e["offset"] for e in ref] == start.tolist() and [e["duration"] for e in ref] == dur.tolist()
+
+
+def test_window_plan_and_mel_streams(tmp_path):
+    """ClusteringDiarizer._plan_windows (host only): sample ranges, fixed_seq batch lengths and float32 stamps equal the
+    entry-by-entry rule of the dataset / collate; every full-length window starts on a frame of its log-mel stream and
+    the stream holds all of its interior frames."""
+    from whisper_nemo_b200 import titanet as tn
+    from whisper_nemo_b200.diarizer import ClusteringDiarizer
+
+    sr, total = 16000, 16000 * 1400
+    regs = _random_regions(np.random.default_rng(5), n=260)
+    regs = [r for r in regs if r["offset"] + r["duration"] < total / sr - 1]
+    diar = object.__new__(ClusteringDiarizer)  # host-side planning needs no device
+    diar.sample_rate, diar.batch_size = sr, 64
+    diar.AUDIO_RTTM_MAP = {"rec a": {}}
+    diar._wav_offset = {"rec a": (1000, total)}
+    diar.multiscale_args_dict = su.parse_scale_configs([1.5, 1.25, 1.0, 0.75, 0.5], [0.75, 0.625, 0.5, 0.375, 0.25], [1, 1, 1, 1, 1])
+    diar._plan_windows(regs, write_manifests=False)
+    man = tmp_path / "seg.json"
+    man.write_text("".join(json.dumps(r) + "\n" for r in regs))
+    for scale_idx, (w, s) in diar.multiscale_args_dict["scale_dict"].items():
+        entries = su.segments_manifest_to_subsegments_manifest(str(man), str(tmp_path / "s.json"), w, s)
+        plan = diar._scales[scale_idx]
+        start = [1000 + int(e["offset"] * sr) for e in entries]
+        length = [min(int(e["duration"] * sr), total - int(e["offset"] * sr)) for e in entries]
+        fixed = [max(length[b0 : b0 + 64]) for b0 in range(0, len(length), 64) for _ in length[b0 : b0 + 64]]
+        assert plan["start"].tolist() == start and plan["len"].tolist() == length and plan["fixed"].tolist() == fixed
+        stamps = torch.tensor([[e["offset"], e["offset"] + e["duration"]] for e in entries])
+        assert torch.equal(plan["stamps"]["rec a"], stamps)
+    stream_start, stream_off = diar._streams
+    assert np.all(stream_off % tn.STREAM_PAD == 0) and np.all(np.diff(stream_off) > 0)
+    n_full = n_rows = 0
+    for plan in diar._scales.values():
+        full = plan["len"] == plan["fixed"]
+        assert np.array_equal(plan["row0"] >= 0, full)  # exactly the windows that fill their tiled-up length sit on a stream
+        r0, st, fx = plan["row0"][full], plan["start"][full], plan["fixed"][full]
+        sid = np.searchsorted(stream_off, r0, side="right") - 1
+        assert np.array_equal(stream_start[sid] + (r0 - stream_off[sid]) * tn.HOP, st)  # frame row0 is centred on the first sample
+        assert np.all(r0 + (fx - 200) // tn.HOP < stream_off[sid + 1])                   # last interior frame inside the stream
+        n_full += int(full.sum())
+        n_rows += int((fx // tn.HOP + 1).sum())
+    assert n_full > 0 and stream_off[-1] < 0.45 * n_rows  # telephonic scales: two grid phases per region instead of ~10 recomputations

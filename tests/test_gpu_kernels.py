@@ -382,3 +382,44 @@ def test_gemm_epilogues_match_torch(dev, M, N, K):
         tn.gemm(A, W, out, _cabi.EPI_TDNN, scale=scale, shift=shift, rowvec=rb, rows_per_seg=T)
         want = torch.tanh(scale * torch.relu(ref + rb.repeat_interleave(T, 0)[:M]) + shift)
         assert (out.float() - want).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("n,k,p", [(2399, 4, 60), (4000, 50, 80), (6000, 50, 11)])
+def test_eig_bottomk_composite_equals_the_stepwise_iteration(dev, n, k, p):
+    """b200d_eig_bottomk (the whole Chebyshev-filtered subspace iteration inside the library) reproduces the same iteration
+    driven call by call from Python bit for bit: same kernels, same host decisions (polynomial degree, stopping test)."""
+    from whisper_nemo_b200 import clustering as cl
+
+    mat, _ = _clustered_graph(n, k, p, seed=n + k)
+    a16, deg = cl.getAffinityGraphMat(mat.to(dev), p)
+    got = cl.bottom_eigvecs(a16, deg, k, p=p)
+    st = cl.SpectralStats()
+    st.__dict__.update(cl.last_spectral_stats.__dict__)
+    want = cl.bottom_eigvecs(a16, deg, k, p=p, stepwise=True)
+    st2 = cl.last_spectral_stats
+    torch.cuda.synchronize()
+    print(f"eig_bottomk n={n} k={k} p={p}: {st.method} outer {st.outer} gemms {st.gemms} resid {st.max_resid:.2e} | stepwise outer {st2.outer} gemms {st2.gemms}")
+    assert st.converged and (st.method, st.outer, st.gemms) == (st2.method, st2.outer, st2.gemms)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("fixed_len,n,max_frames", [(24000, 12, 8192), (8000, 300, 4096), (48000, 9, 1024), (20000, 7, 131072)])
+def test_titanet_forward_composite_equals_the_stepwise_orchestration(dev, weights, fixed_len, n, max_frames):
+    """b200d_titanet_forward (featurizer + encoder + decoder launched from C++ on the library's packed blob, windows processed
+    in groups that fit the workspace) against the step-by-step Python orchestration over the fine-grained entry points and
+    the Python-packed operands: identical embeddings."""
+    from tools import workload as synth
+    from whisper_nemo_b200 import titanet as tn
+
+    wav, _ = synth.synth_recording(60.0, 3, seed=7)
+    wav_d = torch.from_numpy(wav).to(dev)
+    net = tn.TitaNetB200(weights, dev, max_frames=max_frames)
+    starts = torch.tensor([500 + 2960 * i for i in range(n)], dtype=torch.int32, device=dev)
+    lens = torch.full((n,), fixed_len, dtype=torch.int32, device=dev)
+    lens[-1] = fixed_len // 3
+    got = net.embed_segments(wav_d, starts, lens, fixed_len)
+    taps = {}
+    want = net.embed_segments(wav_d, starts, lens, fixed_len, taps=taps)
+    torch.cuda.synchronize()
+    assert "encoder" in taps
+    assert torch.equal(got, want)

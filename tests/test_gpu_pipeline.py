@@ -81,6 +81,47 @@ def test_featurizer_matches_oracle(dev, oracle_model, weights, fixed_len, lens, 
 
 
 @pytest.mark.parametrize("variant", ["classic", "later"])
+@pytest.mark.parametrize("window_s,shift_s", [(1.5, 0.75), (1.25, 0.625), (0.5, 0.25), (3.0, 1.5)])
+def test_featurizer_once_per_recording_frames(dev, oracle_model, weights, window_s, shift_s, variant, monkeypatch):
+    """The stream path (every 10-ms frame computed once per recording, windows gather their interior frames and compute
+    only their 2 + 2 edge frames) against the generic per-window path and against the oracle: two speech regions at
+    odd millisecond offsets, half-hop shifts (two grid phases), the last window of each region short (tiled, no stream)."""
+    from oracle.clustering_diarizer import collate
+    from tools import workload as synth
+    from whisper_nemo_b200 import speaker_utils as su
+    from whisper_nemo_b200 import titanet as tn
+
+    _featurizer_variant(monkeypatch, variant)
+    wav, _ = synth.synth_recording(40.0, 2, seed=6)
+    wav_t = torch.from_numpy(wav)
+    region, start_s, dur_s = su.subsegment_arrays([0.437, 17.203], [14.9, 21.05], window_s, shift_s)
+    start = (start_s * 16000).astype(np.int64)
+    length = (dur_s * 16000).astype(np.int64)
+    fixed = np.full_like(length, int(length.max()))
+    stream_start, stream_off, row0 = tn.plan_mel_streams(start, length, fixed)
+    assert (row0 >= 0).sum() >= len(start) - 2 and (row0 < 0).sum() >= 1
+    pk = tn.pack_weights(weights, dev)
+    wav_d = wav_t.to(dev)
+    to32 = lambda a: torch.from_numpy(a.astype(np.int32)).to(dev)
+    logmel = tn.mel_stream(pk, wav_d, torch.from_numpy(stream_start).to(dev), torch.from_numpy(stream_off).to(dev), int(stream_off[-1]))
+    F = int(fixed[0])
+    _, generic = tn.featurize(pk, wav_d, to32(start), to32(length), F, want_f32=True)
+    out16, fast = tn.featurize(pk, wav_d, to32(start), to32(length), F, want_f32=True, logmel=logmel, seg_row0=to32(row0))
+    torch.cuda.synchronize()
+    audio, alens = collate([wav_t[s : s + l] for s, l in zip(start.tolist(), length.tolist())])
+    feats, flens = oracle_model.preprocessor(audio, alens)
+    T = tn.frames_of(F)
+    ref = feats[:, :, :T].transpose(1, 2).contiguous()
+    d_paths = (fast - generic).abs().max().item()
+    err = (fast.cpu() - ref).abs().max().item()
+    print(f"streams {window_s}/{shift_s} ({variant}): {len(start)} windows, {len(stream_start)} streams, {int(stream_off[-1])} stream rows for "
+          f"{len(start) * T} window frames; stream path vs generic path max abs diff {d_paths:.1e}; vs oracle {err:.3e}")
+    assert d_paths <= 1e-5
+    assert err <= 2e-4
+    assert out16[:, 80:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("variant", ["classic", "later"])
 @pytest.mark.parametrize("fixed_len,n", [(24000, 12), (8000, 40), (48000, 5), (20000, 7)])
 def test_titanet_embeddings_match_oracle(dev, oracle_model, weights, fixed_len, n, variant, monkeypatch):
     from oracle.clustering_diarizer import collate

@@ -6,6 +6,7 @@ sm_100, every call raises.
 """
 import ctypes
 import os
+import threading
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 import torch
@@ -35,7 +36,43 @@ class GemmEpilogue(Structure):
         ("ldx", c_int32),
         ("vt", c_void_p),
         ("ldvt", c_int32),
+        ("flags", c_int32),
     ]
+
+
+GEMM_NO_PAIR = 1  # include/b200d.h B200D_GEMM_NO_PAIR
+TITANET_MAX_BLOCKS = 8
+
+
+class TitaNetBlockDesc(Structure):
+    _fields_ = [("cin", c_int32), ("cin_pad", c_int32), ("cout", c_int32), ("repeat", c_int32), ("ksize", c_int32), ("residual", c_int32),
+                ("se_hidden", c_int32), ("pad_", c_int32), ("dw", c_int64 * 3), ("w", c_int64 * 3), ("bias", c_int64 * 3),
+                ("se_w1", c_int64), ("se_w2", c_int64), ("res_w", c_int64), ("res_bias", c_int64)]
+
+
+class TitaNetDesc(Structure):
+    _fields_ = [("n_blocks", c_int32), ("feat_in", c_int32), ("feat_pad", c_int32), ("enc_out", c_int32), ("attn", c_int32), ("emb", c_int32),
+                ("emb_pad", c_int32), ("fb_nnz", c_int32), ("block", TitaNetBlockDesc * TITANET_MAX_BLOCKS),
+                ("tdnn_wx", c_int64), ("tdnn_wctx", c_int64), ("tdnn_b", c_int64), ("tdnn_scale", c_int64), ("tdnn_shift", c_int64),
+                ("attn_w2", c_int64), ("attn_b2", c_int64), ("emb_w", c_int64), ("emb_b", c_int64), ("zeros", c_int64),
+                ("fb_start", c_int64), ("fb_off", c_int64), ("fb_w", c_int64), ("window", c_int64), ("packed_bytes", c_int64)]
+
+
+EIG_HISTORY = 40
+
+
+class EigOptions(Structure):
+    _fields_ = [("tol", ctypes.c_double), ("max_outer", c_int32), ("gemm_flags", c_int32), ("sparse_max_row_nnz", c_int32), ("pad_", c_int32),
+                ("sparse_max_density", ctypes.c_double)]
+
+
+class EigStats(Structure):
+    _fields_ = [("block", c_int32), ("outer", c_int32), ("gemms", c_int32), ("converged", c_int32), ("sparse", c_int32), ("max_resid", c_float),
+                ("history", c_float * EIG_HISTORY)]
+
+
+class ProfileSpan(Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("ms", c_float), ("work", ctypes.c_double)]
 
 
 _SIGNATURES = {
@@ -44,10 +81,25 @@ _SIGNATURES = {
     "b200d_check_device": (c_int32, []),
     "b200d_featurize": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                   c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200d_mel_stream": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                   c_void_p]),
+    "b200d_featurize_windows": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                          c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_depthwise_conv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                  POINTER(GemmEpilogue), c_void_p]),
-    "b200d_gemm_set_pair_kernel": (c_int32, [c_int32]),
+    "b200d_titanet_pack_weights": (c_int32, [c_int32, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), POINTER(TitaNetDesc), c_void_p, c_size_t]),
+    "b200d_titanet_workspace_bytes": (c_size_t, [POINTER(TitaNetDesc), c_int32, c_int32]),
+    "b200d_titanet_forward": (c_int32, [POINTER(TitaNetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                        c_int32, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
+    "b200d_titanet_mel_stream": (c_int32, [POINTER(TitaNetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_eig_bottomk_block": (c_int32, [c_int32]),
+    "b200d_eig_bottomk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, POINTER(EigOptions)]),
+    "b200d_eig_bottomk": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, POINTER(EigOptions), POINTER(EigStats),
+                                    c_void_p, c_size_t, c_void_p]),
+    "b200d_launch_count": (c_int64, []),
+    "b200d_profile_start": (c_int32, []),
+    "b200d_profile_stop": (c_int32, [POINTER(ProfileSpan), c_int32, POINTER(c_int32)]),
     "b200d_time_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_se_apply_relu": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_se_apply_relu_stats": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -143,8 +195,9 @@ KERNELS_PER_CALL = {
     "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
     "b200d_resid_norms": 2, "b200d_kmeans": 1, "b200d_csr_from_dense": 3, "b200d_spmm_cheb": 1,
 }
+COMPOSITES = ("b200d_titanet_forward", "b200d_eig_bottomk")  # many kernels per call: counted by the library (b200d_launch_count)
 launch_count = 0
-_pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None  # mirrors b200d_gemm_set_pair_kernel for the profile labels
+_pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None
 _profile = None  # {name: [(event0, event1, work, stream)]} while a profiled step runs
 _profile_base = None
 
@@ -156,6 +209,7 @@ def start_profile():
     _profile = {}
     _profile_base = torch.cuda.Event(enable_timing=True)
     _profile_base.record()
+    load().b200d_profile_start()  # ... and around every kernel the composite entry points launch themselves
 
 
 def stop_profile():
@@ -165,7 +219,19 @@ def stop_profile():
     torch.cuda.synchronize()
     out = {}
     for name, spans in (prof or {}).items():
+        if name in COMPOSITES:
+            continue  # their kernels are reported one by one from the library's own spans below
         out[name] = {"calls": len(spans), "ms": sum(e0.elapsed_time(e1) for e0, e1, *_ in spans), "work": sum(sp[2] for sp in spans)}
+    cap = 1 << 16
+    buf = (ProfileSpan * cap)()
+    n = c_int32(0)
+    check(load().b200d_profile_stop(buf, cap, ctypes.byref(n)), "b200d_profile_stop")
+    for i in range(min(n.value, cap)):
+        key = "b200d::" + buf[i].name.decode()
+        d = out.setdefault(key, {"calls": 0, "ms": 0.0, "work": 0.0})
+        d["calls"] += 1
+        d["ms"] += buf[i].ms
+        d["work"] += buf[i].work
     path = os.environ.get("B200D_TIMELINE")  # development aid: per-call (key, stream, start ms, end ms) of the profiled step
     if path and prof:
         import json
@@ -174,6 +240,12 @@ def stop_profile():
         with open(path, "w") as f:
             json.dump(sorted(rows, key=lambda r: r[2]), f)
     return out
+
+
+def total_launches() -> int:
+    """Kernels of this library launched so far by this process: fine-grained calls made through `call` + the kernels the
+    composite entry points launched themselves."""
+    return launch_count + int(load().b200d_launch_count())
 
 
 def call(name, *args):
@@ -190,14 +262,14 @@ def call(name, *args):
             M, N, mode = args[4], args[5], args[9]._obj.mode
             work = 2.0 * M * N * args[6]
             # same rule as b200d_gemm_f16's dispatch (gemm_tcgen05.cu): which launches run the CTA-pair kernel
-            pair = _pair_kernel_on and ((N == 192 and M >= 4096) if mode == EPI_CHEB else (N % 256 == 0 and -(-M // 256) * (N // 256) >= 74))
+            pair = _pair_kernel_on and not (args[9]._obj.flags & GEMM_NO_PAIR) and ((N == 192 and M >= 4096) if mode == EPI_CHEB else (N % 256 == 0 and -(-M // 256) * (N // 256) >= 74))
             key = f"{name}[{_EPI_NAMES[mode]}{'|2cta' if pair else ''}]"
         elif name == "b200d_small_eig":
             key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"
         _profile.setdefault(key, []).append((e0, e1, work, torch.cuda.current_stream().cuda_stream))
     else:
         rc = fn(*args)
-    launch_count += KERNELS_PER_CALL.get(name, 1)
+    launch_count += 0 if name in COMPOSITES else KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 
@@ -223,20 +295,26 @@ class short_gil_switch:
         return False
 
 
+_tls = threading.local()
+
+
+def gemm_flags() -> int:
+    """B200D_GEMM_* bits for GEMM launches made from THIS host thread (per call, no process-wide switch)."""
+    return getattr(_tls, "gemm_flags", 0)
+
+
 class single_cta_gemms:
-    """Context manager around a multi-stream region: the cluster-launched CTA-pair GEMM is switched off inside
-    (see b200d_gemm_set_pair_kernel in include/b200d.h)."""
+    """Context manager for a host thread that drives one of several concurrently busy streams: every GEMM it launches inside
+    carries B200D_GEMM_NO_PAIR, so the cluster-launched CTA-pair kernel never shares the device with another stream's
+    kernels (see include/b200d.h).  Thread-local and re-entrant: other threads / regions are unaffected."""
 
     def __enter__(self):
-        global _pair_kernel_on
-        self.prev = load().b200d_gemm_set_pair_kernel(0)
-        _pair_kernel_on = False
+        self.prev = gemm_flags()
+        _tls.gemm_flags = self.prev | GEMM_NO_PAIR
         return self
 
     def __exit__(self, *exc):
-        global _pair_kernel_on
-        load().b200d_gemm_set_pair_kernel(self.prev)
-        _pair_kernel_on = bool(self.prev)
+        _tls.gemm_flags = self.prev
         return False
 
 

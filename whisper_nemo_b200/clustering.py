@@ -299,6 +299,7 @@ def _gemm_cheb(A16, lda, vt_in, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vt_
     epi.ldx = x.stride(0)
     epi.vt = vt_out.data_ptr() if vt_out is not None else None
     epi.ldvt = ldvt
+    epi.flags = _cabi.gemm_flags()
     _cabi.call("b200d_gemm_f16", ptr(A16), lda, ptr(vt_in), ldvt, n, nw, n, ptr(out), out.stride(0), ctypes.byref(epi), _s())
 
 
@@ -341,16 +342,48 @@ def _use_csr_products(n: int, p: Optional[int]) -> bool:
 
 
 def bottom_eigvecs(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e-6, max_outer: int = 40, seed: int = 0,
-                   p: Optional[int] = None) -> torch.Tensor:
-    """The k lowest eigenvectors of L = diag(deg) - A for the binarised graph A (bf16 [n, lda]).
+                   p: Optional[int] = None, stepwise: bool = False) -> torch.Tensor:
+    """The k lowest eigenvectors of L = diag(deg) - A for the binarised graph A (bf16 [n, lda]): `b200d_eig_bottomk`, the
+    Chebyshev-filtered subspace iteration as one library call (upstream: a dense eigh(N x N) with k columns kept; k-means
+    only sees the k-dimensional invariant subspace, which is what converges here).  The random start block comes from the
+    CPU torch generator (seed 1000 + seed).  When the graph was built from few neighbours (`p` given, see _use_csr_products)
+    the products run in fp32 over its CSR lists instead of the tcgen05 GEMM.  `stepwise=True` runs the same iteration call by
+    call from Python (`bottom_eigvecs_stepwise`, the cross-check of the composite)."""
+    if stepwise:
+        return bottom_eigvecs_stepwise(a16, deg, k, tol, max_outer, seed, p)
+    n, lda = a16.shape
+    dev = a16.device
+    lib = _cabi.load()
+    b = int(lib.b200d_eig_bottomk_block(int(k)))
+    if b == 0:
+        raise NotImplementedError(f"spectral embedding for {k} clusters: the subspace block is limited to 64 vectors")
+    if n < 2 * b:
+        raise NotImplementedError(f"spectral embedding of {k} clusters on {n} points: needs n >= {2 * b} (or n <= {DENSE_EIG_MAX})")
+    opt = _cabi.EigOptions(tol=float(tol), max_outer=int(max_outer), gemm_flags=_cabi.gemm_flags(), sparse_max_row_nnz=SPARSE_MAX_ROW_NNZ,
+                           sparse_max_density=SPARSE_MAX_DENSITY)
+    stats = _cabi.EigStats()
+    pp = int(p) if p is not None else 0
+    ws_bytes = int(lib.b200d_eig_bottomk_workspace_bytes(n, int(k), pp, ctypes.byref(opt)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    X = torch.empty(n, b, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device="cpu").manual_seed(1000 + seed)
+    X.copy_(torch.randn(n, b, generator=gen))
+    _cabi.call("b200d_eig_bottomk", ptr(a16), lda, ptr(deg), n, int(k), pp, ptr(X), b, ctypes.byref(opt), ctypes.byref(stats), ptr(ws), ws_bytes, _s())
+    st = SpectralStats()
+    st.outer, st.gemms, st.n, st.max_resid, st.converged = stats.outer, stats.gemms, n, float(stats.max_resid), bool(stats.converged)
+    st.method = f"chfsi{b}" + ("-csr" if stats.sparse else "")
+    last_spectral_stats.__dict__.update(st.__dict__)
+    if len(spectral_log) < 256:
+        spectral_log.append({"n": n, "k": k, "p": p, "method": st.method, "block": b, "outer": st.outer, "gemms": st.gemms, "resid": st.max_resid,
+                             "converged": st.converged, "history": [float(f"{stats.history[i]:.2e}") for i in range(min(stats.outer, _cabi.EIG_HISTORY))]})
+    return X[:, :k].contiguous()
 
-    Chebyshev-filtered subspace iteration: a block of b = 32 / 64 vectors is repeatedly pushed
-    through a Chebyshev polynomial of L that damps [theta_b, lambda_max] (each term one tcgen05
-    GEMM A*V with V split into three bf16 parts, i.e. fp32-accurate products on an exactly
-    representable A), re-orthonormalised by CholQR2 and rotated to Ritz vectors.  Upstream
-    calls a dense eigh(N x N) and keeps k columns; k-means only sees the k-dimensional
-    invariant subspace, which is what converges here.  When the graph was built from few neighbours
-    (`p` given, see _use_csr_products) the products run in fp32 over its CSR lists instead."""
+
+def bottom_eigvecs_stepwise(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: float = 2e-6, max_outer: int = 40, seed: int = 0,
+                            p: Optional[int] = None) -> torch.Tensor:
+    """The iteration of b200d_eig_bottomk driven call by call from Python over the fine-grained entry points (gemm / spmm /
+    gram / small_eig / right_mul / resid_norms).  Kept as the readable statement of the algorithm and as the test that the
+    composite reproduces it bit for bit."""
     n, lda = a16.shape
     dev = a16.device
     if k + 8 <= 32:

@@ -1,0 +1,210 @@
+// b200d_eig_bottomk: the k lowest eigenvectors of L = diag(deg) - A for the binarised affinity graph -- the device work behind
+// upstream's SpectralClustering.getSpectralEmbeddings (offline_clustering.py: torch.linalg.eigh of the full N x N Laplacian,
+// k columns kept), as ONE composite C-ABI call.
+//
+// Chebyshev-filtered subspace iteration: a block of b = 32 / 64 vectors is repeatedly pushed through a Chebyshev polynomial
+// of L that damps [theta_b, lambda_max] (each term one tcgen05 GEMM A*V with V split into three bf16 parts, i.e.
+// fp32-accurate products on an exactly representable A -- or an fp32 row-gather product over the graph's CSR lists when it
+// has few neighbours), re-orthonormalised by CholQR2 and rotated to Ritz vectors.  k-means only sees the k-dimensional
+// invariant subspace, which is what converges here.  The polynomial degree and the stopping test are decided on the host
+// from 2 x b floats read back per outer iteration, so this entry point synchronises `stream` (~10-15 times per call).
+#include "common.cuh"
+#include "composite.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace b200d {
+
+static inline int block_of(int k) { return k + 8 <= 32 ? 32 : (k + 8 <= 64 ? 64 : 0); }
+static inline int operand_rows(int b) { return b == 64 ? 192 : 128; }  // [hi | mid | lo] parts of b rows each (b = 32: 32 zero rows)
+
+static bool use_csr(int n, int p, int max_row_nnz, double max_density) {
+  if (p <= 0) return false;
+  const long long nnz = 2LL * p;
+  return nnz <= max_row_nnz || static_cast<double>(nnz) <= max_density * n;
+}
+
+struct EigWs {
+  float *W, *Y[3], *G, *Q, *theta, *resid;
+  void* vt[2];
+  void* gws;
+  size_t gws_bytes;
+  int32_t* rowptr;
+  uint32_t* colw;
+  long long capacity;
+};
+
+static size_t carve_eig(uint8_t* base, int n, int b, bool sparse, int p, EigWs* out) {
+  size_t pos = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* q = base ? base + pos : nullptr;
+    pos = (pos + bytes + 255) & ~static_cast<size_t>(255);
+    return q;
+  };
+  EigWs w{};
+  const size_t nb = static_cast<size_t>(n) * b * 4;
+  w.W = reinterpret_cast<float*>(take(nb));
+  for (int i = 0; i < 3; ++i) w.Y[i] = reinterpret_cast<float*>(take(nb));
+  w.G = reinterpret_cast<float*>(take(static_cast<size_t>(b) * b * 4));
+  w.Q = reinterpret_cast<float*>(take(static_cast<size_t>(b) * b * 4));
+  w.theta = reinterpret_cast<float*>(take(b * 4));
+  w.resid = reinterpret_cast<float*>(take(b * 4));
+  w.gws_bytes = b200d_gram_workspace_bytes(n, b);
+  w.gws = take(w.gws_bytes);
+  const size_t ldvt = (static_cast<size_t>(n) + 7) / 8 * 8;
+  if (sparse) {
+    w.capacity = static_cast<long long>(std::min(2LL * p, static_cast<long long>(n))) * n;
+    w.rowptr = reinterpret_cast<int32_t*>(take((static_cast<size_t>(n) + 1) * 4));
+    w.colw = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(w.capacity) * 4));
+  } else {
+    for (int i = 0; i < 2; ++i) w.vt[i] = take(static_cast<size_t>(operand_rows(b)) * ldvt * 2);
+  }
+  if (out) *out = w;
+  return pos;
+}
+
+}  // namespace b200d
+
+using namespace b200d;
+
+extern "C" int32_t b200d_eig_bottomk_block(int32_t k) { return block_of(k); }
+
+extern "C" size_t b200d_eig_bottomk_workspace_bytes(int32_t n, int32_t k, int32_t p, const b200d_eig_options* opt) {
+  const int b = block_of(k);
+  if (n <= 0 || b == 0) return 0;
+  const int max_row_nnz = opt ? opt->sparse_max_row_nnz : 32;
+  const double max_density = opt ? opt->sparse_max_density : 1.0 / 64.0;
+  return carve_eig(nullptr, n, b, use_csr(n, p, max_row_nnz, max_density), p, nullptr);
+}
+
+extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* deg, int32_t n, int32_t k, int32_t p, float* x, int32_t ldx,
+                                 const b200d_eig_options* opt, b200d_eig_stats* stats, void* ws, size_t ws_bytes, void* stream) {
+  B200D_CHECK_ARG(a_bf16 && deg && x && ws && n > 0 && k > 0 && lda >= n && lda % 8 == 0);
+  const int b = block_of(k);
+  if (b == 0) return set_error(B200D_EINVAL, "%s: the subspace block is limited to 64 vectors (k <= 56)%s", "b200d_eig_bottomk");
+  B200D_CHECK_ARG(ldx == b);
+  if (n < 2 * b) return set_error(B200D_EINVAL, "%s: needs n >= 2 * block (use b200d_small_eig on the dense Laplacian for tiny graphs)%s", "b200d_eig_bottomk");
+  const double tol = opt && opt->tol > 0 ? opt->tol : 2e-6;
+  const int max_outer = opt && opt->max_outer > 0 ? opt->max_outer : 40;
+  const int flags = opt ? opt->gemm_flags : 0;
+  const bool sparse = use_csr(n, p, opt ? opt->sparse_max_row_nnz : 32, opt ? opt->sparse_max_density : 1.0 / 64.0);
+  if (carve_eig(nullptr, n, b, sparse, p, nullptr) > ws_bytes)
+    return set_error(B200D_EWORKSPACE, "%s: workspace too small (b200d_eig_bottomk_workspace_bytes)%s", "b200d_eig_bottomk");
+  B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0);
+  EigWs w;
+  carve_eig(reinterpret_cast<uint8_t*>(ws), n, b, sparse, p, &w);
+  cudaStream_t st = as_stream(stream);
+  const int nw = operand_rows(b);
+  const int ldvt = (n + 7) / 8 * 8;
+  float* X = x;
+
+  // Gershgorin bound on lambda_max(L) = 2 max deg
+  std::vector<float> host(std::max(n, 2 * b));
+  B200D_CHECK_CUDA(cudaMemcpyAsync(host.data(), deg, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, st));
+  B200D_CHECK_CUDA(cudaStreamSynchronize(st));
+  const double up = 2.0 * static_cast<double>(*std::max_element(host.begin(), host.begin() + n)) * 1.01 + 1e-3;
+
+  if (sparse) {
+    ProfScope ps("csr_from_dense", 0, st, 3);
+    RC(b200d_csr_from_dense(a_bf16, n, lda, w.rowptr, w.colw, w.capacity, st));
+  } else {
+    for (int i = 0; i < 2; ++i) B200D_CHECK_CUDA(cudaMemsetAsync(w.vt[i], 0, static_cast<size_t>(nw) * ldvt * 2, st));
+  }
+  int gemms = 0;
+  // one operator application: out = ca (deg x - A x) + cb x + cc xprev; vin / vout are the bf16 splits of x / out (dense path)
+  auto step = [&](const void* vin, float* out, const float* xx, const float* xprev, double ca, double cb, double cc, void* vout) -> int {
+    ++gemms;
+    if (sparse) {
+      ProfScope ps("spmm_cheb", 0, st);
+      return b200d_spmm_cheb(w.rowptr, w.colw, n, b, deg, xx, xprev, b, static_cast<float>(ca), static_cast<float>(cb), static_cast<float>(cc), out, b, st);
+    }
+    b200d_gemm_epilogue e{};
+    e.mode = B200D_EPI_CHEB;
+    e.deg = deg;
+    e.x32 = xx;
+    e.xprev32 = xprev;
+    e.ca = static_cast<float>(ca); e.cb = static_cast<float>(cb); e.cc = static_cast<float>(cc);
+    e.ldx = b;
+    e.vt = vout;
+    e.ldvt = ldvt;
+    e.flags = flags;
+    ProfScope ps(gemm_uses_pair_kernel(n, nw, B200D_EPI_CHEB, flags) ? "gemm[cheb|2cta]" : "gemm[cheb]", 2.0 * n * nw * static_cast<double>(n), st);
+    return b200d_gemm_f16(a_bf16, lda, vin, ldvt, n, nw, n, out, b, &e, st);
+  };
+  auto gram = [&](const float* a, const float* c, float* out) -> int {
+    ProfScope ps("gram", 0, st, 2);
+    return b200d_gram(a, c, n, b, b, out, w.gws, w.gws_bytes, st);
+  };
+  auto cholqr = [&](float* V, void* want_vt) -> int {
+    RC(gram(V, V, w.G));
+    { ProfScope ps("small_eig[cholesky]", 0, st); RC(b200d_small_eig(w.G, b, nullptr, w.Q, 1, st)); }
+    ProfScope ps("right_mul", 0, st);
+    return b200d_right_mul(V, n, b, b, w.Q, V, want_vt, ldvt, st);
+  };
+  RC(cholqr(X, nullptr));
+  RC(cholqr(X, w.vt[0]));
+  std::vector<double> history;
+  double max_resid = NAN;
+  bool converged = false;
+  int outer = 0;
+  for (; outer < max_outer;) {
+    ++outer;
+    // Rayleigh-Ritz on span(X): W = L X, H = X^T W, X <- X Q, W <- W Q
+    RC(step(w.vt[0], w.W, X, nullptr, 1.0, 0.0, 0.0, nullptr));
+    RC(gram(X, w.W, w.G));
+    { ProfScope ps("small_eig[jacobi]", 0, st); RC(b200d_small_eig(w.G, b, w.theta, w.Q, 0, st)); }
+    { ProfScope ps("right_mul", 0, st); RC(b200d_right_mul(X, n, b, b, w.Q, X, w.vt[0], ldvt, st)); }
+    { ProfScope ps("right_mul", 0, st); RC(b200d_right_mul(w.W, n, b, b, w.Q, w.W, nullptr, ldvt, st)); }
+    { ProfScope ps("resid_norms", 0, st, 2); RC(b200d_resid_norms(w.W, X, w.theta, n, b, b, w.resid, w.gws, w.gws_bytes, st)); }
+    B200D_CHECK_CUDA(cudaMemcpyAsync(host.data(), w.theta, b * 4, cudaMemcpyDeviceToHost, st));
+    B200D_CHECK_CUDA(cudaMemcpyAsync(host.data() + b, w.resid, b * 4, cudaMemcpyDeviceToHost, st));
+    B200D_CHECK_CUDA(cudaStreamSynchronize(st));
+    double rmax = 0.0;
+    for (int j = 0; j < k; ++j) rmax = std::max(rmax, std::sqrt(std::max(static_cast<double>(host[b + j]), 0.0)));
+    max_resid = rmax / up;
+    history.push_back(max_resid);
+    if (stats && outer <= B200D_EIG_HISTORY) stats->history[outer - 1] = static_cast<float>(max_resid);
+    if (max_resid <= tol) { converged = true; break; }
+    if (history.size() >= 8 && max_resid < 5e-5 && max_resid > 0.5 * history[history.size() - 4]) { converged = true; break; }  // fp32 floor of the products
+    // filter interval [a, up]: damp everything above the block's largest Ritz value
+    const double th_b = host[b - 1], th_k = host[k - 1];
+    const double a = std::min(std::max(th_b, 1e-3 * up), 0.95 * up);
+    const double e = (up - a) / 2.0, c = (up + a) / 2.0;
+    const double t_k = (c - std::max(th_k, 0.0)) / e, t_0 = c / e;
+    int m = static_cast<int>(std::nearbyint(std::acosh(1e3) / std::max(std::acosh(std::max(t_k, 1.0 + 1e-9)), 1e-6)));
+    const int m_cap = static_cast<int>(std::acosh(1e7) / std::acosh(t_0));
+    m = std::max(3, std::min(std::min(m, std::max(m_cap, 3)), 48));
+    // scaled three-term recurrence (gain 1 at lambda = 0):  Y1 = (s1/e)(L - c) X,  Y_{i+1} = (2 s_{i+1}/e)(L - c) Y_i - s_i s_{i+1} Y_{i-1}
+    const double sigma1 = e / (0.0 - c);
+    double sigma = sigma1;
+    const double tau = 2.0 / sigma1;
+    RC(step(w.vt[0], w.Y[0], X, nullptr, sigma1 / e, -c * sigma1 / e, 0.0, w.vt[1]));
+    const float* prev = X;
+    float* cur = w.Y[0];
+    int vin = 1;
+    for (int i = 2; i <= m; ++i) {
+      float* nxt = w.Y[(i - 1) % 3];
+      const double sigma_new = 1.0 / (tau - sigma);
+      const double ca = 2.0 * sigma_new / e;
+      RC(step(w.vt[vin], nxt, cur, prev, ca, -c * ca, -sigma * sigma_new, w.vt[1 - vin]));
+      sigma = sigma_new;
+      prev = cur;
+      cur = nxt;
+      vin = 1 - vin;
+    }
+    B200D_CHECK_CUDA(cudaMemcpyAsync(X, cur, static_cast<size_t>(n) * b * 4, cudaMemcpyDeviceToDevice, st));
+    RC(cholqr(X, nullptr));
+    RC(cholqr(X, w.vt[0]));
+  }
+  if (stats) {
+    stats->block = b;
+    stats->outer = outer;
+    stats->gemms = gemms;
+    stats->max_resid = static_cast<float>(max_resid);
+    stats->converged = converged ? 1 : 0;
+    stats->sparse = sparse ? 1 : 0;
+  }
+  return B200D_OK;
+}

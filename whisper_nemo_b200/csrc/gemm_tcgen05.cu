@@ -635,11 +635,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-// The cluster-launched CTA-pair kernel must have the GPU to itself: on B200 / driver 580.159 a __cluster_dims__(2)
-// tcgen05 kernel sharing the device with a register-heavy kernel of ANOTHER stream (depthwise_kernel: 3 CTAs x 20 k
-// registers per SM) deadlocked the device (tools/concurrency_check.py big2cta depthwise), while the cta_group::1 kernel
-// in the same situation is fine.  Hosts that run several streams switch the pair kernel off for that region.
-static std::atomic<int> g_pair_kernel_enabled{1};
 static std::once_flag g_encode_once;
 
 static EncodeTiledFn get_encode() {
@@ -731,13 +726,20 @@ static int dispatch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   return set_error(B200D_EINVAL, "%s: unknown epilogue mode%s", "b200d_gemm_f16");
 }
 
+// Which launches take the CTA-pair kernel: at least one 256 x 256 tile per TPC (the large pointwise convs), and the
+// Chebyshev products of 64-vector blocks on large graphs (L2-traffic bound: the pair halves the W bytes per SM) -- unless
+// the caller asks for the 1-CTA kernel on this call (B200D_GEMM_NO_PAIR: it runs several streams at once, see b200d.h).
+bool gemm_uses_pair_kernel(int M, int N, int mode, int flags) {
+  static const bool env_allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
+  if (!env_allow_2cta || (flags & B200D_GEMM_NO_PAIR)) return false;
+  if (mode == B200D_EPI_CHEB) return N == 192 && M >= 4096;
+  const long long tiles2 = static_cast<long long>((M + 255) / 256) * (N / 256);
+  return N % 256 == 0 && tiles2 >= kNumSMs / 2;
+}
+
 }  // namespace b200d
 
 using namespace b200d;
-
-extern "C" int b200d_gemm_set_pair_kernel(int32_t enable) {
-  return g_pair_kernel_enabled.exchange(enable ? 1 : 0);
-}
 
 extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K, void* out,
                               int32_t ldo, const b200d_gemm_epilogue* epi, void* stream) {
@@ -760,12 +762,7 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
   }
   const bool bf16 = mode == B200D_EPI_CHEB;
   const int block_n = (mode == B200D_EPI_CHEB) ? N : (N % 256 == 0) ? 256 : 128;
-  // CTA-pair kernel when there is at least one 256 x 256 tile per TPC (the large pointwise convs), and for the
-  // Chebyshev products of 64-vector blocks on large graphs (L2-traffic bound: the pair halves the W bytes per SM)
-  static const bool env_allow_2cta = getenv("B200D_GEMM_1CTA") == nullptr;
-  const bool allow_2cta = env_allow_2cta && g_pair_kernel_enabled.load(std::memory_order_relaxed) != 0;
-  const long long tiles2 = static_cast<long long>((M + 255) / 256) * (N / 256);
-  const bool use_2cta = allow_2cta && (mode == B200D_EPI_CHEB ? (N == 192 && M >= 4096) : (block_n == 256 && tiles2 >= kNumSMs / 2));
+  const bool use_2cta = gemm_uses_pair_kernel(M, N, mode, epi->flags);
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
   if (rc) return rc;

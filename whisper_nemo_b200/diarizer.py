@@ -40,6 +40,20 @@ def _get(cfg, dotted, default=None):
     return default if cur is None else cur
 
 
+_PINNED: Dict[int, torch.Tensor] = {}
+
+
+def _pinned_buffer(n: int) -> torch.Tensor:
+    """float32 [n] view on a process-wide pinned staging buffer that only grows: cudaHostAlloc of 230 MB (one hour of
+    audio) costs ~0.1 s, as much as the whole device path, and the reference builds a fresh diarizer object per recording."""
+    have = _PINNED.get(0)
+    if have is None or have.numel() < n:
+        have = None
+        _PINNED.pop(0, None)
+        _PINNED[0] = have = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
+    return have[:n]
+
+
 class DeviceTimer:
     """Per-stage device time from CUDA events on the launching stream (no host sync until read)."""
 
@@ -140,7 +154,7 @@ class ClusteringDiarizer:
         if manifest is None:
             raise ValueError("diarizer.manifest_filepath is required")
         self.AUDIO_RTTM_MAP = su.audio_rttm_map(manifest)
-        # every recording is decoded ONCE into one pinned host buffer (upstream re-opens the WAV per segment)
+        # every recording is decoded ONCE (memory-mapped) into one pinned host buffer (upstream re-opens the WAV per segment)
         wavs = {u: su.read_wav(m["audio_filepath"], self.sample_rate) for u, m in self.AUDIO_RTTM_MAP.items()}
         self._wav_offset, total = {}, 0
         for u, w in wavs.items():
@@ -148,10 +162,12 @@ class ClusteringDiarizer:
             total += len(w)
         if total >= 2 ** 31:
             raise ValueError("more than 2^31 samples in one manifest; split the batch")
-        self._wav_host = torch.empty(total, dtype=torch.float32).pin_memory()
+        self._wav_host = _pinned_buffer(total)
+        host_np = self._wav_host.numpy()
         for u, w in wavs.items():
             o, n = self._wav_offset[u]
-            self._wav_host[o : o + n] = torch.from_numpy(w)
+            host_np[o : o + n] = w
+        del wavs
         durations = {u: n / self.sample_rate for u, (o, n) in self._wav_offset.items()}
         ext = _get(cfg, "diarizer.vad.external_vad_manifest")
         if _get(cfg, "diarizer.oracle_vad", False):
@@ -159,84 +175,140 @@ class ClusteringDiarizer:
         elif ext:
             speech_manifest = ext
         else:
+            speech_manifest = self._run_vad(durations)
+        regions = su.read_speech_regions(speech_manifest)
+        self._plan_windows(regions, write_manifests=True)
+
+    def _run_vad(self, durations):
+        """`oracle_vad: False` without an external VAD manifest: upstream runs MarbleNet here.  A user-supplied callable
+        (`vad_fn(uniq_id, waveform float32 numpy) -> [(start_s, end_s), ...]`, set as `diarizer.vad_fn` on this object) stands
+        in for it; the MarbleNet network itself is outside the B200 path."""
+        vad_fn = getattr(self, "vad_fn", None)
+        if vad_fn is None:
             raise NotImplementedError(
                 "MarbleNet VAD is outside the B200 hot path (embed + NME-SC): set diarizer.oracle_vad=True with rttm_filepath "
-                "in the manifest, or diarizer.vad.external_vad_manifest")
+                "in the manifest, diarizer.vad.external_vad_manifest, or assign a callable to ClusteringDiarizer.vad_fn")
+        path = os.path.join(self._speaker_dir, "vad_fn_manifest.json")
+        host_np = self._wav_host.numpy()
+        with open(path, "w") as out:
+            for uniq_id, meta in self.AUDIO_RTTM_MAP.items():
+                o, n = self._wav_offset[uniq_id]
+                for a, b in su._merge_on_grid([[float(x), float(y)] for x, y in vad_fn(uniq_id, host_np[o : o + n])], 5):
+                    a, b = max(a, 0.0), min(b, durations[uniq_id])
+                    if b > a:
+                        json.dump({"audio_filepath": meta["audio_filepath"], "offset": round(a, 5), "duration": round(b - a, 5), "label": "UNK",
+                                   "uniq_id": uniq_id}, out)
+                        out.write("\n")
+        return path
+
+    def _plan_windows(self, regions: List[dict], write_manifests: bool):
+        """Window descriptors of every scale from the speech regions (vectorised `get_subsegments`), the once-per-recording
+        log-mel stream plan (titanet.plan_mel_streams) and, per recording and scale, the row range of its windows in the
+        scale's embedding matrix + the [start, end] stamps."""
+        from .titanet import plan_mel_streams
+
+        sr = self.sample_rate
+        uniq_of = [r.get("uniq_id") or su.get_uniqname_from_filepath(r["audio_filepath"]) for r in regions]
+        uniq_ids = list(self.AUDIO_RTTM_MAP.keys())
+        uniq_index = {u: i for i, u in enumerate(uniq_ids)}
+        reg_uniq = np.asarray([uniq_index[u] for u in uniq_of], dtype=np.int64)
+        reg_off = np.asarray([self._wav_offset[u][0] for u in uniq_of], dtype=np.int64)
+        reg_tot = np.asarray([self._wav_offset[u][1] for u in uniq_of], dtype=np.int64)
+        offsets = np.asarray([r["offset"] for r in regions], dtype=np.float64)
+        durs = np.asarray([r["duration"] for r in regions], dtype=np.float64)
         self._scales = {}
         for scale_idx, (window, shift) in self.multiscale_args_dict["scale_dict"].items():
-            path = os.path.join(self._speaker_dir, f"subsegments_scale{scale_idx}.json")
-            entries = su.segments_manifest_to_subsegments_manifest(speech_manifest, path, window, shift)
-            self._scales[scale_idx] = self._plan_scale(entries)
-        # per recording and scale: row range of its windows in the scale's embedding matrix + the [start, end] stamps
-        for plan in self._scales.values():
-            uniq_arr = np.asarray(plan["uniq"])
-            plan["rows"], plan["stamps"] = {}, {}
-            for u in self.AUDIO_RTTM_MAP.keys():
-                sel = np.nonzero(uniq_arr == u)[0]
+            region, start_s, dur_s = su.subsegment_arrays(offsets, durs, window, shift)
+            if write_manifests:
+                su.write_subsegments_manifest(os.path.join(self._speaker_dir, f"subsegments_scale{scale_idx}.json"), regions, region, start_s, dur_s)
+            s = (start_s * sr).astype(np.int64)  # int(offset * sr), as the dataset's slicing
+            length = np.minimum((dur_s * sr).astype(np.int64), reg_tot[region] - s)
+            if length.size and int(length.min()) < 1:
+                bad = int(np.argmin(length))
+                raise ValueError(f"empty window at {start_s[bad]} s in {uniq_ids[reg_uniq[region[bad]]]}")
+            # the frame count each window is tiled up to: the max length inside its dataloader batch of `batch_size` windows
+            # (label_models' fixed_seq collate)
+            nb = -(-length.size // self.batch_size)
+            padded = np.zeros(nb * self.batch_size, dtype=np.int64)
+            padded[: length.size] = length
+            fixed = np.repeat(padded.reshape(nb, self.batch_size).max(axis=1), self.batch_size)[: length.size]
+            uniq_arr = reg_uniq[region]
+            plan = {"n": int(length.size), "uniq_idx": uniq_arr, "start": reg_off[region] + s, "len": length, "fixed": fixed,
+                    "t0": start_s, "t1": start_s + dur_s, "rows": {}, "stamps": {}}
+            stamps32 = np.stack([plan["t0"], plan["t1"]], axis=1).astype(np.float32) if length.size else np.zeros((0, 2), np.float32)
+            for u, ui in uniq_index.items():
+                sel = np.nonzero(uniq_arr == ui)[0]
                 if len(sel):
                     plan["rows"][u] = sel
-                    plan["stamps"][u] = torch.tensor([[plan["t0"][i], plan["t1"][i]] for i in sel])  # float32, as upstream
-
-    def _plan_scale(self, entries: List[dict]) -> dict:
-        """Window descriptors of one scale: sample ranges in the concatenated waveform, and the frame
-        count each window is tiled up to (the max length inside its dataloader batch of `batch_size`,
-        label_models' fixed_seq collate)."""
-        sr = self.sample_rate
-        uniq, start, length, t0, t1 = [], [], [], [], []
-        for dic in entries:
-            u = dic.get("uniq_id") or su.get_uniqname_from_filepath(dic["audio_filepath"])
-            off, n_total = self._wav_offset[u]
-            s = int(dic["offset"] * sr)
-            n = min(int(dic["duration"] * sr), n_total - s)
-            if n < 1:
-                raise ValueError(f"empty window at {dic['offset']} s in {u}")
-            uniq.append(u)
-            start.append(off + s)
-            length.append(n)
-            t0.append(dic["offset"])
-            t1.append(dic["offset"] + dic["duration"])
-        length_np = np.asarray(length, dtype=np.int64)
-        fixed = np.empty_like(length_np)
-        for b0 in range(0, len(length_np), self.batch_size):
-            fixed[b0 : b0 + self.batch_size] = length_np[b0 : b0 + self.batch_size].max() if len(length_np) else 0
-        return {"uniq": uniq, "start": np.asarray(start, dtype=np.int64), "len": length_np, "fixed": fixed, "t0": t0, "t1": t1}
+                    plan["stamps"][u] = torch.from_numpy(stamps32[sel])  # float32, as upstream's torch.tensor(list of floats)
+            self._scales[scale_idx] = plan
+        plans = list(self._scales.values())
+        cat = lambda key: np.concatenate([pl[key] for pl in plans]) if plans else np.zeros(0, np.int64)
+        stream_start, stream_off, row0 = plan_mel_streams(cat("start"), cat("len"), cat("fixed"))
+        pos = 0
+        for pl in plans:
+            pl["row0"] = row0[pos : pos + pl["n"]]
+            pos += pl["n"]
+        self._streams = (stream_start, stream_off)
 
     # ------------------------------------------------------------------ device work
-    def _extract_embeddings(self, plan: dict, wav_dev: torch.Tensor) -> torch.Tensor:
-        """All windows of one scale -> float32 [n, 192] on device (manifest order)."""
-        n = len(plan["uniq"])
+    def _extract_embeddings(self, plan: dict, wav_dev: torch.Tensor, logmel: torch.Tensor = None) -> torch.Tensor:
+        """All windows of one scale -> float32 [n, 192] on device (manifest order).  `logmel`: the stream frames of
+        `_mel_streams` (interior frames of every window are gathered from it instead of recomputed)."""
+        n = plan["n"]
         out = torch.empty(n, 192, dtype=torch.float32, device=self.device)
         if n == 0:
             return out
         fixed = plan["fixed"]
+        lo, hi = 0, n
         if self.shard_windows:
             from . import sharding
 
             rank, world = sharding.rank_world()
             lo, hi = sharding.shard_range(n, rank, world)
-            local = torch.empty(hi - lo, 192, dtype=torch.float32, device=self.device)
-            for fl in np.unique(fixed[lo:hi]):
-                idx = lo + np.nonzero(fixed[lo:hi] == fl)[0]
-                st = torch.from_numpy(plan["start"][idx].astype(np.int32)).to(self.device)
-                ln = torch.from_numpy(plan["len"][idx].astype(np.int32)).to(self.device)
-                local.index_copy_(0, torch.from_numpy(idx - lo).to(self.device), self._speaker_model.embed_segments(wav_dev, st, ln, int(fl)))
-            return sharding.all_gather_rows(local, n)
-        for fl in np.unique(fixed):
-            idx = np.nonzero(fixed == fl)[0]
-            idx_t = torch.from_numpy(idx).to(self.device)
-            st = torch.from_numpy(plan["start"][idx].astype(np.int32)).to(self.device)
-            ln = torch.from_numpy(plan["len"][idx].astype(np.int32)).to(self.device)
-            emb = self._speaker_model.embed_segments(wav_dev, st, ln, int(fl))
-            out.index_copy_(0, idx_t, emb)
+            out = torch.empty(hi - lo, 192, dtype=torch.float32, device=self.device)
+        # one upload per array and scale; the per-length groups below are device-side index_selects
+        dev_arrays = plan.get("_dev")
+        if dev_arrays is None or dev_arrays[0].device != self.device:
+            dev_arrays = plan["_dev"] = tuple(torch.from_numpy(np.ascontiguousarray(plan[k].astype(np.int32))).to(self.device)
+                                              for k in ("start", "len", "row0"))
+        st_all, ln_all, r0_all = dev_arrays
+        uniq_fixed = np.unique(fixed[lo:hi])
+        for fl in uniq_fixed:
+            if len(uniq_fixed) == 1:
+                st, ln, r0, idx_t = st_all[lo:hi], ln_all[lo:hi], r0_all[lo:hi], None
+            else:
+                idx_t = torch.from_numpy(lo + np.nonzero(fixed[lo:hi] == fl)[0]).to(self.device)
+                st, ln, r0 = st_all.index_select(0, idx_t), ln_all.index_select(0, idx_t), r0_all.index_select(0, idx_t)
+            emb = self._speaker_model.embed_segments(wav_dev, st, ln, int(fl), logmel=logmel, seg_row0=r0 if logmel is not None else None)
+            if idx_t is None:
+                out.copy_(emb)
+            else:
+                out.index_copy_(0, idx_t - lo, emb)
+        if self.shard_windows:
+            from . import sharding
+
+            return sharding.all_gather_rows(out, n)
         return out
+
+    def _mel_streams(self, wav_dev: torch.Tensor):
+        """The recording's log-mel frames, each computed once (b200d_mel_stream); None when no window lies on a stream."""
+        stream_start, stream_off = self._streams
+        if stream_start.size == 0 or os.environ.get("B200D_NO_MEL_STREAMS") == "1":
+            return None
+        dev = getattr(self, "_streams_dev", None)
+        if dev is None or dev[0].device != self.device or dev[2] is not self._streams:
+            dev = self._streams_dev = (torch.from_numpy(stream_start).to(self.device), torch.from_numpy(stream_off).to(self.device), self._streams)
+        return self._speaker_model.mel_stream(wav_dev, dev[0], dev[1], int(stream_off[-1]))
 
     def _embed_all_scales(self, wav_dev: torch.Tensor) -> Dict[int, torch.Tensor]:
         """Embeddings of every scale.  B200D_EMBED_STREAMS > 1 keeps several scales in flight on separate streams (own
         activation workspaces); off by default: the multi-stream region has to give up the CTA-pair GEMM (see
         _cabi.single_cta_gemms), which costs more than the overlap wins."""
         n_streams = min(len(self._scales), max(1, int(os.environ.get("B200D_EMBED_STREAMS", "1"))))
+        logmel = self._mel_streams(wav_dev)
         if n_streams <= 1 or self.shard_windows:
-            return {k: self._extract_embeddings(plan, wav_dev) for k, plan in self._scales.items()}
+            return {k: self._extract_embeddings(plan, wav_dev, logmel) for k, plan in self._scales.items()}
         from concurrent.futures import ThreadPoolExecutor
 
         main = torch.cuda.current_stream()
@@ -252,15 +324,15 @@ class ClusteringDiarizer:
             torch.cuda.set_device(dev_index)
             st = free.pop()  # list.pop / append are atomic under the GIL; at most n_streams workers run
             try:
-                with torch.cuda.stream(st), torch.no_grad():
-                    out = self._extract_embeddings(plan, wav_dev)
+                with torch.cuda.stream(st), torch.no_grad(), _cabi.single_cta_gemms():
+                    out = self._extract_embeddings(plan, wav_dev, logmel)
                     out.record_stream(main)
                     return scale_idx, out
             finally:
                 free.append(st)
 
         main.synchronize()
-        with _cabi.single_cta_gemms(), _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+        with _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
             results = dict(f.result() for f in [pool.submit(work, k, plan) for k, plan in self._scales.items()])
             for st in streams:
                 st.synchronize()
@@ -342,7 +414,7 @@ class ClusteringDiarizer:
                 torch.cuda.set_device(dev_index)
                 st = free.pop()
                 try:
-                    with torch.cuda.stream(st), torch.no_grad():
+                    with torch.cuda.stream(st), torch.no_grad(), _cabi.single_cta_gemms():
                         labels, sc = self._cluster_one(uniq_id, self.embs_and_timestamps[uniq_id], chunk_streams=1)
                         labels.record_stream(main)
                         st.synchronize()
@@ -350,7 +422,7 @@ class ClusteringDiarizer:
                 finally:
                     free.append(st)
 
-            with _cabi.single_cta_gemms(), _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+            with _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
                 for uniq_id, res in [f.result() for f in [pool.submit(work, u) for u in todo]]:
                     pending[uniq_id] = res
         timer.stop(h)
@@ -418,29 +490,18 @@ class ClusteringDiarizer:
         self.AUDIO_RTTM_MAP = {uniq_id: {"audio_filepath": uniq_id + ".wav", "rttm_filepath": None, "offset": 0, "duration": None,
                                          "text": "-", "num_speakers": None, "uem_filepath": None, "ctm_filepath": None}}
         self._wav_offset = {uniq_id: (0, n)}
-        regions = su._merge_on_grid([[float(a), float(b)] for a, b in speech_regions], 5)
         total_s = n / self.sample_rate
-        self._scales = {}
-        for scale_idx, (window, shift) in self.multiscale_args_dict["scale_dict"].items():
-            entries = []
-            for a, b in regions:
-                a, b = max(a, 0.0), min(b, total_s)
-                if b <= a:
-                    continue
-                for start, dur in su.get_subsegments(offset=round(a, 5), window=window, shift=shift, duration=round(b - a, 5)):
-                    if dur > su.MIN_SUBSEGMENT_DURATION:
-                        entries.append({"audio_filepath": uniq_id + ".wav", "offset": start, "duration": dur, "label": "UNK", "uniq_id": uniq_id})
-            self._scales[scale_idx] = self._plan_scale(entries)
-        for plan in self._scales.values():
-            sel = np.arange(len(plan["uniq"]))
-            plan["rows"], plan["stamps"] = {}, {}
-            if len(sel):
-                plan["rows"][uniq_id] = sel
-                plan["stamps"][uniq_id] = torch.tensor([[plan["t0"][i], plan["t1"][i]] for i in sel])
+        regions = []
+        for a, b in su._merge_on_grid([[float(a), float(b)] for a, b in speech_regions], 5):
+            a, b = max(a, 0.0), min(b, total_s)
+            if b > a:
+                regions.append({"audio_filepath": uniq_id + ".wav", "offset": round(a, 5), "duration": round(b - a, 5), "label": "UNK", "uniq_id": uniq_id})
+        self._plan_windows(regions, write_manifests=False)
         if wav.is_cuda:
             wav_dev = wav.contiguous()
         else:
-            self._wav_host = wav.contiguous().pin_memory()
+            self._wav_host = _pinned_buffer(n)
+            self._wav_host.copy_(wav)
             wav_dev = None
         self.run_device(wav_dev=wav_dev)
         r = self.results[uniq_id]

@@ -265,14 +265,14 @@ class LongFormSpeakerClustering:
 
             def work(w, st):
                 torch.cuda.set_device(dev_index)
-                with torch.cuda.stream(st), torch.no_grad():
+                with torch.cuda.stream(st), torch.no_grad(), _cabi.single_cta_gemms():
                     merged_list, mapping_list = cluster_chunk(w, SpeakerClustering())
                     for m in merged_list:
                         m.record_stream(main)
                     return merged_list, mapping_list
 
             main.synchronize()  # nothing of the single-stream phase (CTA-pair GEMMs) may still be running
-            with _cabi.single_cta_gemms(), _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
+            with _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
                 futures = {w: pool.submit(work, w, streams[i % n_streams]) for i, w in enumerate(mine)}
                 for w, fut in futures.items():
                     per_chunk[w] = fut.result()

@@ -139,6 +139,44 @@ def segments_manifest_to_subsegments_manifest(segments_manifest_file: str, subse
     return entries
 
 
+def read_speech_regions(segments_manifest_file: str):
+    """Lines of a speech-region manifest (oracle VAD / external VAD / VAD output) -> list of dicts."""
+    out = []
+    with open(segments_manifest_file, "r") as src:
+        for raw in src:
+            raw = raw.strip()
+            if raw:
+                out.append(json.loads(raw))
+    return out
+
+
+def subsegment_arrays(offsets: np.ndarray, durations: np.ndarray, window: float, shift: float,
+                      min_subsegment_duration: float = MIN_SUBSEGMENT_DURATION):
+    """`get_subsegments` for all speech regions of a manifest at once (float64 numpy, the same IEEE operations in the same
+    order as the per-region Python loop, so every start / duration is bit-identical to it).
+    Returns (region index int64 [n], start float64 [n], duration float64 [n]) with windows <= min_subsegment_duration dropped."""
+    offsets, durations = np.asarray(offsets, dtype=np.float64), np.asarray(durations, dtype=np.float64)
+    base = np.ceil((durations - window) / shift)
+    count = np.where(base < 0, 1, base + 1).astype(np.int64)
+    region = np.repeat(np.arange(offsets.shape[0], dtype=np.int64), count)
+    first = np.cumsum(count) - count
+    k = np.arange(int(count.sum()), dtype=np.int64) - first[region]
+    start = np.where(k == 0, offsets[region], offsets[region] + k * shift)
+    stop = np.minimum(start + window, (offsets + durations)[region])
+    dur = stop - start
+    keep = dur > min_subsegment_duration
+    return region[keep], start[keep], dur[keep]
+
+
+def write_subsegments_manifest(path: str, regions: Sequence[dict], region_idx: np.ndarray, start: np.ndarray, dur: np.ndarray) -> None:
+    """`subsegments_scale<k>.json`, byte-identical to the json.dump lines of segments_manifest_to_subsegments_manifest."""
+    heads = [json.dumps(r["audio_filepath"]) for r in regions]
+    tails = [f', "label": {json.dumps(r["label"])}, "uniq_id": {json.dumps(r.get("uniq_id"))}}}\n' for r in regions]
+    with open(path, "w") as out:
+        out.write("".join(f'{{"audio_filepath": {heads[r]}, "offset": {o!r}, "duration": {d!r}{tails[r]}'
+                          for r, o, d in zip(region_idx.tolist(), start.tolist(), dur.tolist())))
+
+
 def get_embs_and_timestamps(multiscale_embeddings_and_timestamps: dict, multiscale_args_dict: dict) -> Dict[str, dict]:
     """{scale: (embeddings{uniq}, time_stamps{uniq})} -> per recording: concatenated embeddings (device),
     float32 timestamps, per-scale counts and the weight row."""
@@ -226,7 +264,10 @@ def read_wav(path: str, expected_sr: int = 16000) -> np.ndarray:
     (torchaudio.save) and int16 PCM as written by nemo_process.py:24-28 (pydub), like soundfile."""
     from scipy.io import wavfile
 
-    sr, data = wavfile.read(path)
+    try:
+        sr, data = wavfile.read(path, mmap=True)  # float32 files are copied once, straight into the caller's pinned buffer
+    except (ValueError, OSError):
+        sr, data = wavfile.read(path)
     if sr != expected_sr:
         raise ValueError(f"{path}: expected {expected_sr} Hz audio, got {sr}")
     if data.ndim > 1:
@@ -237,4 +278,4 @@ def read_wav(path: str, expected_sr: int = 16000) -> np.ndarray:
         data = data.astype(np.float32) / 2147483648.0
     elif data.dtype == np.uint8:
         data = (data.astype(np.float32) - 128.0) / 128.0
-    return np.ascontiguousarray(data, dtype=np.float32)
+    return data if data.dtype == np.float32 else np.ascontiguousarray(data, dtype=np.float32)

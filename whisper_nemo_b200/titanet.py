@@ -215,22 +215,77 @@ def gemm(A, W, out, mode, M=None, bias=None, scale=None, shift=None, rowvec=None
     epi.shift = shift.data_ptr() if shift is not None else None
     epi.rowvec = rowvec.data_ptr() if rowvec is not None else None
     epi.aux16 = aux16.data_ptr() if aux16 is not None else None
+    epi.flags = _cabi.gemm_flags()
     _cabi.call("b200d_gemm_f16", ptr(A), A.stride(0), ptr(W), W.stride(0), M, N, K, ptr(out), out.stride(0), byref(epi), _cabi._stream())
     return out
 
 
 def featurize(pk: PackedTitaNet, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int,
-              out16: torch.Tensor = None, want_f32: bool = False):
-    """wav float32 [n] on device; seg_start / seg_len int32 [n_seg] on device.  Returns
-    (fp16 [n_seg*T, 128], optional float32 [n_seg, T, 80])."""
+              out16: torch.Tensor = None, want_f32: bool = False, logmel: torch.Tensor = None, seg_row0: torch.Tensor = None):
+    """wav float32 [n] on device; seg_start / seg_len int32 [n_seg] on device.  `logmel` / `seg_row0`: the recording's
+    stream frames (mel_stream) and each segment's first row in them -- interior frames are then copied, not recomputed.
+    Returns (fp16 [n_seg*T, 128], optional float32 [n_seg, T, 80])."""
     n_seg = seg_start.numel()
     T = frames_of(fixed_len)
     if out16 is None:
         out16 = torch.empty(n_seg * T, FEAT_PAD, dtype=torch.float16, device=wav.device)
     out32 = torch.empty(n_seg, T, FEAT, dtype=torch.float32, device=wav.device) if want_f32 else None
-    _cabi.call("b200d_featurize", ptr(wav), wav.numel(), ptr(seg_start), ptr(seg_len), n_seg, fixed_len, ptr(pk.fb_start), ptr(pk.fb_off),
-               ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), FEATURIZER_VARIANT, ptr(out16), out16.stride(0), ptr(out32), _cabi._stream())
+    if logmel is None or seg_row0 is None:
+        logmel = seg_row0 = None
+    _cabi.call("b200d_featurize_windows", ptr(wav), wav.numel(), ptr(logmel), ptr(seg_start), ptr(seg_len), ptr(seg_row0), n_seg, fixed_len,
+               ptr(pk.fb_start), ptr(pk.fb_off), ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), FEATURIZER_VARIANT, ptr(out16), out16.stride(0),
+               ptr(out32), _cabi._stream())
     return out16, out32
+
+
+STREAM_PAD = 32  # rows of a stream are padded to the 32 frames one CTA of mel_stream_kernel computes
+
+
+def plan_mel_streams(start: np.ndarray, length: np.ndarray, fixed: np.ndarray):
+    """Host plan of the once-per-recording frames.  start / length / fixed: int64 [n] first sample (in the concatenated
+    waveform), true length and tiled-up length of every window of every scale.
+    Windows that fill their fixed length and share a grid phase (start mod 160) are chained into STREAMS wherever they
+    overlap or touch; frame g of a stream is centred on sample stream_start + 160 g.
+    Returns (stream_start int64 [S], stream_off int32 [S + 1] (rows, multiples of 32), row0 int32 [n]: the row of the frame
+    centred on each window's first sample, -1 for windows without a stream (tiled ones))."""
+    start, length, fixed = (np.asarray(a, dtype=np.int64) for a in (start, length, fixed))
+    row0 = np.full(start.shape[0], -1, dtype=np.int64)
+    full = np.nonzero(length == fixed)[0]
+    s_start, s_rows = [], []
+    rows_total = 0
+    phase = start[full] % HOP
+    for ph in np.unique(phase):
+        idx = full[phase == ph]
+        idx = idx[np.argsort(start[idx], kind="stable")]
+        s, e = start[idx], start[idx] + fixed[idx]
+        reach = np.maximum.accumulate(e)
+        first = np.concatenate([[True], s[1:] > reach[:-1]])  # a window beyond everything seen so far opens a new stream
+        gid = np.cumsum(first) - 1
+        a = s[first]
+        last = np.concatenate([first[1:], [True]])
+        rows = (reach[last] - a) // HOP + 1
+        rows = (rows + STREAM_PAD - 1) // STREAM_PAD * STREAM_PAD
+        off = rows_total + np.concatenate([[0], np.cumsum(rows)[:-1]])
+        row0[idx] = off[gid] + (s - a[gid]) // HOP
+        s_start.append(a)
+        s_rows.append(rows)
+        rows_total += int(rows.sum())
+    if not s_start:
+        return np.zeros(0, np.int64), np.zeros(1, np.int32), row0.astype(np.int32)
+    s_start, s_rows = np.concatenate(s_start), np.concatenate(s_rows)
+    stream_off = np.concatenate([[0], np.cumsum(s_rows)])
+    if stream_off[-1] >= 2 ** 31:
+        raise ValueError("more than 2^31 stream frames; split the batch")
+    return s_start.astype(np.int64), stream_off.astype(np.int32), row0.astype(np.int32)
+
+
+def mel_stream(pk: PackedTitaNet, wav: torch.Tensor, stream_start: torch.Tensor, stream_off: torch.Tensor, total_rows: int, out: torch.Tensor = None):
+    """log-mel rows float32 [total_rows, 80] of the planned streams (device arrays from plan_mel_streams)."""
+    if out is None:
+        out = torch.empty(total_rows, FEAT, dtype=torch.float32, device=wav.device)
+    _cabi.call("b200d_mel_stream", ptr(wav), wav.numel(), ptr(stream_start), ptr(stream_off), stream_start.numel(), total_rows,
+               ptr(pk.fb_start), ptr(pk.fb_off), ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), ptr(out), _cabi._stream())
+    return out
 
 
 class Workspace:
@@ -322,37 +377,110 @@ def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: d
     return emb[:, :EMB]
 
 
+def pack_weights_cabi(state_dict: Dict[str, torch.Tensor], device="cuda"):
+    """b200d_titanet_pack_weights: the same folding / padding / fp16 conversion as `pack_weights`, done by the library (C++, host)
+    into ONE position-independent blob.  Returns (TitaNetDesc, uint8 tensor on `device`)."""
+    import ctypes
+
+    sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()
+          if torch.is_tensor(v) and v.dtype.is_floating_point}
+    if "preprocessor.featurizer.fb" not in sd:  # NeMo checkpoints carry both buffers; the seeded random init does not
+        sd["preprocessor.featurizer.fb"] = torch.from_numpy(slaney_mel_filterbank()).unsqueeze(0).contiguous()
+    if "preprocessor.featurizer.window" not in sd:
+        sd["preprocessor.featurizer.window"] = torch.hann_window(WIN, periodic=False, dtype=torch.float64).float()
+    names = list(sd)
+    n = len(names)
+    c_names = (ctypes.c_char_p * n)(*[k.encode() for k in names])
+    c_data = (ctypes.c_void_p * n)(*[sd[k].data_ptr() for k in names])
+    c_numel = (ctypes.c_int64 * n)(*[sd[k].numel() for k in names])
+    desc = _cabi.TitaNetDesc()
+    lib = _cabi.load()
+    _cabi.check(lib.b200d_titanet_pack_weights(n, c_names, c_data, c_numel, ctypes.byref(desc), None, 0), "b200d_titanet_pack_weights")
+    blob = torch.empty(int(desc.packed_bytes), dtype=torch.uint8)
+    _cabi.check(lib.b200d_titanet_pack_weights(n, c_names, c_data, c_numel, ctypes.byref(desc), blob.data_ptr(), blob.numel()), "b200d_titanet_pack_weights")
+    return desc, blob.to(device)
+
+
 class TitaNetB200:
     """Speaker-embedding extractor: `embed_segments` is the device-side replacement of the
-    `_extract_embeddings` dataloader loop of upstream ClusteringDiarizer."""
+    `_extract_embeddings` dataloader loop of upstream ClusteringDiarizer -- one `b200d_titanet_forward` call per
+    (scale, window length): the ~60 kernels per group of windows are launched from C++."""
 
     def __init__(self, state_dict, device="cuda", max_frames: int = None):
         _cabi.require_device()
         if max_frames is None:  # frames per launch group: ~21 KB of fp16 activations per frame (2.7 GB at the default)
             max_frames = int(os.environ.get("B200D_MAX_FRAMES", 131072))
         self.device = torch.device(device)
-        self.pk = pack_weights(state_dict, self.device)
+        self._state_dict = state_dict
+        self._pk = None
+        self.desc, self.packed = pack_weights_cabi(state_dict, self.device)
         self.max_frames = max_frames
-        self._ws = {}  # one activation workspace per launching stream (concurrent scales must not share buffers)
+        self._ws = {}   # one activation workspace per launching stream (concurrent scales must not share buffers)
+        self._pyws = {}
 
-    def _workspace(self, T):
+    @property
+    def pk(self) -> PackedTitaNet:
+        """The Python-side packing (per-operand tensors): only the step-by-step reference orchestration (`forward_frames`,
+        `featurize`, taps for the tests) uses it; the product path reads the library's blob."""
+        if self._pk is None:
+            self._pk = pack_weights(self._state_dict, self.device)
+        return self._pk
+
+    def _workspace(self):
         key = torch.cuda.current_stream().cuda_stream
-        max_segs = max(1, self.max_frames // T)
         ws = self._ws.get(key)
-        if ws is None or ws.max_segs < max_segs:
-            ws = self._ws[key] = Workspace(self.max_frames, max(max_segs, 1024), self.device)
+        if ws is None:
+            import ctypes
+
+            nbytes = _cabi.load().b200d_titanet_workspace_bytes(ctypes.byref(self.desc), self.max_frames, max(1024, self.max_frames // 32))
+            ws = self._ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return ws
 
+    def mel_stream(self, wav: torch.Tensor, stream_start: torch.Tensor, stream_off: torch.Tensor, total_rows: int) -> torch.Tensor:
+        """log-mel rows float32 [total_rows, 80] of the planned streams (plan_mel_streams), each frame computed once."""
+        import ctypes
+
+        out = torch.empty(total_rows, FEAT, dtype=torch.float32, device=wav.device)
+        _cabi.call("b200d_titanet_mel_stream", ctypes.byref(self.desc), ptr(self.packed), ptr(wav), wav.numel(), ptr(stream_start), ptr(stream_off),
+                   stream_start.numel(), total_rows, ptr(out), _cabi._stream())
+        return out
+
     @torch.no_grad()
-    def embed_segments(self, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int, taps: dict = None):
-        """All segments share `fixed_len` (batch max under fixed_seq collate).  Returns float32 [n_seg, 192]."""
+    def embed_segments(self, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int, taps: dict = None,
+                       logmel: torch.Tensor = None, seg_row0: torch.Tensor = None):
+        """All segments share `fixed_len` (batch max under fixed_seq collate).  `logmel` / `seg_row0`: see featurize.
+        Returns float32 [n_seg, 192].  `taps` (a dict) selects the step-by-step reference orchestration and receives the
+        intermediate activations."""
+        if taps is not None:
+            return self._embed_segments_stepwise(wav, seg_start, seg_len, fixed_len, taps, logmel, seg_row0)
+        import ctypes
+
+        n_seg = seg_start.numel()
+        out = torch.empty(n_seg, EMB, dtype=torch.float32, device=self.device)
+        if logmel is None or seg_row0 is None:
+            logmel = seg_row0 = None
+        ws = self._workspace()
+        _cabi.call("b200d_titanet_forward", ctypes.byref(self.desc), ptr(self.packed), ptr(wav), wav.numel(), ptr(logmel), ptr(seg_start), ptr(seg_len),
+                   ptr(seg_row0), n_seg, fixed_len, FEATURIZER_VARIANT, _cabi.gemm_flags(), ptr(out), out.stride(0), ptr(ws), ws.numel(), _cabi._stream())
+        return out
+
+    def _py_workspace(self, T):
+        key = torch.cuda.current_stream().cuda_stream
+        max_segs = max(1, self.max_frames // T)
+        ws = self._pyws.get(key)
+        if ws is None or ws.max_segs < max_segs:
+            ws = self._pyws[key] = Workspace(self.max_frames, max(max_segs, 1024), self.device)
+        return ws
+
+    def _embed_segments_stepwise(self, wav, seg_start, seg_len, fixed_len, taps, logmel=None, seg_row0=None):
         n_seg = seg_start.numel()
         T = frames_of(fixed_len)
-        ws = self._workspace(T)
+        ws = self._py_workspace(T)
         segs_per_chunk = max(1, self.max_frames // T)
         out = torch.empty(n_seg, EMB, dtype=torch.float32, device=self.device)
         for c0 in range(0, n_seg, segs_per_chunk):
             c1 = min(n_seg, c0 + segs_per_chunk)
-            featurize(self.pk, wav, seg_start[c0:c1], seg_len[c0:c1], fixed_len, out16=ws.x0)
+            featurize(self.pk, wav, seg_start[c0:c1], seg_len[c0:c1], fixed_len, out16=ws.x0, logmel=logmel,
+                      seg_row0=None if seg_row0 is None else seg_row0[c0:c1])
             out[c0:c1] = forward_frames(self.pk, ws, c1 - c0, T, taps)
         return out
