@@ -63,13 +63,9 @@ int b200d_check_device(void);
  *               ParakeetFeatureExtractor port): constant-zero padding of the pre-emphasised window, no "+ 1"
  *  out_f16      __half  [n_seg*T][ldo]  channels-last, channels 80..ldo-1 zeroed (ldo >= 80, ldo % 8 == 0)
  *  out_f32      float32 [n_seg][T][80] or NULL (parity taps)
+ *  (these are the arguments of b200d_featurize_windows below; there is no separate per-window entry point)
  * ------------------------------------------------------------------------------------------ */
-int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, const int32_t* seg_len,
-                    int32_t n_seg, int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off,
-                    const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant,
-                    void* out_f16, int32_t ldo, float* out_f32, void* stream);
-
-/* The same featurizer with every 10-ms frame computed ONCE per recording instead of once per window (windows of all scales
+/* Every 10-ms frame is computed ONCE per recording instead of once per window (windows of all scales
  * overlap: upstream recomputes each STFT frame ~10 times).  A frame in the interior of a window depends only on where its 400
  * samples lie, not on the window, so:
  *   b200d_mel_stream         log(mel + 2^-24) of the frames of `n_streams` STREAMS: stream s holds the frames centred on samples
@@ -77,19 +73,21 @@ int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, c
  *                            logmel float32 [total_rows][80].  stream_off[] are multiples of 32 (pad each stream's frame count;
  *                            padding rows are computed from whatever samples lie there and never used).  Samples outside
  *                            [0, n_wav) read as 0.  stream_start int64 [n_streams], stream_off int32 [n_streams + 1] (device).
- *   b200d_featurize_windows  b200d_featurize with seg_row0 int32 [n_seg]: the row in `logmel` of the stream frame centred on the
+ *   b200d_featurize_windows  the featurizer above, with seg_row0 int32 [n_seg]: the row in `logmel` of the stream frame centred on the
  *                            segment's first sample (the host plans streams so that every full-length window starts on a frame of
  *                            one), or < 0.  Segments with seg_row0 >= 0 and seg_len == fixed_len copy their interior frames
  *                            (t*160 - 201 >= 0 and t*160 + 200 <= fixed_len) from the stream and compute only the two frames at
  *                            each end (reflect / zero padding, first-sample pre-emphasis); all others compute every frame.
- *                            logmel == NULL and seg_row0 == NULL together: every segment takes the generic path (== b200d_featurize). */
+ *                            logmel == NULL and seg_row0 == NULL together: every segment takes the generic path.
+ *                            scratch float32 [n_seg][T][80]: un-normalised log-mel of the frames computed per window (two
+ *                            kernels: frames spread over the chip one warp each, then one CTA per window gathers + normalises). */
 int b200d_mel_stream(const float* wav, int64_t n_wav, const int64_t* stream_start, const int32_t* stream_off, int32_t n_streams,
                      int32_t total_rows, const int32_t* fb_start, const int32_t* fb_off, const float* fb_w, int32_t fb_nnz,
                      const float* window, float* logmel, void* stream);
 int b200d_featurize_windows(const float* wav, int64_t n_wav, const float* logmel, const int32_t* seg_start, const int32_t* seg_len,
                             const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off,
-                            const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant, void* out_f16, int32_t ldo,
-                            float* out_f32, void* stream);
+                            const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant, float* scratch, void* out_f16,
+                            int32_t ldo, float* out_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * TitaNet-L building blocks (nemo/collections/asr/parts/submodules/jasper.py JasperBlock,
@@ -145,6 +143,10 @@ typedef struct b200d_gemm_epilogue {
   void* vt;               /* __nv_bfloat16 [N][ldvt] */
   int32_t ldvt;
   int32_t flags;          /* B200D_GEMM_* bits, 0 = default kernel choice */
+  float* colsum;          /* B200D_EPI_BIAS on the CTA-pair kernel only, else must be NULL: float32 [ceil(M / 32)][2][N] partial
+                             column sums of the fp16-rounded output over each group of 32 rows -- [g][0] the rows of the window
+                             (rows_per_seg >= 32 rows each) that row 32 g belongs to, [g][1] the rows of the next window; reduced
+                             to per-window means by b200d_se_mean_from_colsum (SqueezeExcite's pool without re-reading the output) */
 } b200d_gemm_epilogue;
 
 /* Kernel choice is a PER-CALL property (no process-wide state): large GEMMs run on a cluster-launched CTA-pair kernel
@@ -157,6 +159,10 @@ int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32
                    void* out, int32_t ldo, const b200d_gemm_epilogue* epi, void* stream);
 /* SqueezeExcite = b200d_time_stats(with_std=0) -> b200d_gemm_f16(fc.0, BIAS_RELU with zero bias)
  * -> b200d_gemm_f16(fc.2, SIGMOID_F32) -> gate float32 [n_seg][C].                                 */
+
+/* mean16 __half [n_seg][C] = per-window time mean from the colsum partials a B200D_EPI_BIAS GEMM left behind
+ * (== b200d_time_stats(with_std = 0) of that GEMM's output up to fp32 summation order).  colsum float32 [ceil(n_seg*T/32)][2][C]. */
+int b200d_se_mean_from_colsum(const float* colsum, int32_t n_seg, int32_t T, int32_t C, void* mean16, void* stream);
 
 /* y = relu(x * gate[seg]) elementwise (block without residual: B0, B4).  x,y __half [n_seg*T][C] */
 int b200d_se_apply_relu(const void* x, const float* gate, void* y, int32_t n_seg, int32_t T, int32_t C, void* stream);
@@ -186,7 +192,7 @@ int b200d_attn_pool(const void* x, const void* e, int32_t n_seg, int32_t T, int3
  *   host arrays in upstream's layouts, numel[i] their element counts (all shapes follow from them).  Writes the folded /
  *   padded / fp16 operands into packed_host (position independent: copy it to the device as is, 256-byte aligned) and the
  *   byte offset of every operand into *desc.  packed_host == NULL: only fills *desc (desc->packed_bytes is the size needed).
- * b200d_titanet_forward: embeddings of n_seg windows that all share fixed_len (see b200d_featurize for wav / seg_* / variant,
+ * b200d_titanet_forward: embeddings of n_seg windows that all share fixed_len (see the featurizer section for wav / seg_* / variant,
  *   b200d_featurize_windows for logmel / seg_row0, both may be NULL).  Windows are processed in groups that fit `ws`
  *   (b200d_titanet_workspace_bytes(desc, max_frames, max_segs) holds groups of max_segs windows / max_frames frames; any
  *   size that holds one window works).  emb_out float32 [n_seg][ld_emb], first desc->emb columns written.  flags: B200D_GEMM_*.

@@ -149,6 +149,15 @@ class OracleClusteringDiarizer:
             self.multiscale_embeddings_and_timestamps[scale_idx] = ({u: torch.cat(v) for u, v in embeddings.items()}, time_stamps)
         self.embs_and_timestamps = su.get_embs_and_timestamps(self.multiscale_embeddings_and_timestamps, self.multiscale_args_dict)
         self._sigs, self._embs = {}, {}
+        if _get(self.cfg, "diarizer.speaker_embeddings.parameters.save_embeddings", False):
+            # upstream _extract_embeddings: {uniq_id: [n, 192]} per scale, read back by the MSDD stage
+            import pickle as pkl
+
+            emb_dir = os.path.join(self.speaker_dir, "embeddings")
+            os.makedirs(emb_dir, exist_ok=True)
+            for scale_idx, (embeddings, _) in self.multiscale_embeddings_and_timestamps.items():
+                with open(os.path.join(emb_dir, f"subsegments_scale{scale_idx}_embeddings.pkl"), "wb") as f:
+                    pkl.dump(embeddings, f)
 
     def embed(self):
         t0 = time.perf_counter()

@@ -245,6 +245,16 @@ def _gloo_worker(rank, world, port, tmp):
         dist.all_gather_object(out, {i: f"labels-of-{i}" for i in mine})
         merged = {k: v for part in out for k, v in part.items()}
         assert sorted(merged) == list(range(len(dur)))
+        # long-form chunks dealt round-robin; every rank ends with every chunk's (labels, mass), bit for bit
+        n_chunks, m_chunk = 5, 1000
+        lens = [1000, 1000, 1000, 1000, 337]
+        g = torch.Generator().manual_seed(7)
+        truth = {w: (torch.randint(0, 50, (lens[w],), generator=g, dtype=torch.int32), torch.rand(lens[w], generator=g)) for w in range(n_chunks)}
+        mine_chunks = sharding.chunks_of_rank(n_chunks, rank, world)
+        assert sorted(sum((sharding.chunks_of_rank(n_chunks, r, world) for r in range(world)), [])) == list(range(n_chunks))
+        got = sharding.all_gather_chunk_results({w: truth[w] for w in mine_chunks}, n_chunks, m_chunk, lens)
+        for w in range(n_chunks):
+            assert torch.equal(got[w][0], truth[w][0]) and torch.equal(got[w][1], truth[w][1])
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -99,7 +99,7 @@ def test_featurizer_once_per_recording_frames(dev, oracle_model, weights, window
     length = (dur_s * 16000).astype(np.int64)
     fixed = np.full_like(length, int(length.max()))
     stream_start, stream_off, row0 = tn.plan_mel_streams(start, length, fixed)
-    assert (row0 >= 0).sum() >= len(start) - 2 and (row0 < 0).sum() >= 1
+    assert (row0 >= 0).sum() >= len(start) - 6 and (row0 < 0).sum() >= 1
     pk = tn.pack_weights(weights, dev)
     wav_d = wav_t.to(dev)
     to32 = lambda a: torch.from_numpy(a.astype(np.int32)).to(dev)
@@ -533,6 +533,55 @@ def test_in_memory_waveform_api_matches_file_path(dev, weights, tmp_path):
     for source in (torch.from_numpy(wav), torch.from_numpy(wav).to(dev)):
         mem_ts = ClusteringDiarizer(cfg=cfg, speaker_model=weights).diarize_waveform(source, regions)
         assert mem_ts == file_ts
+
+
+def test_neural_diarizer_wrapper_and_msdd_handoff_files(dev, oracle_model, weights, tmp_path):
+    """The reference's literal call -- NeuralDiarizer(cfg=create_config(dir)).to(device).diarize() (diarize.py:200-201) --
+    through the B200 wrapper, and the files NeMo's MSDD stage reads afterwards against the oracle's: the per-scale
+    subsegments_scale<k>.json byte for byte, the base-scale cluster.label identical, the embedding pickles with the same
+    keys / shapes and within 1e-3 cosine."""
+    import pickle as pkl
+    import shutil
+    import warnings
+
+    import whisper_nemo_b200 as pkg
+    from oracle.clustering_diarizer import OracleClusteringDiarizer
+
+    ref_dir = tmp_path / "oracle"
+    cfg_o, wav, turns = make_session_cfg(ref_dir, "telephonic", 60.0, 2, seed=21)
+    assert cfg_o.diarizer.speaker_embeddings.parameters.save_embeddings is True
+    state = torch.get_rng_state()
+    oracle = OracleClusteringDiarizer(cfg_o, oracle_model)
+    oracle.diarize()
+    torch.set_rng_state(state)
+    # the reference's helpers.create_config as is (oracle_vad False, MarbleNet named): speech regions come from a vad_fn
+    out = tmp_path / "b200"
+    os.makedirs(out)
+    shutil.copy(ref_dir / "mono_file.wav", out / "mono_file.wav")
+    cfg = pkg.create_config(str(out), "telephonic")
+    assert cfg.diarizer.oracle_vad is False and cfg.diarizer.vad.model_path == "vad_multilingual_marblenet"
+    cfg.diarizer.speaker_embeddings.model_path = "titanet_large_random"
+    regions = [(a, b) for a, b, _ in turns]
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        nd = pkg.NeuralDiarizer(cfg=cfg, vad_fn=lambda uniq_id, samples: regions).to("cuda")
+        assert nd.diarize() is None
+    assert nd.msdd_refinement_skipped and any("MSDD" in str(w.message) for w in caught)
+    so_o, so_g = ref_dir / "speaker_outputs", out / "speaker_outputs"
+    n_scales = 5
+    for k in range(n_scales):
+        a = (so_o / f"subsegments_scale{k}.json").read_text().replace(str(ref_dir), "")
+        b = (so_g / f"subsegments_scale{k}.json").read_text().replace(str(out), "")
+        assert a == b, f"subsegments_scale{k}.json differs"
+        with open(so_o / "embeddings" / f"subsegments_scale{k}_embeddings.pkl", "rb") as f:
+            eo = pkl.load(f)
+        with open(so_g / "embeddings" / f"subsegments_scale{k}_embeddings.pkl", "rb") as f:
+            eg = pkl.load(f)
+        assert list(eo) == list(eg) == ["mono_file"] and eo["mono_file"].shape == eg["mono_file"].shape
+        cos = torch.nn.functional.cosine_similarity(eo["mono_file"], eg["mono_file"].float(), dim=1)
+        assert (1 - cos).max().item() <= 1e-3
+    assert (so_o / f"subsegments_scale{n_scales - 1}_cluster.label").read_text() == (so_g / f"subsegments_scale{n_scales - 1}_cluster.label").read_text()
+    assert rttm_der_between(str(ref_dir / "pred_rttms" / "mono_file.rttm"), str(out / "pred_rttms" / "mono_file.rttm")) == 0.0
 
 
 def test_fullsize_meeting_one_hour_matches_oracle(dev, oracle_model, weights, tmp_path):

@@ -54,12 +54,15 @@ def main():
 
         t0 = time.time()
         gen = torch.Generator().manual_seed(0)
-        runs = {"b200": r["labels"], "oracle32": oracle(emb), "oracle64": oracle(emb, True),
-                "oracle32_pert": oracle(emb * (1.0 + 3e-3 * torch.randn(emb.shape, generator=gen)))}
+        runs = {"b200": r["labels"], "oracle32": oracle(emb)}
+        if os.environ.get("STABILITY_FP64", "0") == "1":
+            runs["oracle64"] = oracle(emb, True)
+        for i in range(int(os.environ.get("STABILITY_PERTURBATIONS", "2"))):
+            runs[f"oracle32_pert{i}"] = oracle(emb * (1.0 + 3e-3 * torch.randn(emb.shape, generator=gen)))
         ag = workload.best_permutation_agreement
         print(f"{case}: N={len(mid)} " + " ".join(f"{k}: k={len(set(v.tolist()))} purity={ag(v[ok], truth[ok]):.4f}" for k, v in runs.items()) +
               " | agreement with oracle32: " + " ".join(f"{k}={ag(v, runs['oracle32']):.5f}" for k, v in runs.items() if k != "oracle32") +
-              f" | b200 vs oracle64 {ag(runs['b200'], runs['oracle64']):.5f} ({time.time() - t0:.0f} s of oracle)", flush=True)
+              f" ({time.time() - t0:.0f} s of oracle)", flush=True)
 
 
 if __name__ == "__main__":

@@ -11,8 +11,8 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # torch / CUDA are only touched when the diarizer is actually requested
-    if name == "ClusteringDiarizer":
-        from .diarizer import ClusteringDiarizer
+    if name in ("ClusteringDiarizer", "NeuralDiarizer"):
+        from . import diarizer
 
-        return ClusteringDiarizer
+        return getattr(diarizer, name)
     raise AttributeError(name)

@@ -37,6 +37,7 @@ class GemmEpilogue(Structure):
         ("vt", c_void_p),
         ("ldvt", c_int32),
         ("flags", c_int32),
+        ("colsum", c_void_p),
     ]
 
 
@@ -79,12 +80,10 @@ _SIGNATURES = {
     "b200d_version": (c_char_p, []),
     "b200d_last_error": (c_char_p, []),
     "b200d_check_device": (c_int32, []),
-    "b200d_featurize": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
-                                  c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_mel_stream": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                    c_void_p]),
     "b200d_featurize_windows": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                          c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+                                          c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_depthwise_conv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                  POINTER(GemmEpilogue), c_void_p]),
@@ -101,6 +100,7 @@ _SIGNATURES = {
     "b200d_profile_start": (c_int32, []),
     "b200d_profile_stop": (c_int32, [POINTER(ProfileSpan), c_int32, POINTER(c_int32)]),
     "b200d_time_stats": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "b200d_se_mean_from_colsum": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_se_apply_relu": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_se_apply_relu_stats": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b200d_attn_pool": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
@@ -189,13 +189,13 @@ def check(rc, name):
 
 # kernels launched per C-ABI call (bench.py's gpu_launches claim is the sum over the timed region)
 KERNELS_PER_CALL = {
-    "b200d_featurize": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_apply_relu": 1, "b200d_se_apply_relu_stats": 1,
+    "b200d_featurize_windows": 2, "b200d_mel_stream": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_mean_from_colsum": 1, "b200d_se_apply_relu": 1, "b200d_se_apply_relu_stats": 1,
     "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
     "b200d_masked_rowsum": 1, "b200d_gather_segment_mean": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
     "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
     "b200d_resid_norms": 2, "b200d_kmeans": 1, "b200d_csr_from_dense": 3, "b200d_spmm_cheb": 1,
 }
-COMPOSITES = ("b200d_titanet_forward", "b200d_eig_bottomk")  # many kernels per call: counted by the library (b200d_launch_count)
+COMPOSITES = ("b200d_titanet_forward", "b200d_eig_bottomk", "b200d_titanet_mel_stream")  # many kernels per call: counted by the library (b200d_launch_count)
 launch_count = 0
 _pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None
 _profile = None  # {name: [(event0, event1, work, stream)]} while a profiled step runs
@@ -262,7 +262,7 @@ def call(name, *args):
             M, N, mode = args[4], args[5], args[9]._obj.mode
             work = 2.0 * M * N * args[6]
             # same rule as b200d_gemm_f16's dispatch (gemm_tcgen05.cu): which launches run the CTA-pair kernel
-            pair = _pair_kernel_on and not (args[9]._obj.flags & GEMM_NO_PAIR) and ((N == 192 and M >= 4096) if mode == EPI_CHEB else (N % 256 == 0 and -(-M // 256) * (N // 256) >= 74))
+            pair = gemm_uses_pair(M, N, mode, args[9]._obj.flags)
             key = f"{name}[{_EPI_NAMES[mode]}{'|2cta' if pair else ''}]"
         elif name == "b200d_small_eig":
             key = f"{name}[{'cholesky' if args[4] else 'jacobi'} b={args[1]}]"
@@ -296,6 +296,15 @@ class short_gil_switch:
 
 
 _tls = threading.local()
+
+
+def gemm_uses_pair(M: int, N: int, mode: int, flags: int) -> bool:
+    """The dispatch rule of b200d_gemm_f16 (gemm_tcgen05.cu gemm_uses_pair_kernel): which launches run the CTA-pair kernel."""
+    if not _pair_kernel_on or (flags & GEMM_NO_PAIR):
+        return False
+    if mode == EPI_CHEB:
+        return N == 192 and M >= 4096
+    return N % 256 == 0 and -(-M // 256) * (N // 256) >= 74
 
 
 def gemm_flags() -> int:

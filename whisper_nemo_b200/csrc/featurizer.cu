@@ -215,20 +215,42 @@ struct FeatParams {
   int T;
   int zero_pad;  // STFT padding of the (pre-emphasised) window: 0 = reflect (torch.stft's default), 1 = zeros
   FbTables tab;
+  float* scratch;        // [n_seg][T][80] un-normalised log-mel of the frames computed per window
   __half* out16;
   int ldo;
   float* out32;
 };
 
-__global__ void __launch_bounds__(kWinWarps * 32) featurize_windows_kernel(const FeatParams p) {
-  extern __shared__ float logmel[];  // [T][80] | per-warp spectrum scratch: kWinWarps x (256 float2 + 260 float)
-  __shared__ FbShared tabs;
-  __shared__ float s_mean[kMels], s_inv[kMels];
+// Interior frames of a window of F samples / T frames: support [t*160 - 200 - 1, t*160 + 200) inside [0, F) -- those are
+// identical to the stream's frames.  Empty range (lo > hi) when the window has no stream.
+__device__ __forceinline__ void interior_range(const FeatParams& p, int seg, int& t_lo, int& t_hi, int& row0) {
+  const int F = p.fixed_len;
+  row0 = (p.seg_row0 && p.logmel && p.seg_len[seg] >= F) ? p.seg_row0[seg] : -1;
+  t_lo = p.T;
+  t_hi = -1;
+  if (row0 >= 0) {
+    t_lo = (kWin / 2 + 1 + kHop - 1) / kHop;  // smallest t with t*160 - 201 >= 0  (= 2)
+    t_hi = (F - kWin / 2) / kHop;             // largest t with t*160 + 200 <= F
+    if (t_hi > p.T - 1) t_hi = p.T - 1;
+  }
+}
 
-  const int seg = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// Kernel 1: every frame that cannot be taken from a stream -- the 2 + 2 edge frames of a window on a stream, all T frames
+// of a window without one (tiled up by fixed_seq collate / off-grid) -- one warp per frame, spread over the whole chip
+// (grid: ceil(T / 8) x n_seg; CTAs whose 8 frames are all interior exit at once).  Un-normalised log-mel to `scratch`.
+__global__ void __launch_bounds__(kWinWarps * 32) window_frames_kernel(const FeatParams p) {
+  extern __shared__ float dyn[];  // per-warp spectrum scratch: kWinWarps x (256 float2 + 260 float)
+  __shared__ FbShared tabs;
+  const int seg = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t_lo, t_hi, row0;
+  interior_range(p, seg, t_lo, t_hi, row0);
+  const int tb0 = blockIdx.x * kWinWarps, tb1 = min(tb0 + kWinWarps, p.T) - 1;
+  if (tb0 >= t_lo && tb1 <= t_hi) return;
   load_tables(tabs, p.tab);
   __syncthreads();
+  const int t = tb0 + warp;
+  if (t >= p.T || (t >= t_lo && t <= t_hi)) return;
 
   const int F = p.fixed_len;
   const int len = p.seg_len[seg];
@@ -253,28 +275,28 @@ __global__ void __launch_bounds__(kWinWarps * 32) featurize_windows_kernel(const
     const float x0 = x_at(j);
     return j == 0 ? x0 : preemph(x0, x_at(j - 1));
   };
-
-  float* scratch = logmel + ((p.T * kMels + 3) & ~3) + warp * kWarpScratch;
   LaneTwiddles lt;
   lt.init(lane);
-  // interior frames [t_lo, t_hi]: support [t*160 - 200 - 1, t*160 + 200) inside [0, F) -- identical to the stream's frames
-  const int row0 = (p.seg_row0 && p.logmel && !tiled) ? p.seg_row0[seg] : -1;
-  int t_lo = p.T, t_hi = -1;
-  if (row0 >= 0) {
-    t_lo = (kWin / 2 + 1 + kHop - 1) / kHop;  // smallest t with t*160 - 201 >= 0  (= 2)
-    t_hi = (F - kWin / 2) / kHop;             // largest t with t*160 + 200 <= F
-    if (t_hi > p.T - 1) t_hi = p.T - 1;
-    const float4* srcm = reinterpret_cast<const float4*>(p.logmel + (static_cast<size_t>(row0) + t_lo) * kMels);
-    float4* dstm = reinterpret_cast<float4*>(logmel + t_lo * kMels);
-    const int n4 = (t_hi - t_lo + 1) * (kMels / 4);
-    for (int i = tid; i < n4; i += blockDim.x) dstm[i] = __ldg(srcm + i);
-  }
-  // the other frames (window edges, or every frame of a window without a stream)
-  const int n_int = t_hi >= t_lo ? t_hi - t_lo + 1 : 0;
-  for (int e = warp; e < p.T - n_int; e += kWinWarps) {
-    const int t = (n_int == 0 || e < t_lo) ? e : e + n_int;
-    const int base = t * kHop - kNFFT / 2;
-    frame_logmel(tabs, lt, scratch, lane, [&](int i) { return sample(base + i); }, logmel + t * kMels);
+  const int base = t * kHop - kNFFT / 2;
+  frame_logmel(tabs, lt, dyn + warp * kWarpScratch, lane, [&](int i) { return sample(base + i); },
+               p.scratch + (static_cast<size_t>(seg) * p.T + t) * kMels);
+}
+
+// Kernel 2: one CTA per window gathers its T frames (interior ones from the stream, the others from `scratch`), takes the
+// exact two-pass per-feature mean / unbiased std over the window and writes the normalised features.  Pure data movement.
+__global__ void __launch_bounds__(kWinWarps * 32) window_normalise_kernel(const FeatParams p) {
+  extern __shared__ float logmel[];  // [T][80]
+  __shared__ float s_mean[kMels], s_inv[kMels];
+  const int seg = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int t_lo, t_hi, row0;
+  interior_range(p, seg, t_lo, t_hi, row0);
+  {
+    const float4* own = reinterpret_cast<const float4*>(p.scratch + static_cast<size_t>(seg) * p.T * kMels);
+    const float4* shared = row0 >= 0 ? reinterpret_cast<const float4*>(p.logmel + static_cast<size_t>(row0) * kMels) : own;
+    float4* dst = reinterpret_cast<float4*>(logmel);
+    const int lo4 = t_lo * (kMels / 4), hi4 = (t_hi + 1) * (kMels / 4);
+    for (int i = tid; i < p.T * (kMels / 4); i += blockDim.x) dst[i] = __ldg(((i >= lo4 && i < hi4) ? shared : own) + i);
   }
   __syncthreads();
 
@@ -344,10 +366,10 @@ extern "C" int b200d_mel_stream(const float* wav, int64_t n_wav, const int64_t* 
 extern "C" int b200d_featurize_windows(const float* wav, int64_t n_wav, const float* logmel, const int32_t* seg_start, const int32_t* seg_len,
                                        const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len, const int32_t* fb_start,
                                        const int32_t* fb_off, const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant,
-                                       void* out_f16, int32_t ldo, float* out_f32, void* stream) {
-  B200D_CHECK_ARG(wav && seg_start && seg_len && out_f16);
+                                       float* scratch, void* out_f16, int32_t ldo, float* out_f32, void* stream) {
+  B200D_CHECK_ARG(wav && seg_start && seg_len && scratch && out_f16);
   B200D_CHECK_ARG((logmel == nullptr) == (seg_row0 == nullptr));
-  B200D_CHECK_ARG(n_seg > 0 && fixed_len >= kNFFT / 2 + 1);
+  B200D_CHECK_ARG(n_seg > 0 && n_seg <= 65535 * 16 && fixed_len >= kNFFT / 2 + 1);
   B200D_CHECK_ARG(ldo >= kMels && ldo % 8 == 0);
   B200D_CHECK_ARG(variant >= 0 && variant <= 3);
   if (int rc = check_tables(fb_start, fb_off, fb_w, fb_nnz, window)) return rc;
@@ -357,18 +379,23 @@ extern "C" int b200d_featurize_windows(const float* wav, int64_t n_wav, const fl
   p.zero_pad = (variant & B200D_FEAT_ZERO_PAD) ? 1 : 0;
   B200D_CHECK_ARG(p.T >= 2);
   p.tab = {fb_start, fb_off, fb_w, window};
+  p.scratch = scratch;
   p.out16 = reinterpret_cast<__half*>(out_f16); p.ldo = ldo; p.out32 = out_f32;
-  const size_t smem = (((static_cast<size_t>(p.T) * kMels + 3) & ~static_cast<size_t>(3)) + static_cast<size_t>(kWinWarps) * kWarpScratch) * sizeof(float);
-  B200D_CHECK_ARG(smem <= 200 * 1024);  // T <= 480 frames (4.8 s windows)
-  B200D_CHECK_CUDA(cudaFuncSetAttribute(featurize_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024)));
-  featurize_windows_kernel<<<n_seg, kWinWarps * 32, smem, as_stream(stream)>>>(p);
+  const size_t smem_n = ((static_cast<size_t>(p.T) * kMels + 3) & ~static_cast<size_t>(3)) * sizeof(float);
+  B200D_CHECK_ARG(smem_n <= 200 * 1024);  // T <= 640 frames (6.4 s windows)
+  constexpr size_t smem_f = static_cast<size_t>(kWinWarps) * kWarpScratch * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  for (int s0 = 0; s0 < n_seg; s0 += 65535) {  // grid.y limit
+    FeatParams q = p;
+    const int n = n_seg - s0 < 65535 ? n_seg - s0 : 65535;
+    q.seg_start += s0; q.seg_len += s0; q.n_seg = n;
+    if (q.seg_row0) q.seg_row0 += s0;
+    q.scratch += static_cast<size_t>(s0) * p.T * kMels;
+    window_frames_kernel<<<dim3((p.T + kWinWarps - 1) / kWinWarps, n), kWinWarps * 32, smem_f, st>>>(q);
+  }
+  B200D_CHECK_LAUNCH();
+  B200D_CHECK_CUDA(cudaFuncSetAttribute(window_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024)));
+  window_normalise_kernel<<<n_seg, kWinWarps * 32, smem_n, st>>>(p);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
-}
-
-extern "C" int b200d_featurize(const float* wav, int64_t n_wav, const int32_t* seg_start, const int32_t* seg_len, int32_t n_seg,
-                               int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off, const float* fb_w, int32_t fb_nnz,
-                               const float* window, int32_t variant, void* out_f16, int32_t ldo, float* out_f32, void* stream) {
-  return b200d_featurize_windows(wav, n_wav, nullptr, seg_start, seg_len, nullptr, n_seg, fixed_len, fb_start, fb_off, fb_w, fb_nnz, window,
-                                 variant, out_f16, ldo, out_f32, stream);
 }

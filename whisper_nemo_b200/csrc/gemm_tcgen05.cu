@@ -601,12 +601,60 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (c & 1) {
             __syncwarp();
             const int col0 = n_blk * BN + (c - 1) * 32;  // 64 columns = 128 bytes per row
+            // B200D_EPI_BIAS with epi.colsum: per-window column sums of the (fp16-rounded) output for SqueezeExcite's time
+            // mean, taken from the staged tile on its way out -- lane (seg, rows seg-group) already holds 8 columns of 8
+            // rows; rows before / from the window boundary `br` go to two partial sums, combined over the four lanes that
+            // share a column segment.  Replaces a full re-read of the activation by time_stats_kernel.
+            float sa[8], sb[8];
+            bool want_sums = false;
+            int br = 32;
+            if constexpr (MODE == B200D_EPI_BIAS) {
+              want_sums = p.epi.colsum != nullptr;
+              if (want_sums) {
+                const int T = p.epi.rows_per_seg;
+                br = (row_w0 / T + 1) * T - row_w0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sa[q] = sb[q] = 0.f;
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3), seg = lane & 7;
               const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * STAGE_PITCH + ((seg ^ (rr & 7)) << 4));
-              if (row_w0 + rr < p.M)
+              if (row_w0 + rr < p.M) {
                 *reinterpret_cast<uint4*>(out16 + static_cast<size_t>(row_w0 + rr) * p.ldo + col0 + seg * 8) = v;
+                if constexpr (MODE == B200D_EPI_BIAS) {
+                  if (want_sums) {
+                    float f[8];
+                    unpack8_f16(v, f);
+                    if (rr < br) {
+#pragma unroll
+                      for (int q = 0; q < 8; ++q) sa[q] += f[q];
+                    } else {
+#pragma unroll
+                      for (int q = 0; q < 8; ++q) sb[q] += f[q];
+                    }
+                  }
+                }
+              }
+            }
+            if constexpr (MODE == B200D_EPI_BIAS) {
+              if (want_sums) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  sa[q] += __shfl_xor_sync(0xffffffffu, sa[q], 8);
+                  sa[q] += __shfl_xor_sync(0xffffffffu, sa[q], 16);
+                  sb[q] += __shfl_xor_sync(0xffffffffu, sb[q], 8);
+                  sb[q] += __shfl_xor_sync(0xffffffffu, sb[q], 16);
+                }
+                if (lane < 8 && row_w0 < p.M) {
+                  float* o = p.epi.colsum + (static_cast<size_t>(row_w0 >> 5) * 2) * p.N + col0 + lane * 8;
+                  *reinterpret_cast<float4*>(o) = make_float4(sa[0], sa[1], sa[2], sa[3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(sa[4], sa[5], sa[6], sa[7]);
+                  *reinterpret_cast<float4*>(o + p.N) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+                  *reinterpret_cast<float4*>(o + p.N + 4) = make_float4(sb[4], sb[5], sb[6], sb[7]);
+                }
+              }
             }
             __syncwarp();
           }
@@ -763,6 +811,10 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
   const bool bf16 = mode == B200D_EPI_CHEB;
   const int block_n = (mode == B200D_EPI_CHEB) ? N : (N % 256 == 0) ? 256 : 128;
   const bool use_2cta = gemm_uses_pair_kernel(M, N, mode, epi->flags);
+  if (epi->colsum != nullptr) {  // per-window column sums: an extra of the CTA-pair kernel's staged fp16 epilogue
+    if (mode != B200D_EPI_BIAS || !use_2cta || epi->rows_per_seg < 32)
+      return set_error(B200D_EINVAL, "%s: epi.colsum needs B200D_EPI_BIAS on a launch that takes the CTA-pair kernel and rows_per_seg >= 32%s", "b200d_gemm_f16");
+  }
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
   if (rc) return rc;

@@ -330,7 +330,7 @@ struct Workspace {
 
 struct Buffers {
   __half *x0, *a, *b, *y, *d, *x, *e, *hid, *mean16, *sehid, *stats16, *pool16;
-  float *gate, *segbias, *emb;
+  float *gate, *segbias, *emb, *colsum, *feat_scratch;
 };
 
 static size_t carve(const b200d_titanet_desc& ds, uint8_t* base, size_t frames, size_t segs, Buffers* out) {
@@ -354,6 +354,8 @@ static size_t carve(const b200d_titanet_desc& ds, uint8_t* base, size_t frames, 
   b.segbias = w.take<float>(segs * ds.attn);
   b.pool16 = w.take<__half>(segs * 2 * E);
   b.emb = w.take<float>(segs * ds.emb_pad);
+  b.feat_scratch = w.take<float>(frames * 80);  // un-normalised log-mel of the frames the featurizer computes per window
+  b.colsum = w.take<float>((frames / 32 + 1) * 2 * E);  // per-32-row column sums left by the GEMM feeding each squeeze-excite
   if (out) *out = b;
   return w.pos;
 }
@@ -369,11 +371,14 @@ static int gemm(const char* what, const void* A, int lda, const void* W, int ldw
   return b200d_gemm_f16(A, lda, W, ldw, M, N, K, out, ldo, &epi, st);
 }
 
+// SqueezeExcite gate of block `blk_i` for the activation y; `from_colsum`: the GEMM that produced y left per-32-row column
+// sums in b.colsum (b200d_gemm_epilogue.colsum), so the time mean needs no second pass over y.
 static int se_gate(const b200d_titanet_desc& ds, const uint8_t* pk, const Buffers& b, int blk_i, const __half* y, int n_seg, int T, int flags,
-                   cudaStream_t st) {
+                   bool from_colsum, cudaStream_t st) {
   const auto& blk = ds.block[blk_i];
   const int C = blk.cout, H = blk.se_hidden;
-  { ProfScope ps("time_stats", 0, st); RC(b200d_time_stats(y, n_seg, T, C, 0, b.mean16, st)); }
+  if (from_colsum) { ProfScope ps("se_mean_from_colsum", 0, st); RC(b200d_se_mean_from_colsum(b.colsum, n_seg, T, C, b.mean16, st)); }
+  else { ProfScope ps("time_stats", 0, st); RC(b200d_time_stats(y, n_seg, T, C, 0, b.mean16, st)); }
   b200d_gemm_epilogue e1{};
   e1.mode = B200D_EPI_BIAS_RELU;
   e1.bias = reinterpret_cast<const float*>(pk + ds.zeros);
@@ -397,12 +402,23 @@ static int forward_group(const b200d_titanet_desc& ds, const uint8_t* pk, const 
     e.bias = reinterpret_cast<const float*>(pk + bias_off);
     return e;
   };
+  // the GEMM in front of a squeeze-excite also leaves the column sums its time mean needs (pair kernel, windows >= 32 frames)
+  auto se_input_epi = [&](int64_t bias_off, int N, bool* from_colsum) {
+    b200d_gemm_epilogue e = bias_epi(B200D_EPI_BIAS, bias_off);
+    *from_colsum = T >= 32 && gemm_uses_pair_kernel(M, N, B200D_EPI_BIAS, flags);
+    if (*from_colsum) {
+      e.colsum = b.colsum;
+      e.rows_per_seg = T;
+    }
+    return e;
+  };
+  bool cs = false;
   // ---- block 0: dw -> pw feat -> C -> BN -> SE -> ReLU
   const auto& b0 = ds.block[0];
   const int C = b0.cout;
   RC(dwc(b.x0, b.d, b0.dw[0], ds.feat_pad, b0.ksize));
-  RC(gemm("b0", b.d, ds.feat_pad, pk + b0.w[0], ds.feat_pad, M, C, ds.feat_pad, b.y, C, bias_epi(B200D_EPI_BIAS, b0.bias[0]), flags, st));
-  RC(se_gate(ds, pk, b, 0, b.y, n_seg, T, flags, st));
+  RC(gemm("b0", b.d, ds.feat_pad, pk + b0.w[0], ds.feat_pad, M, C, ds.feat_pad, b.y, C, se_input_epi(b0.bias[0], C, &cs), flags, st));
+  RC(se_gate(ds, pk, b, 0, b.y, n_seg, T, flags, cs, st));
   { ProfScope ps("se_apply_relu", 0, st); RC(b200d_se_apply_relu(b.y, b.gate, b.a, n_seg, T, C, st)); }
   __half *cur = b.a, *nxt = b.b;
   // ---- residual blocks: repeat x (dw -> pw -> BN [-> ReLU]) -> SE ; + BN(conv1x1(in)) ; ReLU
@@ -412,10 +428,10 @@ static int forward_group(const b200d_titanet_desc& ds, const uint8_t* pk, const 
     for (int r = 0; r < blk.repeat; ++r) {
       RC(dwc(src, b.d, blk.dw[r], C, blk.ksize));
       const bool last = r == blk.repeat - 1;
-      RC(gemm("pw", b.d, C, pk + blk.w[r], C, M, C, C, b.y, C, bias_epi(last ? B200D_EPI_BIAS : B200D_EPI_BIAS_RELU, blk.bias[r]), flags, st));
+      RC(gemm("pw", b.d, C, pk + blk.w[r], C, M, C, C, b.y, C, last ? se_input_epi(blk.bias[r], C, &cs) : bias_epi(B200D_EPI_BIAS_RELU, blk.bias[r]), flags, st));
       src = b.y;  // the next depthwise reads y and writes d; its GEMM then overwrites y
     }
-    RC(se_gate(ds, pk, b, bi, b.y, n_seg, T, flags, st));
+    RC(se_gate(ds, pk, b, bi, b.y, n_seg, T, flags, cs, st));
     b200d_gemm_epilogue e = bias_epi(B200D_EPI_SE_RES, blk.res_bias);
     e.rowvec = b.gate;
     e.aux16 = b.y;
@@ -426,8 +442,8 @@ static int forward_group(const b200d_titanet_desc& ds, const uint8_t* pk, const 
   // ---- last block: (dw k = 1 folded) pw C -> E -> BN -> SE -> ReLU, with the [mean | std] of the result in the same pass
   const auto& bl = ds.block[nb - 1];
   const int E = ds.enc_out;
-  RC(gemm("b_last", cur, C, pk + bl.w[0], C, M, E, C, b.e, E, bias_epi(B200D_EPI_BIAS, bl.bias[0]), flags, st));
-  RC(se_gate(ds, pk, b, nb - 1, b.e, n_seg, T, flags, st));
+  RC(gemm("b_last", cur, C, pk + bl.w[0], C, M, E, C, b.e, E, se_input_epi(bl.bias[0], E, &cs), flags, st));
+  RC(se_gate(ds, pk, b, nb - 1, b.e, n_seg, T, flags, cs, st));
   { ProfScope ps("se_apply_relu_stats", 0, st); RC(b200d_se_apply_relu_stats(b.e, b.gate, b.x, n_seg, T, E, b.stats16, st)); }
   // ---- decoder: attentive statistics pooling + embedding projection
   RC(gemm("tdnn_ctx", b.stats16, 2 * E, pk + ds.tdnn_wctx, 2 * E, n_seg, ds.attn, 2 * E, b.segbias, ds.attn, bias_epi(B200D_EPI_BIAS_F32, ds.tdnn_b), flags, st));
@@ -496,11 +512,11 @@ extern "C" int b200d_titanet_forward(const b200d_titanet_desc* desc, const void*
   for (int c0 = 0; c0 < n_seg; c0 += group) {
     const int n = n_seg - c0 < group ? n_seg - c0 : group;
     {
-      ProfScope ps("featurize_windows", 0, st);
+      ProfScope ps("featurize_windows", 0, st, 2);
       RC(b200d_featurize_windows(wav, n_wav, logmel, seg_start + c0, seg_len + c0, seg_row0 ? seg_row0 + c0 : nullptr, n, fixed_len,
                                  reinterpret_cast<const int32_t*>(pk + desc->fb_start), reinterpret_cast<const int32_t*>(pk + desc->fb_off),
                                  reinterpret_cast<const float*>(pk + desc->fb_w), desc->fb_nnz, reinterpret_cast<const float*>(pk + desc->window),
-                                 variant, b.x0, desc->feat_pad, nullptr, st));
+                                 variant, b.feat_scratch, b.x0, desc->feat_pad, nullptr, st));
     }
     RC(forward_group(*desc, pk, b, n, T, flags, st));
     B200D_CHECK_CUDA(cudaMemcpy2DAsync(emb_out + static_cast<size_t>(c0) * ld_emb, static_cast<size_t>(ld_emb) * 4, b.emb,

@@ -182,6 +182,26 @@ __global__ void __launch_bounds__(64 * kTsSlices) time_stats_kernel(const __half
   }
 }
 
+// ------------------------------------------------------------------------------------ SE mean from GEMM partials
+// The producing GEMM's epilogue left, per group of 32 rows, the column sums of the rows before and from the window
+// boundary inside the group (b200d_gemm_epilogue.colsum).  Window s owns part[g][0] of the groups that start inside it and
+// part[g][1] of the group that started in window s - 1 and runs into it; summed in group order (deterministic).
+__global__ void se_mean_from_colsum_kernel(const float* __restrict__ part, int n_seg, int T, int C, __half* __restrict__ mean16) {
+  const int seg = blockIdx.x;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  const long long r0 = static_cast<long long>(seg) * T, r1 = r0 + T - 1;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long g = r0 >> 5; g <= (r1 >> 5); ++g) {
+    const int which = ((g << 5) / T == seg) ? 0 : 1;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (static_cast<size_t>(g) * 2 + which) * C + c));
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+  }
+  const float inv = 1.f / static_cast<float>(T);
+  const float m[4] = {s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv};
+  store4h(mean16 + static_cast<size_t>(seg) * C + c, m);
+}
+
 // ------------------------------------------------------------------------------------ SE apply
 __global__ void se_apply_relu_kernel(const __half* __restrict__ x, const float* __restrict__ gate, __half* __restrict__ y,
                                      size_t total4, int T, int C) {
@@ -368,6 +388,15 @@ extern "C" int b200d_time_stats(const void* x, int32_t n_seg, int32_t T, int32_t
     time_stats_kernel<true><<<grid, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
   else
     time_stats_kernel<false><<<grid, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), T, C, reinterpret_cast<__half*>(out16));
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_se_mean_from_colsum(const float* colsum, int32_t n_seg, int32_t T, int32_t C, void* mean16, void* stream) {
+  B200D_CHECK_ARG(colsum && mean16 && n_seg > 0 && T >= 32 && C % 4 == 0);
+  const int threads = 128;
+  se_mean_from_colsum_kernel<<<dim3(n_seg, (C / 4 + threads - 1) / threads), threads, 0, as_stream(stream)>>>(colsum, n_seg, T, C,
+                                                                                                              reinterpret_cast<__half*>(mean16));
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }

@@ -519,3 +519,39 @@ class ClusteringDiarizer:
             speaker_ts.append([s_ms, s_ms + int(dur_s * 1000), int(speaker.split("_")[-1])])
         return speaker_ts
 
+
+
+class NeuralDiarizer:
+    """The class the reference actually instantiates (diarize.py:19,200-201; nemo_process.py:6,31-32):
+    `NeuralDiarizer(cfg=create_config(dir)).to(device).diarize()`.  NeMo's NeuralDiarizer builds a `ClusteringDiarizer`,
+    runs it, and then refines the clustering result with the MSDD decoder (`diar_msdd_telephonic`).
+
+    This wrapper keeps the constructor / `.to()` / `.diarize()` surface and runs the CLUSTERING STAGE on the B200 path.  The
+    MSDD refinement is NOT performed (out of scope of the accelerated path): the RTTMs in
+    `out_dir/pred_rttms/` are the clustering stage's -- what upstream writes before MSDD overwrites them -- and
+    everything MSDD reads is left in `out_dir/speaker_outputs/` (`subsegments_scale<k>.json`, `..._cluster.label`,
+    `embeddings/subsegments_scale<k>_embeddings.pkl`), so NeMo's own MSDD stage can be run on top of this output.
+    `msdd_refinement_skipped` is True after `diarize()` so callers can tell.  Speech regions: `oracle_vad`, an
+    `external_vad_manifest`, or a `vad_fn` callable (see ClusteringDiarizer._run_vad); MarbleNet itself is not bundled."""
+
+    def __init__(self, cfg, speaker_model=None, vad_fn=None):
+        self._cfg = as_config(cfg)
+        self.clustering_embedding = self  # upstream attribute chain: neural_diarizer.clustering_embedding.clus_diar_model
+        self.clus_diar_model = ClusteringDiarizer(self._cfg, speaker_model=speaker_model)
+        if vad_fn is not None:
+            self.clus_diar_model.vad_fn = vad_fn
+        self.msdd_refinement_skipped = False
+
+    def to(self, device):
+        self.clus_diar_model.to(device)
+        return self
+
+    def diarize(self, paths2audio_files: List[str] = None, batch_size: int = 0):
+        import warnings
+
+        self.clus_diar_model._cfg.diarizer.speaker_embeddings.parameters.save_embeddings = True  # MSDD reads the pickles
+        self.clus_diar_model.diarize(paths2audio_files=paths2audio_files, batch_size=batch_size)
+        self.msdd_refinement_skipped = True
+        warnings.warn("whisper_nemo_b200.NeuralDiarizer ran the clustering stage only; the MSDD refinement of NeMo's NeuralDiarizer was "
+                      "skipped (its inputs are in out_dir/speaker_outputs/)", RuntimeWarning, stacklevel=2)
+        return None

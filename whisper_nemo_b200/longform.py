@@ -172,22 +172,15 @@ class LongFormSpeakerClustering:
         self.timestamps_in_scales = self.speaker_clustering.timestamps_in_scales
         return labels
 
-    def _reduce_chunk(self, emb_part: torch.Tensor, mat: torch.Tensor, Y_part: torch.Tensor, class_target_vol: torch.Tensor,
-                      offset_index: int, y_host: torch.Tensor = None):
+    def _reduce_chunk(self, emb_part: torch.Tensor, y_host: torch.Tensor, mass_np, class_target_vol: torch.Tensor, offset_index: int):
         """run_reducer for every cluster of one chunk.  Returns ([merged_embs per cluster], [index mappings]).
-        The index bookkeeping (<= 50 clusters) is host work on the labels; the embedding traffic is three device
-        operations for the whole chunk: within-cluster affinity mass, merged means, one gather."""
+        The index bookkeeping (<= 50 clusters) is host work on the labels and the within-cluster affinity mass; the
+        embedding traffic is two device operations for the whole chunk: merged means, one gather."""
         n, d = emb_part.shape
         dev = emb_part.device
-        y_np = (Y_part.cpu() if y_host is None else y_host).numpy()
+        y_np = y_host.numpy()
         vols = [int(v) for v in class_target_vol.tolist()]
-        mass_np = None
-        if mat is not None and sum(vols) > 0:
-            mass = torch.empty(n, dtype=torch.float32, device=dev)
-            y32 = Y_part.to(torch.int32).contiguous()
-            _cabi.call("b200d_masked_rowsum", ptr(mat), n, ptr(y32), ptr(mass), _s())
-            mass_np = mass.cpu().numpy()
-        mapping_list, sizes, sel_idx, seg_off, order, n_avg = plan_cluster_merges(y_np, vols, mass_np, n, offset_index)
+        mapping_list, sizes, sel_idx, seg_off, order, n_avg = plan_cluster_merges(y_np, vols, mass_np if sum(vols) > 0 else None, n, offset_index)
         src = emb_part
         if n_avg > 0:
             idx_d = torch.from_numpy(np.concatenate(sel_idx).astype(np.int32)).to(dev)
@@ -218,32 +211,35 @@ class LongFormSpeakerClustering:
             from . import sharding
 
             rank, world = sharding.rank_world()
-        def cluster_chunk(win_index: int, clusterer: SpeakerClustering):
+
+        def chunk_range(win_index: int):
             if embeddings_per_chunk * (win_index + 1) > n_total:  # last chunk is aligned to the end (overlaps the previous one)
                 offset_index = n_total - embeddings_per_chunk
             else:
                 offset_index = embeddings_per_chunk * win_index
-            emb_part = emb[offset_index : offset_index + embeddings_per_chunk]
-            if emb_part.shape[0] == 1:
-                Y_part = torch.zeros((1,), dtype=torch.int64, device=emb.device)
-                mat = None
-            else:
-                cos, mm = cos_affinity(emb_part)
-                ident = torch.arange(emb_part.shape[0], dtype=torch.int32, device=emb.device)
-                mat = _fuse([cos], [ident], [mm], [1.0], emb_part.shape[0])
-                del cos
-                overcluster_count = min(chunk_cluster_count, mat.shape[0])
-                Y_part = clusterer.forward_unit_infer(
-                    mat=mat, oracle_num_speakers=overcluster_count, max_rp_threshold=max_rp_threshold,
-                    max_num_speakers=chunk_cluster_count, sparse_search_volume=sparse_search_volume)
-            num_to_be_merged = int(min(embeddings_per_chunk, emb_part.shape[0]) - chunk_cluster_count)
-            y_host = Y_part.cpu()
-            min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
-            class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
-            self.chunk_labels[win_index] = (offset_index, y_host)
-            return self._reduce_chunk(emb_part, mat, Y_part, class_target_vol, offset_index, y_host)
+            return offset_index, emb[offset_index : offset_index + embeddings_per_chunk]
 
-        mine = [w for w in range(n_chunks) if w % world == rank]
+        def cluster_chunk(win_index: int, clusterer: SpeakerClustering):
+            """The expensive, per-chunk part (the unit dealt to ranks / streams): affinity, NME sweep, binarisation, spectral
+            embedding, k-means(50) and the within-cluster affinity mass.  Returns (labels int32 [m], mass float32 [m]) on device."""
+            _, emb_part = chunk_range(win_index)
+            m = emb_part.shape[0]
+            if m == 1:
+                return torch.zeros((1,), dtype=torch.int32, device=emb.device), torch.zeros((1,), dtype=torch.float32, device=emb.device)
+            cos, mm = cos_affinity(emb_part)
+            ident = torch.arange(m, dtype=torch.int32, device=emb.device)
+            mat = _fuse([cos], [ident], [mm], [1.0], m)
+            del cos
+            overcluster_count = min(chunk_cluster_count, mat.shape[0])
+            Y_part = clusterer.forward_unit_infer(
+                mat=mat, oracle_num_speakers=overcluster_count, max_rp_threshold=max_rp_threshold,
+                max_num_speakers=chunk_cluster_count, sparse_search_volume=sparse_search_volume)
+            y32 = Y_part.to(torch.int32).contiguous()
+            mass = torch.empty(m, dtype=torch.float32, device=emb.device)
+            _cabi.call("b200d_masked_rowsum", ptr(mat), m, ptr(y32), ptr(mass), _s())
+            return y32, mass
+
+        mine = [w for w in range(n_chunks) if w % world == rank]  # sharding.chunks_of_rank
         want = self.chunk_streams if self.chunk_streams is not None else int(os.environ.get("B200D_CHUNK_STREAMS", "2"))
         n_streams = min(len(mine), max(1, want))
         per_chunk = {}
@@ -263,28 +259,43 @@ class LongFormSpeakerClustering:
                 st.wait_stream(main)
             dev_index = emb.device.index
 
-            def work(w, st):
+            free = list(streams)
+
+            def work(w):
                 torch.cuda.set_device(dev_index)
-                with torch.cuda.stream(st), torch.no_grad(), _cabi.single_cta_gemms():
-                    merged_list, mapping_list = cluster_chunk(w, SpeakerClustering())
-                    for m in merged_list:
-                        m.record_stream(main)
-                    return merged_list, mapping_list
+                st = free.pop()  # each worker thread takes a stream of its own (list.pop / append are atomic under the GIL)
+                try:
+                    with torch.cuda.stream(st), torch.no_grad(), _cabi.single_cta_gemms():
+                        y32, mass = cluster_chunk(w, SpeakerClustering())
+                        y32.record_stream(main)
+                        mass.record_stream(main)
+                        return y32, mass
+                finally:
+                    free.append(st)
 
             main.synchronize()  # nothing of the single-stream phase (CTA-pair GEMMs) may still be running
             with _cabi.short_gil_switch(), ThreadPoolExecutor(max_workers=n_streams) as pool:
-                futures = {w: pool.submit(work, w, streams[i % n_streams]) for i, w in enumerate(mine)}
+                futures = {w: pool.submit(work, w) for w in mine}
                 for w, fut in futures.items():
                     per_chunk[w] = fut.result()
                 for st in streams:
                     st.synchronize()  # the multi-stream region is drained before the pair kernel is allowed again
-        if world > 1:  # tiny payload: <= chunk_cluster_count x 192 floats + the index lists of one chunk per entry
-            payload = {w: ([m.cpu() for m in ml], mp) for w, (ml, mp) in per_chunk.items()}
-            gathered = [None] * world
-            torch.distributed.all_gather_object(gathered, payload)
-            per_chunk = {w: ([m.to(emb.device) for m in ml], mp) for part in gathered for w, (ml, mp) in part.items()}
+        # every rank needs every chunk's over-clustering: 2 x 4 bytes per window (labels + affinity mass), gathered as one
+        # device tensor per rank (NCCL over NVLink; gloo in the CPU tests) -- the merge bookkeeping below is then replicated
+        m_chunk = min(embeddings_per_chunk, n_total)
+        if world > 1:
+            from . import sharding
+
+            per_chunk = sharding.all_gather_chunk_results(per_chunk, n_chunks, m_chunk, [chunk_range(w)[1].shape[0] for w in range(n_chunks)])
         for win_index in range(n_chunks):
-            merged_list, mapping_list = per_chunk[win_index]
+            offset_index, emb_part = chunk_range(win_index)
+            y32, mass = per_chunk[win_index]
+            y_host = y32.cpu().long()
+            self.chunk_labels[win_index] = (offset_index, y_host)
+            num_to_be_merged = int(min(embeddings_per_chunk, emb_part.shape[0]) - chunk_cluster_count)
+            min_count_per_cluster = self.get_div_ceil_count(chunk_cluster_count, len(torch.unique(y_host)))
+            class_target_vol = get_merge_quantity(num_to_be_merged, y_host, min_count_per_cluster)
+            merged_list, mapping_list = self._reduce_chunk(emb_part, y_host, mass.cpu().numpy(), class_target_vol, offset_index)
             for merged, mapping in zip(merged_list, mapping_list):
                 total_emb.append(merged)
                 absolute_merge_mapping.append(mapping)

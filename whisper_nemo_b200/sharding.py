@@ -8,7 +8,7 @@ Two levels, matching SURVEY.md section 8(e):
     (`all_gather_rows`, NCCL over NVLink on GPUs, gloo in the CPU tests); <= 128 MB for 4 hours of audio.
 The reference has no distributed code at all; nothing here mirrors a reference interface.
 """
-from typing import List, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import torch
 
@@ -58,3 +58,32 @@ def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
         lo, hi = shard_range(n_total, r, world)
         pieces.append(out[r * pad_rows : r * pad_rows + (hi - lo)])
     return torch.cat(pieces, dim=0)
+
+
+def chunks_of_rank(n_chunks: int, rank: int, world: int) -> List[int]:
+    """Long-form chunks are dealt round-robin: chunk w belongs to rank w % world."""
+    return [w for w in range(n_chunks) if w % world == rank]
+
+
+def all_gather_chunk_results(mine: Dict[int, Tuple[torch.Tensor, torch.Tensor]], n_chunks: int, m_chunk: int,
+                             chunk_lens: Sequence[int]) -> Dict[int, Tuple[torch.Tensor, torch.Tensor]]:
+    """Long-form path on several ranks: every rank clustered the chunks of `chunks_of_rank`; `mine[w]` = (labels int32 [m_w],
+    within-cluster affinity mass float32 [m_w]) of chunk w on this rank's device.  One all_gather_into_tensor of a
+    [chunks per rank, 2, m_chunk] int32 tensor (the mass bit-cast) gives every rank every chunk -- 8 bytes per window, no
+    pickling through the host (round 1 used all_gather_object on the merged embeddings and index lists)."""
+    rank, world = rank_world()
+    per_rank = -(-n_chunks // world)
+    ref = next(iter(mine.values()))[0] if mine else None
+    device = ref.device if ref is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    buf = torch.zeros(per_rank, 2, m_chunk, dtype=torch.int32, device=device)
+    for slot, w in enumerate(chunks_of_rank(n_chunks, rank, world)):
+        y32, mass = mine[w]
+        buf[slot, 0, : y32.numel()] = y32.to(torch.int32)
+        buf[slot, 1, : mass.numel()] = mass.contiguous().view(torch.int32)
+    out = torch.empty(world * per_rank, 2, m_chunk, dtype=torch.int32, device=device)
+    torch.distributed.all_gather_into_tensor(out, buf)
+    result = {}
+    for w in range(n_chunks):
+        row = out[(w % world) * per_rank + w // world]
+        result[w] = (row[0, : chunk_lens[w]], row[1, : chunk_lens[w]].view(torch.float32))
+    return result

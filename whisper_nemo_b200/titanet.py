@@ -69,7 +69,7 @@ def slaney_mel_filterbank(sr: int = 16000, n_fft: int = NFFT, n_mels: int = FEAT
 
 
 def pack_filterbank(fb: np.ndarray):
-    """Sparse (start bin, offset, packed weights) form consumed by b200d_featurize."""
+    """Sparse (start bin, offset, packed weights) form consumed by b200d_featurize_windows / b200d_mel_stream."""
     starts, offs, weights = [], [0], []
     for m in range(fb.shape[0]):
         nz = np.nonzero(fb[m])[0]
@@ -203,7 +203,7 @@ def pack_weights(state_dict: Dict[str, torch.Tensor], device="cuda") -> PackedTi
 
 
 # ------------------------------------------------------------------------------------------ kernels
-def gemm(A, W, out, mode, M=None, bias=None, scale=None, shift=None, rowvec=None, aux16=None, rows_per_seg=0):
+def gemm(A, W, out, mode, M=None, bias=None, scale=None, shift=None, rowvec=None, aux16=None, rows_per_seg=0, colsum=None):
     """out = epilogue(A[M,K] @ W[N,K]^T) through b200d_gemm_f16."""
     M = A.shape[0] if M is None else M
     N, K = W.shape
@@ -216,6 +216,7 @@ def gemm(A, W, out, mode, M=None, bias=None, scale=None, shift=None, rowvec=None
     epi.rowvec = rowvec.data_ptr() if rowvec is not None else None
     epi.aux16 = aux16.data_ptr() if aux16 is not None else None
     epi.flags = _cabi.gemm_flags()
+    epi.colsum = colsum.data_ptr() if colsum is not None else None
     _cabi.call("b200d_gemm_f16", ptr(A), A.stride(0), ptr(W), W.stride(0), M, N, K, ptr(out), out.stride(0), byref(epi), _cabi._stream())
     return out
 
@@ -232,9 +233,10 @@ def featurize(pk: PackedTitaNet, wav: torch.Tensor, seg_start: torch.Tensor, seg
     out32 = torch.empty(n_seg, T, FEAT, dtype=torch.float32, device=wav.device) if want_f32 else None
     if logmel is None or seg_row0 is None:
         logmel = seg_row0 = None
+    scratch = torch.empty(n_seg * T, FEAT, dtype=torch.float32, device=wav.device)
     _cabi.call("b200d_featurize_windows", ptr(wav), wav.numel(), ptr(logmel), ptr(seg_start), ptr(seg_len), ptr(seg_row0), n_seg, fixed_len,
-               ptr(pk.fb_start), ptr(pk.fb_off), ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), FEATURIZER_VARIANT, ptr(out16), out16.stride(0),
-               ptr(out32), _cabi._stream())
+               ptr(pk.fb_start), ptr(pk.fb_off), ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), FEATURIZER_VARIANT, ptr(scratch), ptr(out16),
+               out16.stride(0), ptr(out32), _cabi._stream())
     return out16, out32
 
 
@@ -309,6 +311,7 @@ class Workspace:
         self.segbias = torch.empty(max_segs, 128, dtype=torch.float32, device=device)
         self.pool16 = h(max_segs, 6144)
         self.emb = torch.empty(max_segs, EMB_PAD, dtype=torch.float32, device=device)
+        self.colsum = torch.empty((max_frames // 32 + 1) * 2 * 3072, dtype=torch.float32, device=device)
 
 
 def _flat(buf, rows, cols):
@@ -316,14 +319,25 @@ def _flat(buf, rows, cols):
     return buf.view(-1)[: rows * cols].view(rows, cols)
 
 
-def _se_gate(pk, ws, blk: Block, y, n_seg, T, C):
+def _se_gate(pk, ws, blk: Block, y, n_seg, T, C, from_colsum=False):
     mean16 = _flat(ws.mean16, n_seg, C)
     hid = _flat(ws.sehid, n_seg, C // 8)
     gate = _flat(ws.gate, n_seg, C)
-    _cabi.call("b200d_time_stats", ptr(y), n_seg, T, C, 0, ptr(mean16), _cabi._stream())
+    if from_colsum:  # the GEMM that produced y left per-32-row column sums (GemmEpilogue.colsum)
+        _cabi.call("b200d_se_mean_from_colsum", ptr(ws.colsum), n_seg, T, C, ptr(mean16), _cabi._stream())
+    else:
+        _cabi.call("b200d_time_stats", ptr(y), n_seg, T, C, 0, ptr(mean16), _cabi._stream())
     gemm(mean16, blk.se_w1, hid, _cabi.EPI_BIAS_RELU, bias=pk.zeros)
     gemm(hid, blk.se_w2, gate, _cabi.EPI_SIGMOID_F32)
     return gate
+
+
+def _se_input_gemm(ws, A, W, out, M, T, bias):
+    """The pointwise conv in front of a squeeze-excite; when it runs on the CTA-pair kernel its epilogue also leaves the
+    column sums the SE time mean needs.  Returns whether it did."""
+    cs = T >= 32 and _cabi.gemm_uses_pair(M, W.shape[0], _cabi.EPI_BIAS, _cabi.gemm_flags())
+    gemm(A, W, out, _cabi.EPI_BIAS, M=M, bias=bias, rows_per_seg=T if cs else 0, colsum=ws.colsum if cs else None)
+    return cs
 
 
 def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: dict = None) -> torch.Tensor:
@@ -335,8 +349,8 @@ def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: d
     b0 = pk.blocks[0]
     d0v = _flat(ws.d, M, FEAT_PAD)
     dwc(ws.x0, d0v, b0.subs[0].dw, FEAT_PAD, b0.subs[0].ksize)
-    gemm(d0v, b0.subs[0].w, ws.y, _cabi.EPI_BIAS, M=M, bias=b0.subs[0].bias)
-    gate = _se_gate(pk, ws, b0, ws.y, n_seg, T, 1024)
+    cs = _se_input_gemm(ws, d0v, b0.subs[0].w, ws.y, M, T, b0.subs[0].bias)
+    gate = _se_gate(pk, ws, b0, ws.y, n_seg, T, 1024, cs)
     _cabi.call("b200d_se_apply_relu", ptr(ws.y), ptr(gate), ptr(ws.a), n_seg, T, 1024, s)
     cur, nxt = ws.a, ws.b
     if taps is not None:
@@ -347,18 +361,20 @@ def forward_frames(pk: PackedTitaNet, ws: Workspace, n_seg: int, T: int, taps: d
         src = cur
         for r, sb in enumerate(blk.subs):
             dwc(src, ws.d, sb.dw, 1024, sb.ksize)
-            last = r == len(blk.subs) - 1
-            gemm(ws.d, sb.w, ws.y, _cabi.EPI_BIAS if last else _cabi.EPI_BIAS_RELU, M=M, bias=sb.bias)
+            if r == len(blk.subs) - 1:
+                cs = _se_input_gemm(ws, ws.d, sb.w, ws.y, M, T, sb.bias)
+            else:
+                gemm(ws.d, sb.w, ws.y, _cabi.EPI_BIAS_RELU, M=M, bias=sb.bias)
             src = ws.y  # next depthwise reads y and writes d; its GEMM then overwrites y
-        gate = _se_gate(pk, ws, blk, ws.y, n_seg, T, 1024)
+        gate = _se_gate(pk, ws, blk, ws.y, n_seg, T, 1024, cs)
         gemm(cur, blk.res_w, nxt, _cabi.EPI_SE_RES, M=M, bias=blk.res_bias, rowvec=gate, aux16=ws.y, rows_per_seg=T)
         cur, nxt = nxt, cur
         if taps is not None:
             taps[f"block{bi}"] = cur[:M].clone()
     # ---- block 4: (dw k=1 folded) pw 1024->3072 -> BN -> SE -> ReLU
     b4 = pk.blocks[4]
-    gemm(cur, b4.subs[0].w, ws.e, _cabi.EPI_BIAS, M=M, bias=b4.subs[0].bias)
-    gate = _se_gate(pk, ws, b4, ws.e, n_seg, T, 3072)
+    cs = _se_input_gemm(ws, cur, b4.subs[0].w, ws.e, M, T, b4.subs[0].bias)
+    gate = _se_gate(pk, ws, b4, ws.e, n_seg, T, 3072, cs)
     stats16 = ws.stats16[:n_seg]
     _cabi.call("b200d_se_apply_relu_stats", ptr(ws.e), ptr(gate), ptr(ws.x), n_seg, T, 3072, ptr(stats16), s)
     if taps is not None:
