@@ -78,16 +78,19 @@ int b200d_check_device(void);
  *                            one), or < 0.  Segments with seg_row0 >= 0 and seg_len == fixed_len copy their interior frames
  *                            (t*160 - 201 >= 0 and t*160 + 200 <= fixed_len) from the stream and compute only the two frames at
  *                            each end (reflect / zero padding, first-sample pre-emphasis); all others compute every frame.
- *                            logmel == NULL and seg_row0 == NULL together: every segment takes the generic path.
+ *                            n_on_stream: the caller orders the segments so that the first n_on_stream are the ones on a stream
+ *                            (their edge frames: one CTA per window; the rest: every frame, spread over the chip); a segment placed
+ *                            in the wrong part is still computed correctly, only slower.
+ *                            logmel == NULL and seg_row0 == NULL together (n_on_stream ignored): every segment takes the generic path.
  *                            scratch float32 [n_seg][T][80]: un-normalised log-mel of the frames computed per window (two
  *                            kernels: frames spread over the chip one warp each, then one CTA per window gathers + normalises). */
 int b200d_mel_stream(const float* wav, int64_t n_wav, const int64_t* stream_start, const int32_t* stream_off, int32_t n_streams,
                      int32_t total_rows, const int32_t* fb_start, const int32_t* fb_off, const float* fb_w, int32_t fb_nnz,
                      const float* window, float* logmel, void* stream);
 int b200d_featurize_windows(const float* wav, int64_t n_wav, const float* logmel, const int32_t* seg_start, const int32_t* seg_len,
-                            const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len, const int32_t* fb_start, const int32_t* fb_off,
-                            const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant, float* scratch, void* out_f16,
-                            int32_t ldo, float* out_f32, void* stream);
+                            const int32_t* seg_row0, int32_t n_on_stream, int32_t n_seg, int32_t fixed_len, const int32_t* fb_start,
+                            const int32_t* fb_off, const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant, float* scratch,
+                            void* out_f16, int32_t ldo, float* out_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * TitaNet-L building blocks (nemo/collections/asr/parts/submodules/jasper.py JasperBlock,
@@ -217,8 +220,9 @@ int b200d_titanet_pack_weights(int32_t n_tensors, const char* const* names, cons
                                b200d_titanet_desc* desc, void* packed_host, size_t packed_bytes);
 size_t b200d_titanet_workspace_bytes(const b200d_titanet_desc* desc, int32_t max_frames, int32_t max_segs);
 int b200d_titanet_forward(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav, const float* logmel,
-                          const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len,
-                          int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes, void* stream);
+                          const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_on_stream, int32_t n_seg,
+                          int32_t fixed_len, int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes,
+                          void* stream);
 int b200d_titanet_mel_stream(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav,
                              const int64_t* stream_start, const int32_t* stream_off, int32_t n_streams, int32_t total_rows, float* logmel,
                              void* stream);

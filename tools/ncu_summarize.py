@@ -2,6 +2,8 @@
 
   python tools/ncu_summarize.py launches gpurun_out/launches.csv profiles/out.csv "<command line>"
   python tools/ncu_summarize.py full gpurun_out/prof.ncu-rep profiles/out.txt
+  python tools/ncu_summarize.py traffic gpurun_out/prof.ncu-rep profiles/ncu_traffic.json [kernel-substring] [algorithmic bytes]
+      -> the json bench.py reads for roofline.traffic: DRAM bytes of the longest captured launch of the dominant kernel
 """
 import collections
 import csv
@@ -53,8 +55,50 @@ def full(src, dst):
     print("\n".join(out))
 
 
+def traffic(src, dst, kernel="gemm_tcgen05_2cta_kernel", algorithmic=None):
+    import json
+    import os
+
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def num(r, key):
+        v = float(r[col[key]].replace(",", ""))
+        u = units[col[key]]
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3,
+                 "msecond": 1e3}.get(u, 1.0)
+        return v * scale
+
+    best = None
+    for r in rows[2:]:
+        if kernel not in r[col["Kernel Name"]]:
+            continue
+        dur = num(r, "gpu__time_duration.sum")
+        if best is None or dur > best[0]:
+            best = (dur, r)
+    if best is None:
+        raise SystemExit(f"no launch of {kernel} in {src}")
+    dur, r = best
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    out = {"kernel": re.sub(r"\(.*", "", r[col["Kernel Name"]])[:120], "bytes_per_launch": int(num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum")),
+           "dram_read_bytes": int(num(r, "dram__bytes_read.sum")), "dram_write_bytes": int(num(r, "dram__bytes_write.sum")),
+           "duration_us_under_ncu": round(dur, 1), "grid": r[col["launch__grid_size"]] if "launch__grid_size" in col else None,
+           "tensor_pipe_active_pct": float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])
+           if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in col else None,
+           "algorithmic_bytes": int(algorithmic) if algorithmic else None,
+           "source": os.path.basename(src), "commit": commit,
+           "note": "longest captured launch of the kernel, ncu --set full --clock-control none (cold-cache replay; a number under ncu is never a bench value)"}
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], *(sys.argv[4:6]))
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
     else:
         full(sys.argv[2], sys.argv[3])

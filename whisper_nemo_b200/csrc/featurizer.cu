@@ -235,22 +235,27 @@ __device__ __forceinline__ void interior_range(const FeatParams& p, int seg, int
   }
 }
 
-// Kernel 1: every frame that cannot be taken from a stream -- the 2 + 2 edge frames of a window on a stream, all T frames
-// of a window without one (tiled up by fixed_seq collate / off-grid) -- one warp per frame, spread over the whole chip
-// (grid: ceil(T / 8) x n_seg; CTAs whose 8 frames are all interior exit at once).  Un-normalised log-mel to `scratch`.
-__global__ void __launch_bounds__(kWinWarps * 32) window_frames_kernel(const FeatParams p) {
+// Kernel 1: every frame that cannot be taken from a stream, one warp per frame, un-normalised log-mel to `scratch`.
+//   EDGE  == true : segments [0, n_on_stream) -- windows on a stream: one CTA per window computes its 2 + 2 edge frames;
+//   EDGE  == false: segments [n_on_stream, n_seg) -- windows without one (tiled up by fixed_seq collate / off-grid): all T
+//                   frames, spread over the whole chip (grid: ceil(T / 8) x windows).
+template <bool EDGE>
+__global__ void __launch_bounds__(kWinWarps * 32) window_frames_kernel(const FeatParams p, int seg_base) {
   extern __shared__ float dyn[];  // per-warp spectrum scratch: kWinWarps x (256 float2 + 260 float)
   __shared__ FbShared tabs;
-  const int seg = blockIdx.y;
+  const int seg = seg_base + blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int t_lo, t_hi, row0;
   interior_range(p, seg, t_lo, t_hi, row0);
-  const int tb0 = blockIdx.x * kWinWarps, tb1 = min(tb0 + kWinWarps, p.T) - 1;
-  if (tb0 >= t_lo && tb1 <= t_hi) return;
   load_tables(tabs, p.tab);
   __syncthreads();
-  const int t = tb0 + warp;
-  if (t >= p.T || (t >= t_lo && t <= t_hi)) return;
+  const int n_int = t_hi >= t_lo ? t_hi - t_lo + 1 : 0;
+  if (EDGE && n_int == p.T) return;
+  // this warp's first frame; EDGE: e-th non-interior frame, e = warp, warp + 8, ...
+  int e = EDGE ? warp : blockIdx.x * kWinWarps + warp;
+  auto frame_of = [&](int q) { return (n_int == 0 || q < t_lo) ? q : q + n_int; };
+  int t = frame_of(e);
+  if (t >= p.T) return;
 
   const int F = p.fixed_len;
   const int len = p.seg_len[seg];
@@ -277,9 +282,15 @@ __global__ void __launch_bounds__(kWinWarps * 32) window_frames_kernel(const Fea
   };
   LaneTwiddles lt;
   lt.init(lane);
-  const int base = t * kHop - kNFFT / 2;
-  frame_logmel(tabs, lt, dyn + warp * kWarpScratch, lane, [&](int i) { return sample(base + i); },
-               p.scratch + (static_cast<size_t>(seg) * p.T + t) * kMels);
+  for (;;) {
+    const int base = t * kHop - kNFFT / 2;
+    frame_logmel(tabs, lt, dyn + warp * kWarpScratch, lane, [&](int i) { return sample(base + i); },
+                 p.scratch + (static_cast<size_t>(seg) * p.T + t) * kMels);
+    if (!EDGE) break;
+    e += kWinWarps;
+    t = frame_of(e);
+    if (t >= p.T) break;
+  }
 }
 
 // Kernel 2: one CTA per window gathers its T frames (interior ones from the stream, the others from `scratch`), takes the
@@ -364,12 +375,12 @@ extern "C" int b200d_mel_stream(const float* wav, int64_t n_wav, const int64_t* 
 }
 
 extern "C" int b200d_featurize_windows(const float* wav, int64_t n_wav, const float* logmel, const int32_t* seg_start, const int32_t* seg_len,
-                                       const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len, const int32_t* fb_start,
-                                       const int32_t* fb_off, const float* fb_w, int32_t fb_nnz, const float* window, int32_t variant,
-                                       float* scratch, void* out_f16, int32_t ldo, float* out_f32, void* stream) {
+                                       const int32_t* seg_row0, int32_t n_on_stream, int32_t n_seg, int32_t fixed_len,
+                                       const int32_t* fb_start, const int32_t* fb_off, const float* fb_w, int32_t fb_nnz, const float* window,
+                                       int32_t variant, float* scratch, void* out_f16, int32_t ldo, float* out_f32, void* stream) {
   B200D_CHECK_ARG(wav && seg_start && seg_len && scratch && out_f16);
   B200D_CHECK_ARG((logmel == nullptr) == (seg_row0 == nullptr));
-  B200D_CHECK_ARG(n_seg > 0 && n_seg <= 65535 * 16 && fixed_len >= kNFFT / 2 + 1);
+  B200D_CHECK_ARG(n_seg > 0 && n_on_stream >= 0 && n_on_stream <= n_seg && fixed_len >= kNFFT / 2 + 1);
   B200D_CHECK_ARG(ldo >= kMels && ldo % 8 == 0);
   B200D_CHECK_ARG(variant >= 0 && variant <= 3);
   if (int rc = check_tables(fb_start, fb_off, fb_w, fb_nnz, window)) return rc;
@@ -385,14 +396,11 @@ extern "C" int b200d_featurize_windows(const float* wav, int64_t n_wav, const fl
   B200D_CHECK_ARG(smem_n <= 200 * 1024);  // T <= 640 frames (6.4 s windows)
   constexpr size_t smem_f = static_cast<size_t>(kWinWarps) * kWarpScratch * sizeof(float);
   cudaStream_t st = as_stream(stream);
-  for (int s0 = 0; s0 < n_seg; s0 += 65535) {  // grid.y limit
-    FeatParams q = p;
-    const int n = n_seg - s0 < 65535 ? n_seg - s0 : 65535;
-    q.seg_start += s0; q.seg_len += s0; q.n_seg = n;
-    if (q.seg_row0) q.seg_row0 += s0;
-    q.scratch += static_cast<size_t>(s0) * p.T * kMels;
-    window_frames_kernel<<<dim3((p.T + kWinWarps - 1) / kWinWarps, n), kWinWarps * 32, smem_f, st>>>(q);
-  }
+  const int n_fast = (logmel != nullptr) ? n_on_stream : 0;
+  for (int s0 = 0; s0 < n_fast; s0 += 65535)  // grid.y limit
+    window_frames_kernel<true><<<dim3(1, n_fast - s0 < 65535 ? n_fast - s0 : 65535), kWinWarps * 32, smem_f, st>>>(p, s0);
+  for (int s0 = n_fast; s0 < n_seg; s0 += 65535)
+    window_frames_kernel<false><<<dim3((p.T + kWinWarps - 1) / kWinWarps, n_seg - s0 < 65535 ? n_seg - s0 : 65535), kWinWarps * 32, smem_f, st>>>(p, s0);
   B200D_CHECK_LAUNCH();
   B200D_CHECK_CUDA(cudaFuncSetAttribute(window_normalise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(200 * 1024)));
   window_normalise_kernel<<<n_seg, kWinWarps * 32, smem_n, st>>>(p);

@@ -126,6 +126,7 @@ struct GemmCfg {
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192) ? 5 : 6;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int TMEM_COLS = (BLOCK_N > 128) ? 512 : 256;  // two accumulators, allocation a power of two
+  static constexpr int ACC_STRIDE = (BLOCK_N == 96) ? 128 : BLOCK_N;  // TMEM columns between the two accumulator buffers
   static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + 256;
 };
 
@@ -219,19 +220,21 @@ __device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& h, __nv_bflo
 
 // 32 block vectors [c0, c0 + 32) of one accumulator row: the Chebyshev step y = ca (deg x - A x) + cb x + cc xprev and
 // the same 3-way split of y for the next step's W operand.
-template <int B>
-__device__ __forceinline__ void cheb_epilogue_cols(const GemmParams& p, int row, uint32_t t_addr, int c0) {
+// TS: distance (TMEM columns) between the hi / mid / lo accumulators of one vector; VS: the same in rows of the W operand
+// (the block size b).  c_tmem: first accumulator column of the 32 vectors; c_out: their first column in x / out / V.
+template <int TS, int VS>
+__device__ __forceinline__ void cheb_epilogue_cols(const GemmParams& p, int row, uint32_t t_addr, int c_tmem, int c_out) {
   const b200d_gemm_epilogue& e = p.epi;
   uint32_t r0[32], r1[32], r2[32];
-  tmem_ld32(t_addr + c0, r0);
-  tmem_ld32(t_addr + B + c0, r1);
-  tmem_ld32(t_addr + 2 * B + c0, r2);
+  tmem_ld32(t_addr + c_tmem, r0);
+  tmem_ld32(t_addr + TS + c_tmem, r1);
+  tmem_ld32(t_addr + 2 * TS + c_tmem, r2);
   tmem_ld_wait();
   if (row < p.M) {
     const float dg = __ldg(e.deg + row);
-    const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + c0;
-    const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + c0 : nullptr;
-    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c0;
+    const float* x = e.x32 + static_cast<size_t>(row) * e.ldx + c_out;
+    const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + c_out : nullptr;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c_out;
     __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -243,10 +246,10 @@ __device__ __forceinline__ void cheb_epilogue_cols(const GemmParams& p, int row,
       if (vh) {
         __nv_bfloat16 h, m, l;
         split3_bf16(y, h, m, l);
-        const size_t vrow = static_cast<size_t>(c0 + j);
+        const size_t vrow = static_cast<size_t>(c_out + j);
         vh[(vrow) * e.ldvt + row] = h;
-        vh[(vrow + B) * e.ldvt + row] = m;
-        vh[(vrow + 2 * B) * e.ldvt + row] = l;
+        vh[(vrow + VS) * e.ldvt + row] = m;
+        vh[(vrow + 2 * VS) * e.ldvt + row] = l;
       }
     }
   }
@@ -289,8 +292,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // BLOCK_N == 96: the 64-vector Chebyshev product split over TWO CTAs per row tile (32 vectors x [hi | mid | lo] each), so
+  // that a 10 000-row graph gives 158 tiles instead of 79 on the 148 SMs; the second read of the A rows comes from L2
+  constexpr bool SPLIT = BLOCK_N == 96;
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int num_n = p.N / BLOCK_N;
+  const int num_n = SPLIT ? 2 : p.N / BLOCK_N;
   const int total = num_m * num_n;
   const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
 
@@ -304,7 +310,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], A_BYTES + Cfg::B_BYTES);
           tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if constexpr (SPLIT) {  // rows [32 h, 32 h + 32) of the hi, mid and lo parts (64 rows apart) of V^T: three 32-row boxes
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              tma_load_2d(sB + stage * Cfg::B_BYTES + q * 32 * BLOCK_K * 2, &tmB, &full[stage], kb * BLOCK_K, q * 64 + n_blk * 32);
+          } else {
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -323,7 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -349,11 +361,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + wq * 32 + lane;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
-      if constexpr (MODE == B200D_EPI_CHEB) {
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      if constexpr (MODE == B200D_EPI_CHEB && SPLIT) {
+        cheb_epilogue_cols<32, 64>(p, row, t_row, 0, n_blk * 32);
+      } else if constexpr (MODE == B200D_EPI_CHEB) {
         constexpr int B = (BLOCK_N == 192) ? 64 : 32;  // one block of vectors per launch (N == BLOCK_N)
 #pragma unroll 1
-        for (int c0 = 0; c0 < B; c0 += 32) cheb_epilogue_cols<B>(p, row, t_row, c0);
+        for (int c0 = 0; c0 < B; c0 += 32) cheb_epilogue_cols<B, B>(p, row, t_row, c0, c0);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -568,7 +582,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row = m_blk * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
       if constexpr (MODE == B200D_EPI_CHEB) {
-        cheb_epilogue_cols<64>(p, row, t_row, half * 32);
+        cheb_epilogue_cols<64, 64>(p, row, t_row, half * 32, half * 32);
       } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
 #pragma unroll 1
         for (int c = half * 4; c < half * 4 + 4; ++c) {
@@ -724,7 +738,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BLOCK_N);
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (BLOCK_N == 96 ? 2 : p.N / BLOCK_N);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   B200D_CHECK_LAUNCH();
@@ -742,6 +756,24 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   constexpr int BN = (MODE == B200D_EPI_CHEB) ? 192 : 256;
   const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (p.N / BN);
   int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+  // development knobs for tools/concurrency_check.py (the pair kernel next to another stream's kernels, see b200d.h)
+  static const int exp_pairs = getenv("B200D_EXP_PAIRS") ? atoi(getenv("B200D_EXP_PAIRS")) : 0;
+  static const int exp_policy = getenv("B200D_EXP_POLICY") ? atoi(getenv("B200D_EXP_POLICY")) : 0;
+  if (exp_pairs > 0 && pairs > exp_pairs) pairs = exp_pairs;
+  if (exp_policy != 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(THREADS2);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+    attr[0].val.clusterSchedulingPolicyPreference = exp_policy == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyLoadBalancing;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    return B200D_OK;
+  }
   kern<<<2 * pairs, THREADS2, SMEM2_BYTES, stream>>>(ta, tb, p);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
@@ -815,15 +847,19 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
     if (mode != B200D_EPI_BIAS || !use_2cta || epi->rows_per_seg < 32)
       return set_error(B200D_EINVAL, "%s: epi.colsum needs B200D_EPI_BIAS on a launch that takes the CTA-pair kernel and rows_per_seg >= 32%s", "b200d_gemm_f16");
   }
+  // 64-vector Chebyshev products that leave SMs idle as one tile per 128 rows: two CTAs per row tile (BLOCK_N 96 kernel)
+  static const bool env_no_split = getenv("B200D_CHEB_NO_SPLIT") != nullptr;
+  const bool cheb_split = mode == B200D_EPI_CHEB && N == 192 && !use_2cta && !env_no_split && (M + BLOCK_M - 1) / BLOCK_M < kNumSMs;
   CUtensorMap ta, tb;
   int rc = make_map(&ta, A, bf16, M, K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&tb, W, bf16, N, K, ldw, use_2cta ? (mode == B200D_EPI_CHEB ? 96 : 128) : block_n);
+  rc = make_map(&tb, W, bf16, N, K, ldw, cheb_split ? 32 : use_2cta ? (mode == B200D_EPI_CHEB ? 96 : 128) : block_n);
   if (rc) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.epi = *epi;
   if (use_2cta) return dispatch_mode_2cta(ta, tb, p, as_stream(stream));
   if (mode == B200D_EPI_CHEB) {
+    if (cheb_split) return launch<96, B200D_EPI_CHEB, true>(ta, tb, p, as_stream(stream));
     if (N == 192) return launch<192, B200D_EPI_CHEB, true>(ta, tb, p, as_stream(stream));
     return launch<128, B200D_EPI_CHEB, true>(ta, tb, p, as_stream(stream));
   }

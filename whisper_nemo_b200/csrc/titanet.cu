@@ -490,10 +490,11 @@ extern "C" size_t b200d_titanet_workspace_bytes(const b200d_titanet_desc* desc, 
 }
 
 extern "C" int b200d_titanet_forward(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav, const float* logmel,
-                                     const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_seg, int32_t fixed_len,
-                                     int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes, void* stream) {
+                                     const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_on_stream, int32_t n_seg,
+                                     int32_t fixed_len, int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes,
+                                     void* stream) {
   B200D_CHECK_ARG(desc && packed_dev && wav && seg_start && seg_len && emb_out && ws);
-  B200D_CHECK_ARG(n_seg > 0 && fixed_len > 0 && ld_emb >= desc->emb && desc->n_blocks >= 3);
+  B200D_CHECK_ARG(n_seg > 0 && n_on_stream >= 0 && n_on_stream <= n_seg && fixed_len > 0 && ld_emb >= desc->emb && desc->n_blocks >= 3);
   B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(packed_dev) & 255) == 0 && (reinterpret_cast<uintptr_t>(ws) & 255) == 0);
   const int T = fixed_len / 160 + ((variant & B200D_FEAT_NO_PLUS_ONE) ? 0 : 1);
   B200D_CHECK_ARG(T >= 2);
@@ -512,8 +513,9 @@ extern "C" int b200d_titanet_forward(const b200d_titanet_desc* desc, const void*
   for (int c0 = 0; c0 < n_seg; c0 += group) {
     const int n = n_seg - c0 < group ? n_seg - c0 : group;
     {
-      ProfScope ps("featurize_windows", 0, st, 2);
-      RC(b200d_featurize_windows(wav, n_wav, logmel, seg_start + c0, seg_len + c0, seg_row0 ? seg_row0 + c0 : nullptr, n, fixed_len,
+      ProfScope ps("featurize_windows", 0, st, 3);
+      const int fast = n_on_stream - c0 < 0 ? 0 : (n_on_stream - c0 > n ? n : n_on_stream - c0);
+      RC(b200d_featurize_windows(wav, n_wav, logmel, seg_start + c0, seg_len + c0, seg_row0 ? seg_row0 + c0 : nullptr, fast, n, fixed_len,
                                  reinterpret_cast<const int32_t*>(pk + desc->fb_start), reinterpret_cast<const int32_t*>(pk + desc->fb_off),
                                  reinterpret_cast<const float*>(pk + desc->fb_w), desc->fb_nnz, reinterpret_cast<const float*>(pk + desc->window),
                                  variant, b.feat_scratch, b.x0, desc->feat_pad, nullptr, st));

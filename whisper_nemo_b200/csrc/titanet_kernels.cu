@@ -7,6 +7,8 @@
 //           nemo/collections/asr/parts/submodules/tdnn_attention.py (AttentivePoolLayer).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b200d {
 
 __device__ __forceinline__ void load4h(const __half* p, float (&v)[4]) {
@@ -364,10 +366,15 @@ extern "C" int b200d_depthwise_conv(const void* x, void* y, const float* w, int3
   const __half* xi = reinterpret_cast<const __half*>(x);
   __half* yo = reinterpret_cast<__half*>(y);
   cudaStream_t st = as_stream(stream);
-#define B200D_DW(KS)                                                                                      \
-  if (C == 1024) depthwise_kernel<KS, 1024><<<grid, threads, 0, st>>>(xi, yo, w, n_seg, T, C, strips);   \
-  else if (C == 128) depthwise_kernel<KS, 128><<<grid, threads, 0, st>>>(xi, yo, w, n_seg, T, C, strips); \
-  else depthwise_kernel<KS, 0><<<grid, threads, 0, st>>>(xi, yo, w, n_seg, T, C, strips)
+  // development knob for tools/concurrency_check.py: dynamic shared memory that only lowers this kernel's residency per SM
+  static const int dw_smem = getenv("B200D_EXP_DW_SMEM") ? atoi(getenv("B200D_EXP_DW_SMEM")) : 0;
+#define B200D_DW(KS)                                                                                            \
+  if (C == 1024) {                                                                                              \
+    if (dw_smem > 48 * 1024) cudaFuncSetAttribute(depthwise_kernel<KS, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem); \
+    depthwise_kernel<KS, 1024><<<grid, threads, dw_smem, st>>>(xi, yo, w, n_seg, T, C, strips);                 \
+  }                                                                                                             \
+  else if (C == 128) depthwise_kernel<KS, 128><<<grid, threads, dw_smem, st>>>(xi, yo, w, n_seg, T, C, strips); \
+  else depthwise_kernel<KS, 0><<<grid, threads, dw_smem, st>>>(xi, yo, w, n_seg, T, C, strips)
   switch (ksize) {
     case 3: B200D_DW(3); break;
     case 7: B200D_DW(7); break;

@@ -267,24 +267,23 @@ class ClusteringDiarizer:
             rank, world = sharding.rank_world()
             lo, hi = sharding.shard_range(n, rank, world)
             out = torch.empty(hi - lo, 192, dtype=torch.float32, device=self.device)
-        # one upload per array and scale; the per-length groups below are device-side index_selects
-        dev_arrays = plan.get("_dev")
-        if dev_arrays is None or dev_arrays[0].device != self.device:
-            dev_arrays = plan["_dev"] = tuple(torch.from_numpy(np.ascontiguousarray(plan[k].astype(np.int32))).to(self.device)
-                                              for k in ("start", "len", "row0"))
-        st_all, ln_all, r0_all = dev_arrays
-        uniq_fixed = np.unique(fixed[lo:hi])
-        for fl in uniq_fixed:
-            if len(uniq_fixed) == 1:
-                st, ln, r0, idx_t = st_all[lo:hi], ln_all[lo:hi], r0_all[lo:hi], None
-            else:
-                idx_t = torch.from_numpy(lo + np.nonzero(fixed[lo:hi] == fl)[0]).to(self.device)
-                st, ln, r0 = st_all.index_select(0, idx_t), ln_all.index_select(0, idx_t), r0_all.index_select(0, idx_t)
-            emb = self._speaker_model.embed_segments(wav_dev, st, ln, int(fl), logmel=logmel, seg_row0=r0 if logmel is not None else None)
-            if idx_t is None:
-                out.copy_(emb)
-            else:
-                out.index_copy_(0, idx_t - lo, emb)
+        # per tiled-up length: the windows of this rank's slice, those on a log-mel stream first (the featurizer handles the
+        # two kinds with different kernels); index / descriptor arrays are uploaded once per plan and slice
+        groups = plan.setdefault("_groups", {}).get((lo, hi, str(self.device)))
+        if groups is None:
+            groups = []
+            i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.int32))).to(self.device)
+            for fl in np.unique(fixed[lo:hi]):
+                idx = lo + np.nonzero(fixed[lo:hi] == fl)[0]
+                on_stream = plan["row0"][idx] >= 0
+                idx = np.concatenate([idx[on_stream], idx[~on_stream]])
+                groups.append((int(fl), int(on_stream.sum()), torch.from_numpy(idx - lo).to(self.device), i32(plan["start"][idx]), i32(plan["len"][idx]),
+                               i32(plan["row0"][idx])))
+            plan["_groups"][(lo, hi, str(self.device))] = groups
+        for fl, n_fast, pos, st, ln, r0 in groups:
+            emb = self._speaker_model.embed_segments(wav_dev, st, ln, fl, logmel=logmel, seg_row0=r0 if logmel is not None else None,
+                                                     n_on_stream=n_fast)
+            out.index_copy_(0, pos, emb)
         if self.shard_windows:
             from . import sharding
 

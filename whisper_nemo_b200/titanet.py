@@ -222,9 +222,12 @@ def gemm(A, W, out, mode, M=None, bias=None, scale=None, shift=None, rowvec=None
 
 
 def featurize(pk: PackedTitaNet, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int,
-              out16: torch.Tensor = None, want_f32: bool = False, logmel: torch.Tensor = None, seg_row0: torch.Tensor = None):
+              out16: torch.Tensor = None, want_f32: bool = False, logmel: torch.Tensor = None, seg_row0: torch.Tensor = None,
+              n_on_stream: int = None):
     """wav float32 [n] on device; seg_start / seg_len int32 [n_seg] on device.  `logmel` / `seg_row0`: the recording's
-    stream frames (mel_stream) and each segment's first row in them -- interior frames are then copied, not recomputed.
+    stream frames (mel_stream) and each segment's first row in them -- interior frames are then copied, not recomputed;
+    `n_on_stream`: how many leading segments are on a stream (the caller orders them first; default: unknown -> 0, every
+    segment's non-interior frames are then computed by the spread-out kernel).
     Returns (fp16 [n_seg*T, 128], optional float32 [n_seg, T, 80])."""
     n_seg = seg_start.numel()
     T = frames_of(fixed_len)
@@ -234,7 +237,8 @@ def featurize(pk: PackedTitaNet, wav: torch.Tensor, seg_start: torch.Tensor, seg
     if logmel is None or seg_row0 is None:
         logmel = seg_row0 = None
     scratch = torch.empty(n_seg * T, FEAT, dtype=torch.float32, device=wav.device)
-    _cabi.call("b200d_featurize_windows", ptr(wav), wav.numel(), ptr(logmel), ptr(seg_start), ptr(seg_len), ptr(seg_row0), n_seg, fixed_len,
+    _cabi.call("b200d_featurize_windows", ptr(wav), wav.numel(), ptr(logmel), ptr(seg_start), ptr(seg_len), ptr(seg_row0),
+               int(n_on_stream or 0) if logmel is not None else 0, n_seg, fixed_len,
                ptr(pk.fb_start), ptr(pk.fb_off), ptr(pk.fb_w), pk.fb_w.numel(), ptr(pk.window), FEATURIZER_VARIANT, ptr(scratch), ptr(out16),
                out16.stride(0), ptr(out32), _cabi._stream())
     return out16, out32
@@ -463,12 +467,12 @@ class TitaNetB200:
 
     @torch.no_grad()
     def embed_segments(self, wav: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor, fixed_len: int, taps: dict = None,
-                       logmel: torch.Tensor = None, seg_row0: torch.Tensor = None):
-        """All segments share `fixed_len` (batch max under fixed_seq collate).  `logmel` / `seg_row0`: see featurize.
-        Returns float32 [n_seg, 192].  `taps` (a dict) selects the step-by-step reference orchestration and receives the
+                       logmel: torch.Tensor = None, seg_row0: torch.Tensor = None, n_on_stream: int = None):
+        """All segments share `fixed_len` (batch max under fixed_seq collate).  `logmel` / `seg_row0` / `n_on_stream`: see
+        featurize.  Returns float32 [n_seg, 192].  `taps` (a dict) selects the step-by-step reference orchestration and receives the
         intermediate activations."""
         if taps is not None:
-            return self._embed_segments_stepwise(wav, seg_start, seg_len, fixed_len, taps, logmel, seg_row0)
+            return self._embed_segments_stepwise(wav, seg_start, seg_len, fixed_len, taps, logmel, seg_row0, n_on_stream)
         import ctypes
 
         n_seg = seg_start.numel()
@@ -477,7 +481,7 @@ class TitaNetB200:
             logmel = seg_row0 = None
         ws = self._workspace()
         _cabi.call("b200d_titanet_forward", ctypes.byref(self.desc), ptr(self.packed), ptr(wav), wav.numel(), ptr(logmel), ptr(seg_start), ptr(seg_len),
-                   ptr(seg_row0), n_seg, fixed_len, FEATURIZER_VARIANT, _cabi.gemm_flags(), ptr(out), out.stride(0), ptr(ws), ws.numel(), _cabi._stream())
+                   ptr(seg_row0), int(n_on_stream or 0) if logmel is not None else 0, n_seg, fixed_len, FEATURIZER_VARIANT, _cabi.gemm_flags(), ptr(out), out.stride(0), ptr(ws), ws.numel(), _cabi._stream())
         return out
 
     def _py_workspace(self, T):
@@ -488,7 +492,7 @@ class TitaNetB200:
             ws = self._pyws[key] = Workspace(self.max_frames, max(max_segs, 1024), self.device)
         return ws
 
-    def _embed_segments_stepwise(self, wav, seg_start, seg_len, fixed_len, taps, logmel=None, seg_row0=None):
+    def _embed_segments_stepwise(self, wav, seg_start, seg_len, fixed_len, taps, logmel=None, seg_row0=None, n_on_stream=None):
         n_seg = seg_start.numel()
         T = frames_of(fixed_len)
         ws = self._py_workspace(T)
@@ -497,6 +501,6 @@ class TitaNetB200:
         for c0 in range(0, n_seg, segs_per_chunk):
             c1 = min(n_seg, c0 + segs_per_chunk)
             featurize(self.pk, wav, seg_start[c0:c1], seg_len[c0:c1], fixed_len, out16=ws.x0, logmel=logmel,
-                      seg_row0=None if seg_row0 is None else seg_row0[c0:c1])
+                      seg_row0=None if seg_row0 is None else seg_row0[c0:c1], n_on_stream=max(0, min(int(n_on_stream or 0) - c0, c1 - c0)))
             out[c0:c1] = forward_frames(self.pk, ws, c1 - c0, T, taps)
         return out
