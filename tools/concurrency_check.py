@@ -1,5 +1,5 @@
 """Development aid: do two host threads launching kernels on two streams make progress together?
-usage: python tools/concurrency_check.py <variantA> <variantB> [seconds]   variants: big2cta small1cta cheb2cta featurize depthwise"""
+usage: python tools/concurrency_check.py <variantA> <variantB> [seconds]   variants: big2cta small1cta mid1cta cheb2cta featurize depthwise timestats jacobi kmeans eigvals torchcopy"""
 import os
 import sys
 import threading
@@ -48,6 +48,24 @@ def make(variant):
         st = (torch.arange(600, device=dev, dtype=torch.int32) * 12000).contiguous(); ln = torch.full((600,), 30400, dtype=torch.int32, device=dev)
         out16 = torch.empty(600 * 191, 128, dtype=torch.float16, device=dev)
         return lambda: tn.featurize(pk, wav, st, ln, 30400, out16=out16)
+    if variant == "jacobi":
+        g = torch.randn(64, 64, device=dev); g = g @ g.t()
+        ev = torch.empty(64, device=dev); V = torch.empty(64, 64, device=dev)
+        return lambda: _cabi.call("b200d_small_eig", _cabi.ptr(g), 64, _cabi.ptr(ev), _cabi.ptr(V), 0, _cabi._stream())
+    if variant == "kmeans":
+        X = torch.randn(10000, 50, device=dev)
+        return lambda: cl.kmeans_torch(X, 50)
+    if variant == "eigvals":
+        n, batch = 515, 30
+        a = torch.randn(batch, n, n, device=dev); a = a + a.transpose(1, 2)
+        work = torch.empty_like(a)
+        ws_bytes = _cabi.load().b200d_eigvals_workspace_bytes(batch, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev); ev = torch.empty(batch, 10, device=dev)
+
+        def run():
+            work.copy_(a)
+            _cabi.call("b200d_eigvals_batched", _cabi.ptr(work), batch, n, 9, _cabi.ptr(ev), _cabi.ptr(ws), ws_bytes, _cabi._stream())
+        return run
     if variant == "torchcopy":
         a = torch.randn(4096, 1024, device=dev); b = torch.empty_like(a)
         return lambda: b.copy_(a)

@@ -319,7 +319,9 @@ class single_cta_gemms:
 
     def __enter__(self):
         self.prev = gemm_flags()
-        _tls.gemm_flags = self.prev | GEMM_NO_PAIR
+        # B200D_PAIR_IN_STREAMS=1 (development): keep the pair kernel inside multi-stream regions -- the round-1 deadlock
+        # did not reproduce in round 2 (profiles/r02_concurrency_*.log); the conservative default stays off
+        _tls.gemm_flags = self.prev if os.environ.get("B200D_PAIR_IN_STREAMS") == "1" else self.prev | GEMM_NO_PAIR
         return self
 
     def __exit__(self, *exc):
