@@ -302,7 +302,7 @@ def run_b200(args):
         g = {"calls": 0, "ms": 0.0, "work": 0.0}      # the dominant kernel: gemm_tcgen05_2cta_kernel (all its launches)
         g_all = {"calls": 0, "ms": 0.0, "work": 0.0}  # every tcgen05 GEMM launch, small projections included
         for key, v in prof.items():
-            if key.startswith("b200d_gemm_f16"):
+            if key.startswith("b200d_gemm_f16") or key.startswith("b200d::gemm["):  # fine-grained calls / spans inside the composites
                 for f in g_all:
                     g_all[f] += v[f]
                 if "|2cta" in key:

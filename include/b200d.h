@@ -146,6 +146,13 @@ typedef struct b200d_gemm_epilogue {
   void* vt;               /* __nv_bfloat16 [N][ldvt] */
   int32_t ldvt;
   int32_t flags;          /* B200D_GEMM_* bits, 0 = default kernel choice */
+  /* CHEB on a row shard (b200d_eig_bottomk_sharded): n_peers > 0 -> the launch's rows are one rank's share of a product whose
+   * operands live at the same offsets of every rank's peer buffer (b200d_peer_group); vt -- and out with B200D_GEMM_PEER_OUT32 --
+   * is stored at (address + peer_delta[r]) for r < n_peers (byte distance from this rank's buffer to rank r's mapping of its
+   * own; one entry is 0 = the local copy).  n_peers == 0: plain local stores.                                                 */
+  int32_t n_peers;
+  int32_t pad_;
+  int64_t peer_delta[8];
   float* colsum;          /* B200D_EPI_BIAS on the CTA-pair kernel only, else must be NULL: float32 [ceil(M / 32)][2][N] partial
                              column sums of the fp16-rounded output over each group of 32 rows -- [g][0] the rows of the window
                              (rows_per_seg >= 32 rows each) that row 32 g belongs to, [g][1] the rows of the next window; reduced
@@ -157,6 +164,7 @@ typedef struct b200d_gemm_epilogue {
  * register-heavy kernel of ANOTHER stream (tools/concurrency_check.py), so a caller that keeps several streams busy at
  * once passes B200D_GEMM_NO_PAIR on the calls made inside that region and every such GEMM takes the 1-CTA kernel. */
 #define B200D_GEMM_NO_PAIR 1
+#define B200D_GEMM_PEER_OUT32 2 /* CHEB with n_peers > 0: also store the fp32 rows into every peer's buffer (default: bf16 split only) */
 
 int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K,
                    void* out, int32_t ldo, const b200d_gemm_epilogue* epi, void* stream);
@@ -369,6 +377,72 @@ int32_t b200d_eig_bottomk_block(int32_t k);
 size_t b200d_eig_bottomk_workspace_bytes(int32_t n, int32_t k, int32_t p, const b200d_eig_options* opt);
 int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* deg, int32_t n, int32_t k, int32_t p, float* x, int32_t ldx,
                       const b200d_eig_options* opt, b200d_eig_stats* stats, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One long recording on the GPUs of one NVSwitch box (the reference has no multi-GPU code): the N x N
+ * affinity and its graph are ROW-SHARDED -- rank r holds rows [lo_r, hi_r) -- and the iterative eigensolver's products run on
+ * the row shards, each rank storing its rows of the result straight into every peer's buffer over NVLink from the GEMM
+ * epilogue (no NCCL call per product), with a device-side flag barrier between products.
+ *
+ * Peer memory: every rank allocates ONE buffer of the same size (b200d_peer_alloc: cudaMalloc + CUDA IPC handle, the one
+ * allocation this library makes; released by b200d_peer_free), exchanges the 64-byte handles through the host (e.g.
+ * torch.distributed.all_gather_object) and maps the others (b200d_peer_open / b200d_peer_close).  The first
+ * B200D_PEER_HEADER_BYTES of each buffer are the barrier flags, the rest is laid out by the entry point that uses it.
+ * b200d_peer_group: rank / world (<= 8), base[r] = rank r's buffer as mapped into THIS process (base[rank] = the local
+ * allocation), bytes = size of each buffer, epoch = barrier counter advanced by the library (every rank must make the same
+ * sequence of calls on the group), timeout_ms = how long a barrier waits for a missing rank before the call fails (0: 10 s).
+ * ------------------------------------------------------------------------------------------ */
+#define B200D_MAX_PEERS 8
+#define B200D_PEER_HANDLE_BYTES 64
+#define B200D_PEER_HEADER_BYTES 4096
+#define B200D_PEER_STATUS_WORD 16 /* uint32 index in the header: set to 1 by a barrier that timed out */
+typedef struct b200d_peer_group {
+  int32_t rank, world;
+  void* base[B200D_MAX_PEERS];
+  uint64_t bytes;
+  uint32_t epoch;
+  uint32_t timeout_ms;
+} b200d_peer_group;
+int b200d_peer_alloc(size_t bytes, void** ptr, void* handle_host /* 64 bytes out, may be NULL */);
+int b200d_peer_open(const void* handle_host, void** ptr);
+int b200d_peer_close(void* ptr);
+int b200d_peer_free(void* ptr);
+/* Device-side barrier of the group on `stream` (one tiny kernel: system-scope release of this rank's epoch into every peer's
+ * header, acquire-spin on its own); orders the peer stores of everything enqueued before it on every rank's stream. */
+int b200d_peer_barrier(b200d_peer_group* grp, void* stream);
+/* Synchronises `stream` and fails if a barrier of the group timed out. */
+int b200d_peer_status(const b200d_peer_group* grp, void* stream);
+
+/* Row-sharded forms of the affinity / graph steps: same arithmetic, bit for bit, as the full-matrix entry points above.
+ *  cos_affinity_rows   rows [row_lo, row_hi) of b200d_cos_affinity: cos_rows float32 [row_hi - row_lo][n]; minmax[2] = min / max over
+ *                      THOSE rows (the caller reduces over ranks: min of mins, max of maxes).
+ *  fuse_scales_rows    rows [row_lo, row_hi) of b200d_fuse_scales; cos_host[s] holds the rows [cos_row0_host[s], ...) of scale s's
+ *                      matrix (every row map_s[i], row_lo <= i < row_hi, must be there); minmax_host[s]: the GLOBAL min / max.
+ *  topp_select_rows    the radix select of b200d_topp_binarize on m rows: sel uint8 [m][n] plus, per row, the threshold (as the
+ *                      order-preserving uint32 code of the float) and the last column selected among the entries equal to it.
+ *  sym_combine_rows    a_rows[i][j] = 0.5 ([j in top_p(row i)] + [i in top_p(row j)]) for the local rows i = row_lo + r, using the
+ *                      symmetry of the affinity (mat[i][j] == mat[j][i] bit for bit: both sides of the cosine are the same fused
+ *                      multiply-add chain) and the thresholds of ALL rows (thr_all / cut_all [n], gathered over the ranks);
+ *                      deg_rows float32 [m], fp16-rounded.                                                                       */
+int b200d_cos_affinity_rows(const float* xn, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi, float* cos_rows, float* minmax,
+                            void* stream);
+int b200d_fuse_scales_rows(int32_t n_scales, const float* const* cos_host, const int32_t* ns_host, const int32_t* cos_row0_host,
+                           const int32_t* const* map_host, const float* const* minmax_host, const float* weights_host,
+                           float* fused_rows, int32_t n_base, int32_t row_lo, int32_t row_hi, void* stream);
+int b200d_topp_select_rows(const float* mat_rows, int32_t m, int32_t n, int32_t p, void* sel_u8, uint32_t* thr, int32_t* cut,
+                           void* stream);
+int b200d_sym_combine_rows(const float* mat_rows, const void* sel_u8, const uint32_t* thr_all, const int32_t* cut_all, int32_t row_lo,
+                           int32_t m, int32_t n, void* a_rows_bf16, int32_t lda, float* deg_rows, void* stream);
+
+/* b200d_eig_bottomk on a row-sharded graph: a_rows_bf16 [row_hi - row_lo][lda] = this rank's rows of A, deg float32 [n] (all of
+ * it), x float32 [n][b] IN the same start block on every rank, OUT the same Ritz vectors on every rank -- bit for bit those of
+ * b200d_eig_bottomk on the whole graph (each output row's accumulation order does not depend on which rank computes it, and the
+ * small dense steps run replicated).  Always dense products.  grp->bytes >= b200d_eig_bottomk_sharded_peer_bytes(n, k).
+ * Synchronises `stream` once per outer iteration, like b200d_eig_bottomk.                                                   */
+size_t b200d_eig_bottomk_sharded_peer_bytes(int32_t n, int32_t k);
+int b200d_eig_bottomk_sharded(const void* a_rows_bf16, int32_t lda, const float* deg, int32_t n, int32_t row_lo, int32_t row_hi,
+                              int32_t k, float* x, int32_t ldx, const b200d_eig_options* opt, b200d_eig_stats* stats,
+                              b200d_peer_group* grp, void* stream);
 
 /* k-means of kmeans_torch / kmeans_plusplus_torch with the RNG draws supplied by the host
  * (torch.manual_seed(0) stream: first-centre index, rand(30) per further centre, fallback randints).

@@ -255,6 +255,27 @@ def _gloo_worker(rank, world, port, tmp):
         got = sharding.all_gather_chunk_results({w: truth[w] for w in mine_chunks}, n_chunks, m_chunk, lens)
         for w in range(n_chunks):
             assert torch.equal(got[w][0], truth[w][0]) and torch.equal(got[w][1], truth[w][1])
+        # row-sharded clustering: the small collectives of rowshard.DistComm (per-row thresholds / degrees / NME rows
+        # gathered in rank order, per-scale (min, max) reduced) and the host-side planning of the NME subsample
+        from whisper_nemo_b200 import rowshard
+
+        comm = rowshard.DistComm()
+        n = 4099
+        shards = rowshard.row_shards(n, world)
+        lo, hi = shards[rank]
+        counts = [h - l for l, h in shards]
+        full = torch.arange(n * 2, dtype=torch.int32).view(n, 2)
+        assert torch.equal(comm.all_gather_rows(full[lo:hi].clone(), counts), full)
+        mm = torch.tensor([[-0.25 - rank, 1.0], [0.1 * (rank + 1), 0.5 + rank]])
+        red = comm.all_reduce_minmax(mm)
+        assert torch.equal(red, torch.tensor([[-0.25 - (world - 1), 1.0], [0.1, 0.5 + (world - 1)]]))
+        ratio = max(1, int(n / 512))
+        sub_idx = np.arange(0, n, ratio)
+        cnt = [int(((sub_idx >= l) & (sub_idx < h)).sum()) for l, h in shards]
+        mat = torch.arange(n, dtype=torch.float32)[:, None] * 3 + torch.arange(n, dtype=torch.float32)[None, :]
+        mine = torch.from_numpy(sub_idx[(sub_idx >= lo) & (sub_idx < hi)] - lo)
+        sub = comm.all_gather_rows(mat[lo:hi].index_select(0, mine)[:, ::ratio].contiguous(), cnt)
+        assert torch.equal(sub, mat[::ratio, ::ratio])
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -331,3 +352,14 @@ def test_window_plan_and_mel_streams(tmp_path):
         n_full += int(full.sum())
         n_rows += int((fx // tn.HOP + 1).sum())
     assert n_full > 0 and stream_off[-1] < 0.45 * n_rows  # telephonic scales: two grid phases per region instead of ~10 recomputations
+
+
+def test_row_shards_cover_every_row_once():
+    from whisper_nemo_b200 import rowshard
+
+    for n, world in [(4096, 2), (10000, 3), (57599, 8), (130, 2), (4097, 8)]:
+        sh = rowshard.row_shards(n, world)
+        assert sh[0][0] == 0 and sh[-1][1] == n and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+        assert all(hi > lo for lo, hi in sh)
+        if n >= 16 * world * rowshard.ROW_ALIGN:
+            assert all(lo % rowshard.ROW_ALIGN == 0 for lo, _ in sh)

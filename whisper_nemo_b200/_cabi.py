@@ -37,11 +37,15 @@ class GemmEpilogue(Structure):
         ("vt", c_void_p),
         ("ldvt", c_int32),
         ("flags", c_int32),
+        ("n_peers", c_int32),
+        ("pad_", c_int32),
+        ("peer_delta", c_int64 * 8),
         ("colsum", c_void_p),
     ]
 
 
 GEMM_NO_PAIR = 1  # include/b200d.h B200D_GEMM_NO_PAIR
+GEMM_PEER_OUT32 = 2
 TITANET_MAX_BLOCKS = 8
 
 
@@ -72,6 +76,14 @@ class EigStats(Structure):
                 ("history", c_float * EIG_HISTORY)]
 
 
+MAX_PEERS, PEER_HANDLE_BYTES, PEER_HEADER_BYTES = 8, 64, 4096
+
+
+class PeerGroup(Structure):
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("base", c_void_p * MAX_PEERS), ("bytes", ctypes.c_uint64), ("epoch", ctypes.c_uint32),
+                ("timeout_ms", ctypes.c_uint32)]
+
+
 class ProfileSpan(Structure):
     _fields_ = [("name", ctypes.c_char * 48), ("ms", c_float), ("work", ctypes.c_double)]
 
@@ -96,6 +108,20 @@ _SIGNATURES = {
     "b200d_eig_bottomk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, POINTER(EigOptions)]),
     "b200d_eig_bottomk": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, POINTER(EigOptions), POINTER(EigStats),
                                     c_void_p, c_size_t, c_void_p]),
+    "b200d_eig_bottomk_sharded_peer_bytes": (c_size_t, [c_int32, c_int32]),
+    "b200d_eig_bottomk_sharded": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, POINTER(EigOptions),
+                                            POINTER(EigStats), POINTER(PeerGroup), c_void_p]),
+    "b200d_peer_alloc": (c_int32, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "b200d_peer_open": (c_int32, [c_void_p, POINTER(c_void_p)]),
+    "b200d_peer_close": (c_int32, [c_void_p]),
+    "b200d_peer_free": (c_int32, [c_void_p]),
+    "b200d_peer_barrier": (c_int32, [POINTER(PeerGroup), c_void_p]),
+    "b200d_peer_status": (c_int32, [POINTER(PeerGroup), c_void_p]),
+    "b200d_cos_affinity_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "b200d_fuse_scales_rows": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                         c_void_p]),
+    "b200d_topp_select_rows": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200d_sym_combine_rows": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_launch_count": (c_int64, []),
     "b200d_profile_start": (c_int32, []),
     "b200d_profile_stop": (c_int32, [POINTER(ProfileSpan), c_int32, POINTER(c_int32)]),
@@ -194,8 +220,10 @@ KERNELS_PER_CALL = {
     "b200d_masked_rowsum": 1, "b200d_gather_segment_mean": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
     "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
     "b200d_resid_norms": 2, "b200d_kmeans": 1, "b200d_csr_from_dense": 3, "b200d_spmm_cheb": 1,
+    "b200d_cos_affinity_rows": 3, "b200d_fuse_scales_rows": 1, "b200d_topp_select_rows": 1, "b200d_sym_combine_rows": 1, "b200d_peer_barrier": 1,
+    "b200d_peer_alloc": 0, "b200d_peer_open": 0, "b200d_peer_close": 0, "b200d_peer_free": 0, "b200d_peer_status": 0,
 }
-COMPOSITES = ("b200d_titanet_forward", "b200d_eig_bottomk", "b200d_titanet_mel_stream")  # many kernels per call: counted by the library (b200d_launch_count)
+COMPOSITES = ("b200d_titanet_forward", "b200d_eig_bottomk", "b200d_eig_bottomk_sharded", "b200d_titanet_mel_stream")  # many kernels per call: counted by the library (b200d_launch_count)
 launch_count = 0
 _pair_kernel_on = os.environ.get("B200D_GEMM_1CTA") is None
 _profile = None  # {name: [(event0, event1, work, stream)]} while a profiled step runs

@@ -181,7 +181,10 @@ class NMESC:
 
     def __init__(self, mat: torch.Tensor, max_num_speakers: int = 10, max_rp_threshold: float = 0.15, sparse_search: bool = True,
                  sparse_search_volume: int = 30, nme_mat_size: int = 512, use_subsampling_for_nme: bool = True,
-                 fixed_thres: float = -1.0, maj_vote_spk_count: bool = False):
+                 fixed_thres: float = -1.0, maj_vote_spk_count: bool = False, presampled_ratio: Optional[int] = None):
+        """presampled_ratio: `mat` already IS the strided subsample mat_full[::r, ::r] with r = presampled_ratio (the
+        row-sharded path gathers only those rows from the ranks); p-hat is still reported on the full matrix's scale."""
+        self.presampled_ratio = presampled_ratio
         self.max_num_speakers = int(max_num_speakers)
         self.max_rp_threshold = max_rp_threshold
         self.use_subsampling_for_nme = use_subsampling_for_nme
@@ -211,8 +214,11 @@ class NMESC:
         mat = self.mat
         N = mat.shape[0]
         dev = mat.device
-        ratio = max(1, int(N / self.nme_mat_size)) if self.use_subsampling_for_nme else 1
-        n = len(range(0, N, ratio))
+        if self.presampled_ratio is not None:
+            ratio, n, stride = int(self.presampled_ratio), N, 1
+        else:
+            ratio = max(1, int(N / self.nme_mat_size)) if self.use_subsampling_for_nme else 1
+            n, stride = len(range(0, N, ratio)), ratio
         if n > 1024:
             raise ValueError(f"NME sweep matrix of size {n} exceeds the 1024 limit of the rank kernel (nme_mat_size too large)")
         self.p_value_list = self.getPvalueList(n)
@@ -220,7 +226,7 @@ class NMESC:
         np_ = len(p_list)
         rank = torch.empty(n, n, dtype=torch.int16, device=dev)
         rankT = torch.empty(n, n, dtype=torch.int16, device=dev)
-        _cabi.call("b200d_row_rank", ptr(mat), mat.stride(0), ratio, n, ptr(rank), ptr(rankT), _s())
+        _cabi.call("b200d_row_rank", ptr(mat), mat.stride(0), stride, n, ptr(rank), ptr(rankT), _s())
         m = min(self.max_num_speakers, n - 1)  # gaps[:max_num_speakers] needs lambda_0 .. lambda_m
         n_low = m + 1
         evals_all = []
@@ -609,6 +615,9 @@ class SpeakerClustering:
         self.debug = {}
         self.keep_affinity = False  # parity tests set this to read the fused N x N matrix back (13 GB for a 4-hour recording)
         self.fused_affinity: Optional[torch.Tensor] = None
+        # rowshard.DistComm / LocalComm: one long recording with the affinity, its graph and the eigensolver's products
+        # row-sharded over the ranks of the communicator (recordings of >= rowshard.MIN_ROWS_TO_SHARD base windows)
+        self.row_comm = None
 
     def forward_unit_infer(self, mat: torch.Tensor, oracle_num_speakers: int = -1, max_num_speakers: int = 8,
                            max_rp_threshold: float = 0.15, sparse_search_volume: int = 30, est_num_of_spk_enhanced: int = -1,
@@ -649,6 +658,13 @@ class SpeakerClustering:
             est_num_of_spk_enhanced = -1
         if oracle_num_speakers > 0:
             max_num_speakers = oracle_num_speakers
+        if self.row_comm is not None and self.row_comm.world > 1 and est_num_of_spk_enhanced < 0 and not self.keep_affinity:
+            from . import rowshard
+
+            if emb.shape[0] >= rowshard.MIN_ROWS_TO_SHARD:
+                return rowshard.forward_infer_rows(self, self.row_comm, self.embeddings_in_scales, self.timestamps_in_scales, multiscale_weights,
+                                                   oracle_num_speakers, max_rp_threshold, max_num_speakers, sparse_search_volume, fixed_thres,
+                                                   scale_mapping)
         mat = getMultiScaleCosAffinityMatrix(multiscale_weights, self.embeddings_in_scales, self.timestamps_in_scales, scale_mapping)
         self.fused_affinity = mat if self.keep_affinity else None
         return self.forward_unit_infer(mat=mat, oracle_num_speakers=oracle_num_speakers, max_rp_threshold=max_rp_threshold,

@@ -45,12 +45,14 @@ __global__ void minmax_decode_kernel(unsigned* mm) {
 constexpr int CT = 64;  // tile edge
 constexpr int CK = 16;  // k slab
 
+// row_lo / row_hi: the rows this launch computes (the whole matrix: 0 / n); cosm holds those rows only, row i at (i - row_lo).
+// Row tiles start at row_lo, which does not change any value: an entry is one fused multiply-add chain over k in ascending order.
 __global__ void __launch_bounds__(256) cos_affinity_kernel(const float* __restrict__ xn, int n, int d, float* __restrict__ cosm,
-                                                           unsigned* __restrict__ mm) {
+                                                           unsigned* __restrict__ mm, int row_lo, int row_hi) {
   __shared__ float sa[CK][CT + 4];
   __shared__ float sb[CK][CT + 4];
   __shared__ float s_min[8], s_max[8];
-  const int bi = blockIdx.y * CT, bj = blockIdx.x * CT;
+  const int bi = row_lo + blockIdx.y * CT, bj = blockIdx.x * CT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) cos_affinity_kernel(const float* __restri
       const int e = threadIdx.x + 256 * q;
       const int r = e >> 4, k = e & 15;
       const int gi = bi + r, gj = bj + r, gk = k0 + k;
-      sa[k][r] = (gi < n && gk < d) ? xn[static_cast<size_t>(gi) * d + gk] : 0.f;
+      sa[k][r] = (gi < row_hi && gk < d) ? xn[static_cast<size_t>(gi) * d + gk] : 0.f;
       sb[k][r] = (gj < n && gk < d) ? xn[static_cast<size_t>(gj) * d + gk] : 0.f;
     }
     __syncthreads();
@@ -86,13 +88,13 @@ __global__ void __launch_bounds__(256) cos_affinity_kernel(const float* __restri
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int i = bi + ty * 4 + a;
-    if (i >= n) continue;
+    if (i >= row_hi) continue;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int j = bj + tx * 4 + b;
       if (j >= n) continue;
       const float v = (i == j) ? 1.f : acc[a][b];
-      cosm[static_cast<size_t>(i) * n + j] = v;
+      cosm[static_cast<size_t>(i - row_lo) * n + j] = v;
       mn = fminf(mn, v);
       mx = fmaxf(mx, v);
     }
@@ -121,21 +123,23 @@ struct FuseParams {
   float w[kMaxScales];
   float* fused;
   int n;
+  int row_lo, row_hi;            // rows of the output this launch writes (fused holds those rows only)
+  int cos_row0[kMaxScales];      // first row of scale s's matrix present in cosm[s]
 };
 
 __global__ void __launch_bounds__(256) fuse_scales_kernel(const FuseParams p) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.n) return;
-  for (int i = blockIdx.y; i < p.n; i += gridDim.y) {
+  for (int i = p.row_lo + blockIdx.y; i < p.row_hi; i += gridDim.y) {
     float acc = 0.f;
 #pragma unroll 1
     for (int s = 0; s < p.S; ++s) {
       const float mn = __ldg(p.minmax[s]), mx = __ldg(p.minmax[s] + 1);
-      const int mi = __ldg(p.map[s] + i), mj = __ldg(p.map[s] + j);
+      const int mi = __ldg(p.map[s] + i) - p.cos_row0[s], mj = __ldg(p.map[s] + j);
       const float c = __ldg(p.cosm[s] + static_cast<size_t>(mi) * p.ns[s] + mj);
       acc += p.w[s] * ((c - mn) / (mx - mn));
     }
-    p.fused[static_cast<size_t>(i) * p.n + j] = acc;
+    p.fused[static_cast<size_t>(i - p.row_lo) * p.n + j] = acc;
   }
 }
 
@@ -207,7 +211,19 @@ extern "C" int b200d_cos_affinity(const float* xn, int32_t n, int32_t d, float* 
   unsigned* mm = reinterpret_cast<unsigned*>(minmax);
   minmax_init_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
   dim3 grid((n + CT - 1) / CT, (n + CT - 1) / CT);
-  cos_affinity_kernel<<<grid, 256, 0, as_stream(stream)>>>(xn, n, d, cosm, mm);
+  cos_affinity_kernel<<<grid, 256, 0, as_stream(stream)>>>(xn, n, d, cosm, mm, 0, n);
+  minmax_decode_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_cos_affinity_rows(const float* xn, int32_t n, int32_t d, int32_t row_lo, int32_t row_hi, float* cos_rows, float* minmax,
+                                       void* stream) {
+  B200D_CHECK_ARG(xn && cos_rows && minmax && n > 1 && d > 0 && row_lo >= 0 && row_lo < row_hi && row_hi <= n);
+  unsigned* mm = reinterpret_cast<unsigned*>(minmax);
+  minmax_init_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
+  dim3 grid((n + CT - 1) / CT, (row_hi - row_lo + CT - 1) / CT);
+  cos_affinity_kernel<<<grid, 256, 0, as_stream(stream)>>>(xn, n, d, cos_rows, mm, row_lo, row_hi);
   minmax_decode_kernel<<<1, 1, 0, as_stream(stream)>>>(mm);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
@@ -226,7 +242,34 @@ extern "C" int b200d_fuse_scales(int32_t n_scales, const float* const* cos_host,
   }
   p.fused = fused;
   p.n = n_base;
+  p.row_lo = 0;
+  p.row_hi = n_base;
+  for (int s = 0; s < kMaxScales; ++s) p.cos_row0[s] = 0;
   dim3 grid((n_base + 255) / 256, n_base < 65535 ? n_base : 65535);
+  fuse_scales_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_fuse_scales_rows(int32_t n_scales, const float* const* cos_host, const int32_t* ns_host, const int32_t* cos_row0_host,
+                                      const int32_t* const* map_host, const float* const* minmax_host, const float* weights_host,
+                                      float* fused_rows, int32_t n_base, int32_t row_lo, int32_t row_hi, void* stream) {
+  B200D_CHECK_ARG(n_scales > 0 && n_scales <= kMaxScales && cos_host && ns_host && cos_row0_host && map_host && minmax_host && weights_host && fused_rows);
+  B200D_CHECK_ARG(n_base > 0 && row_lo >= 0 && row_lo < row_hi && row_hi <= n_base);
+  FuseParams p;
+  p.S = n_scales;
+  for (int s = 0; s < kMaxScales; ++s) p.cos_row0[s] = 0;
+  for (int s = 0; s < n_scales; ++s) {
+    B200D_CHECK_ARG(cos_host[s] && map_host[s] && minmax_host[s] && ns_host[s] > 0 && cos_row0_host[s] >= 0);
+    p.cosm[s] = cos_host[s]; p.ns[s] = ns_host[s]; p.map[s] = map_host[s]; p.minmax[s] = minmax_host[s]; p.w[s] = weights_host[s];
+    p.cos_row0[s] = cos_row0_host[s];
+  }
+  p.fused = fused_rows;
+  p.n = n_base;
+  p.row_lo = row_lo;
+  p.row_hi = row_hi;
+  const int m = row_hi - row_lo;
+  dim3 grid((n_base + 255) / 256, m < 65535 ? m : 65535);
   fuse_scales_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
   B200D_CHECK_LAUNCH();
   return B200D_OK;

@@ -79,8 +79,15 @@ extern "C" size_t b200d_eig_bottomk_workspace_bytes(int32_t n, int32_t k, int32_
   return carve_eig(nullptr, n, b, use_csr(n, p, max_row_nnz, max_density), p, nullptr);
 }
 
-extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* deg, int32_t n, int32_t k, int32_t p, float* x, int32_t ldx,
-                                 const b200d_eig_options* opt, b200d_eig_stats* stats, void* ws, size_t ws_bytes, void* stream) {
+// The iteration.  grp == NULL: the whole graph on this GPU (a_bf16 = all n rows).  grp != NULL: a_bf16 holds the rows
+// [row_lo, row_hi) of the graph only; every product computes those rows and stores the bf16 split of the result (and, for the
+// two products per outer iteration whose fp32 result the small dense steps need in full, the fp32 rows) into EVERY rank's
+// workspace over NVLink, followed by a device-side barrier; the O(n b^2) steps around the products run replicated on every
+// rank from identical data, so all ranks take the same host decisions and end with the same block, bit for bit the one the
+// single-GPU call computes.
+static int eig_impl(const void* a_bf16, int32_t lda, const float* deg, int32_t n, int32_t row_lo, int32_t row_hi, int32_t k, int32_t p,
+                    float* x, int32_t ldx, const b200d_eig_options* opt, b200d_eig_stats* stats, void* ws, size_t ws_bytes,
+                    b200d_peer_group* grp, void* stream) {
   B200D_CHECK_ARG(a_bf16 && deg && x && ws && n > 0 && k > 0 && lda >= n && lda % 8 == 0);
   const int b = block_of(k);
   if (b == 0) return set_error(B200D_EINVAL, "%s: the subspace block is limited to 64 vectors (k <= 56)%s", "b200d_eig_bottomk");
@@ -89,7 +96,7 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
   const double tol = opt && opt->tol > 0 ? opt->tol : 2e-6;
   const int max_outer = opt && opt->max_outer > 0 ? opt->max_outer : 40;
   const int flags = opt ? opt->gemm_flags : 0;
-  const bool sparse = use_csr(n, p, opt ? opt->sparse_max_row_nnz : 32, opt ? opt->sparse_max_density : 1.0 / 64.0);
+  const bool sparse = grp == nullptr && use_csr(n, p, opt ? opt->sparse_max_row_nnz : 32, opt ? opt->sparse_max_density : 1.0 / 64.0);
   if (carve_eig(nullptr, n, b, sparse, p, nullptr) > ws_bytes)
     return set_error(B200D_EWORKSPACE, "%s: workspace too small (b200d_eig_bottomk_workspace_bytes)%s", "b200d_eig_bottomk");
   B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255) == 0);
@@ -114,7 +121,9 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
   }
   int gemms = 0;
   // one operator application: out = ca (deg x - A x) + cb x + cc xprev; vin / vout are the bf16 splits of x / out (dense path)
-  auto step = [&](const void* vin, float* out, const float* xx, const float* xprev, double ca, double cb, double cc, void* vout) -> int {
+  // `everywhere`: the fp32 result is needed in full on every rank (sharded call only; the bf16 split always is)
+  auto step = [&](const void* vin, float* out, const float* xx, const float* xprev, double ca, double cb, double cc, void* vout,
+                  bool everywhere) -> int {
     ++gemms;
     if (sparse) {
       ProfScope ps("spmm_cheb", 0, st);
@@ -122,16 +131,35 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
     }
     b200d_gemm_epilogue e{};
     e.mode = B200D_EPI_CHEB;
-    e.deg = deg;
-    e.x32 = xx;
-    e.xprev32 = xprev;
     e.ca = static_cast<float>(ca); e.cb = static_cast<float>(cb); e.cc = static_cast<float>(cc);
     e.ldx = b;
-    e.vt = vout;
     e.ldvt = ldvt;
     e.flags = flags;
-    ProfScope ps(gemm_uses_pair_kernel(n, nw, B200D_EPI_CHEB, flags) ? "gemm[cheb|2cta]" : "gemm[cheb]", 2.0 * n * nw * static_cast<double>(n), st);
-    return b200d_gemm_f16(a_bf16, lda, vin, ldvt, n, nw, n, out, b, &e, st);
+    if (grp == nullptr) {
+      e.deg = deg;
+      e.x32 = xx;
+      e.xprev32 = xprev;
+      e.vt = vout;
+      ProfScope ps(gemm_uses_pair_kernel(n, nw, B200D_EPI_CHEB, flags) ? "gemm[cheb|2cta]" : "gemm[cheb]", 2.0 * n * nw * static_cast<double>(n), st);
+      return b200d_gemm_f16(a_bf16, lda, vin, ldvt, n, nw, n, out, b, &e, st);
+    }
+    const int m_rows = row_hi - row_lo;
+    if (m_rows > 0) {
+      const size_t off = static_cast<size_t>(row_lo) * b;
+      e.deg = deg + row_lo;
+      e.x32 = xx + off;
+      e.xprev32 = xprev ? xprev + off : nullptr;
+      e.vt = vout ? reinterpret_cast<uint16_t*>(vout) + row_lo : nullptr;  // column row_lo + r of V^T for local row r
+      e.n_peers = grp->world;
+      for (int r = 0; r < grp->world; ++r)
+        e.peer_delta[r] = reinterpret_cast<const char*>(grp->base[r]) - reinterpret_cast<const char*>(grp->base[grp->rank]);
+      if (everywhere) e.flags |= B200D_GEMM_PEER_OUT32;
+      ProfScope ps(gemm_uses_pair_kernel(m_rows, nw, B200D_EPI_CHEB, flags) ? "gemm[cheb|2cta|rows]" : "gemm[cheb|rows]",
+                   2.0 * m_rows * nw * static_cast<double>(n), st);
+      RC(b200d_gemm_f16(a_bf16, lda, vin, ldvt, m_rows, nw, n, out + off, b, &e, st));
+    }
+    ProfScope ps("peer_barrier", 0, st);
+    return b200d_peer_barrier(grp, st);
   };
   auto gram = [&](const float* a, const float* c, float* out) -> int {
     ProfScope ps("gram", 0, st, 2);
@@ -152,7 +180,7 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
   for (; outer < max_outer;) {
     ++outer;
     // Rayleigh-Ritz on span(X): W = L X, H = X^T W, X <- X Q, W <- W Q
-    RC(step(w.vt[0], w.W, X, nullptr, 1.0, 0.0, 0.0, nullptr));
+    RC(step(w.vt[0], w.W, X, nullptr, 1.0, 0.0, 0.0, nullptr, true));
     RC(gram(X, w.W, w.G));
     { ProfScope ps("small_eig[jacobi]", 0, st); RC(b200d_small_eig(w.G, b, w.theta, w.Q, 0, st)); }
     { ProfScope ps("right_mul", 0, st); RC(b200d_right_mul(X, n, b, b, w.Q, X, w.vt[0], ldvt, st)); }
@@ -161,6 +189,7 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
     B200D_CHECK_CUDA(cudaMemcpyAsync(host.data(), w.theta, b * 4, cudaMemcpyDeviceToHost, st));
     B200D_CHECK_CUDA(cudaMemcpyAsync(host.data() + b, w.resid, b * 4, cudaMemcpyDeviceToHost, st));
     B200D_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (grp) RC(b200d_peer_status(grp, st));
     double rmax = 0.0;
     for (int j = 0; j < k; ++j) rmax = std::max(rmax, std::sqrt(std::max(static_cast<double>(host[b + j]), 0.0)));
     max_resid = rmax / up;
@@ -180,7 +209,7 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
     const double sigma1 = e / (0.0 - c);
     double sigma = sigma1;
     const double tau = 2.0 / sigma1;
-    RC(step(w.vt[0], w.Y[0], X, nullptr, sigma1 / e, -c * sigma1 / e, 0.0, w.vt[1]));
+    RC(step(w.vt[0], w.Y[0], X, nullptr, sigma1 / e, -c * sigma1 / e, 0.0, w.vt[1], m == 1));
     const float* prev = X;
     float* cur = w.Y[0];
     int vin = 1;
@@ -188,7 +217,7 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
       float* nxt = w.Y[(i - 1) % 3];
       const double sigma_new = 1.0 / (tau - sigma);
       const double ca = 2.0 * sigma_new / e;
-      RC(step(w.vt[vin], nxt, cur, prev, ca, -c * ca, -sigma * sigma_new, w.vt[1 - vin]));
+      RC(step(w.vt[vin], nxt, cur, prev, ca, -c * ca, -sigma * sigma_new, w.vt[1 - vin], i == m));
       sigma = sigma_new;
       prev = cur;
       cur = nxt;
@@ -207,4 +236,32 @@ extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* d
     stats->sparse = sparse ? 1 : 0;
   }
   return B200D_OK;
+}
+
+extern "C" int b200d_eig_bottomk(const void* a_bf16, int32_t lda, const float* deg, int32_t n, int32_t k, int32_t p, float* x, int32_t ldx,
+                                 const b200d_eig_options* opt, b200d_eig_stats* stats, void* ws, size_t ws_bytes, void* stream) {
+  return eig_impl(a_bf16, lda, deg, n, 0, n, k, p, x, ldx, opt, stats, ws, ws_bytes, nullptr, stream);
+}
+
+extern "C" size_t b200d_eig_bottomk_sharded_peer_bytes(int32_t n, int32_t k) {
+  const int b = block_of(k);
+  if (n <= 0 || b == 0) return 0;
+  return B200D_PEER_HEADER_BYTES + carve_eig(nullptr, n, b, false, 0, nullptr);
+}
+
+extern "C" int b200d_eig_bottomk_sharded(const void* a_rows_bf16, int32_t lda, const float* deg, int32_t n, int32_t row_lo, int32_t row_hi,
+                                         int32_t k, float* x, int32_t ldx, const b200d_eig_options* opt, b200d_eig_stats* stats,
+                                         b200d_peer_group* grp, void* stream) {
+  B200D_CHECK_ARG(grp && grp->world >= 1 && grp->world <= B200D_MAX_PEERS && grp->rank >= 0 && grp->rank < grp->world);
+  B200D_CHECK_ARG(row_lo >= 0 && row_lo <= row_hi && row_hi <= n);
+  B200D_CHECK_ARG(row_hi == row_lo || a_rows_bf16 != nullptr);
+  const size_t need = b200d_eig_bottomk_sharded_peer_bytes(n, k);
+  if (need == 0 || need > grp->bytes)
+    return set_error(B200D_EWORKSPACE, "%s: peer buffers too small (b200d_eig_bottomk_sharded_peer_bytes)%s", "b200d_eig_bottomk_sharded");
+  for (int r = 0; r < grp->world; ++r) B200D_CHECK_ARG(grp->base[r] != nullptr);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(grp->base[grp->rank]) + B200D_PEER_HEADER_BYTES;
+  // entry barrier: no rank may store into a peer's workspace while that peer still runs the previous user of it
+  RC(b200d_peer_barrier(grp, stream));
+  const void* a = a_rows_bf16 ? a_rows_bf16 : static_cast<const void*>(ws);  // (an empty shard never dereferences it)
+  return eig_impl(a, lda, deg, n, row_lo, row_hi, k, 0, x, ldx, opt, stats, ws, need - B200D_PEER_HEADER_BYTES, grp, stream);
 }

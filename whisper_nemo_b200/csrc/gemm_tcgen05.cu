@@ -236,20 +236,57 @@ __device__ __forceinline__ void cheb_epilogue_cols(const GemmParams& p, int row,
     const float* xp = e.xprev32 ? e.xprev32 + static_cast<size_t>(row) * e.ldx + c_out : nullptr;
     float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c_out;
     __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
+    if (e.n_peers <= 0) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
-      const float xv = x[j];
-      float y = e.ca * (dg * xv - av) + e.cb * xv;
-      if (xp) y += e.cc * xp[j];
-      o[j] = y;
-      if (vh) {
-        __nv_bfloat16 h, m, l;
-        split3_bf16(y, h, m, l);
-        const size_t vrow = static_cast<size_t>(c_out + j);
-        vh[(vrow) * e.ldvt + row] = h;
-        vh[(vrow + VS) * e.ldvt + row] = m;
-        vh[(vrow + 2 * VS) * e.ldvt + row] = l;
+      for (int j = 0; j < 32; ++j) {
+        const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+        const float xv = x[j];
+        float y = e.ca * (dg * xv - av) + e.cb * xv;
+        if (xp) y += e.cc * xp[j];
+        o[j] = y;
+        if (vh) {
+          __nv_bfloat16 h, m, l;
+          split3_bf16(y, h, m, l);
+          const size_t vrow = static_cast<size_t>(c_out + j);
+          vh[(vrow) * e.ldvt + row] = h;
+          vh[(vrow + VS) * e.ldvt + row] = m;
+          vh[(vrow + 2 * VS) * e.ldvt + row] = l;
+        }
+      }
+    } else {
+      // Row-sharded product: this rank owns the rows of the launch; the bf16 split of y (the next product's W operand, needed
+      // in full by every rank) goes straight into every peer's copy over NVLink (lanes = consecutive rows: 64-byte segments),
+      // the fp32 rows only when the caller needs them everywhere (B200D_GEMM_PEER_OUT32), as 16-byte stores.
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float av = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+        const float xv = x[j];
+        float y = e.ca * (dg * xv - av) + e.cb * xv;
+        if (xp) y += e.cc * xp[j];
+        r0[j] = __float_as_uint(y);
+      }
+      const bool out_everywhere = (e.flags & B200D_GEMM_PEER_OUT32) != 0;
+#pragma unroll 1
+      for (int r = 0; r < e.n_peers; ++r) {
+        const long long delta = e.peer_delta[r];
+        if (out_everywhere || delta == 0) {
+          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(o) + delta);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            o4[j >> 2] = make_float4(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]), __uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3]));
+        }
+        if (vh) {
+          __nv_bfloat16* vr = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(vh) + delta);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            __nv_bfloat16 h, m, l;
+            split3_bf16(__uint_as_float(r0[j]), h, m, l);
+            const size_t vrow = static_cast<size_t>(c_out + j);
+            vr[(vrow) * e.ldvt + row] = h;
+            vr[(vrow + VS) * e.ldvt + row] = m;
+            vr[(vrow + 2 * VS) * e.ldvt + row] = l;
+          }
+        }
       }
     }
   }

@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(1024) graph_reach_rank_kernel(const uint16_t* 
 }
 
 // ------------------------------------------------------------------------------------ full-matrix top-p select
-__global__ void __launch_bounds__(256) topp_select_kernel(const float* __restrict__ mat, int n, int p, unsigned char* __restrict__ sel) {
+// thr_out / cut_out (both or neither): the threshold code of the row and the column of the last selected entry equal to it --
+// all a row-sharded caller needs to evaluate [i in top_p(row j)] for rows j it does not hold (sym_combine_rows_kernel).
+__global__ void __launch_bounds__(256) topp_select_kernel(const float* __restrict__ mat, int n, int p, unsigned char* __restrict__ sel,
+                                                          unsigned* __restrict__ thr_out, int* __restrict__ cut_out) {
   __shared__ int hist[256];
   __shared__ unsigned s_prefix, s_mask;
   __shared__ int s_remaining;
@@ -174,6 +177,10 @@ __global__ void __launch_bounds__(256) topp_select_kernel(const float* __restric
     for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
     before += __popc(bal & ((1u << lane) - 1u));
     if (j < n) sel[static_cast<size_t>(i) * n + j] = (e > thr || (eq && before < need_eq)) ? 1 : 0;
+    if (cut_out != nullptr && eq && before == need_eq - 1) {
+      cut_out[i] = j;
+      thr_out[i] = thr;
+    }
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
@@ -202,6 +209,38 @@ __global__ void __launch_bounds__(1024) sym_combine_kernel(const unsigned char* 
   if (i < n && j < lda) a[static_cast<size_t>(i) * lda + j] = __float2bfloat16_rn(j < n ? v : 0.f);
   const float s = warp_sum(v);
   if (tx == 0 && i < n && s != 0.f) atomicAdd(deg + i, s);  // multiples of 0.5: exact, order independent
+}
+
+// Row shard of sym_combine: local row r is global row i = row_lo + r.  The transposed term [i in top_p(row j)] comes from the
+// symmetric entry mat[i][j] (== mat[j][i]) and row j's threshold / tie cut-off instead of from sel[j][i].
+__global__ void __launch_bounds__(256) sym_combine_rows_kernel(const float* __restrict__ mat_rows, const unsigned char* __restrict__ sel,
+                                                               const unsigned* __restrict__ thr_all, const int* __restrict__ cut_all,
+                                                               int row_lo, int n, __nv_bfloat16* __restrict__ a, int lda,
+                                                               float* __restrict__ deg) {
+  __shared__ float s_part[8];
+  const int r = blockIdx.x, i = row_lo + r;
+  const float* row = mat_rows + static_cast<size_t>(r) * n;
+  const unsigned char* srow = sel + static_cast<size_t>(r) * n;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < lda; j += 256) {
+    float v = 0.f;
+    if (j < n && j != i) {
+      const unsigned e = enc_desc(__ldg(row + j));
+      const unsigned tj = __ldg(thr_all + j);
+      const bool in_j = e > tj || (e == tj && i <= __ldg(cut_all + j));
+      v = 0.5f * (static_cast<float>(srow[j]) + (in_j ? 1.f : 0.f));
+    }
+    a[static_cast<size_t>(r) * lda + j] = __float2bfloat16_rn(v);
+    acc += v;
+  }
+  acc = warp_sum(acc);  // multiples of 0.5 below 2^24: exact in any order
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float d = 0.f;
+    for (int w = 0; w < 8; ++w) d += s_part[w];
+    deg[r] = __half2float(__float2half_rn(d));
+  }
 }
 
 __global__ void deg_round_kernel(float* deg, int n) {
@@ -251,10 +290,28 @@ extern "C" int b200d_topp_binarize(const float* mat, int32_t n, int32_t p, void*
   B200D_CHECK_ARG(mat && a_bf16 && deg && sel_u8 && n > 0 && p > 0 && p <= n && lda >= n && lda % 8 == 0);
   cudaStream_t s = as_stream(stream);
   B200D_CHECK_CUDA(cudaMemsetAsync(deg, 0, sizeof(float) * n, s));
-  topp_select_kernel<<<n, 256, 0, s>>>(mat, n, p, reinterpret_cast<unsigned char*>(sel_u8));
+  topp_select_kernel<<<n, 256, 0, s>>>(mat, n, p, reinterpret_cast<unsigned char*>(sel_u8), nullptr, nullptr);
   dim3 grid((lda + 31) / 32, (n + 31) / 32);
   sym_combine_kernel<<<grid, 1024, 0, s>>>(reinterpret_cast<const unsigned char*>(sel_u8), n, reinterpret_cast<__nv_bfloat16*>(a_bf16), lda, deg);
   deg_round_kernel<<<(n + 255) / 256, 256, 0, s>>>(deg, n);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_topp_select_rows(const float* mat_rows, int32_t m, int32_t n, int32_t p, void* sel_u8, uint32_t* thr, int32_t* cut,
+                                      void* stream) {
+  B200D_CHECK_ARG(mat_rows && sel_u8 && thr && cut && m > 0 && n > 0 && p > 0 && p <= n);
+  topp_select_kernel<<<m, 256, 0, as_stream(stream)>>>(mat_rows, n, p, reinterpret_cast<unsigned char*>(sel_u8), thr, cut);
+  B200D_CHECK_LAUNCH();
+  return B200D_OK;
+}
+
+extern "C" int b200d_sym_combine_rows(const float* mat_rows, const void* sel_u8, const uint32_t* thr_all, const int32_t* cut_all,
+                                      int32_t row_lo, int32_t m, int32_t n, void* a_rows_bf16, int32_t lda, float* deg_rows, void* stream) {
+  B200D_CHECK_ARG(mat_rows && sel_u8 && thr_all && cut_all && a_rows_bf16 && deg_rows && m > 0 && n > 0 && row_lo >= 0 && row_lo + m <= n);
+  B200D_CHECK_ARG(lda >= n && lda % 8 == 0);
+  sym_combine_rows_kernel<<<m, 256, 0, as_stream(stream)>>>(mat_rows, reinterpret_cast<const unsigned char*>(sel_u8), thr_all, cut_all, row_lo, n,
+                                                            reinterpret_cast<__nv_bfloat16*>(a_rows_bf16), lda, deg_rows);
   B200D_CHECK_LAUNCH();
   return B200D_OK;
 }

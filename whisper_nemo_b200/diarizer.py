@@ -104,6 +104,7 @@ class ClusteringDiarizer:
                                                            _get(p, "multiscale_weights"))
         self._cluster_params = _get(self.cfg, "diarizer.clustering.parameters")
         self.shard_windows = bool(shard_windows)
+        self._row_comm = None
         self._embed_streams: List[torch.cuda.Stream] = []
         self._cluster_streams: List[torch.cuda.Stream] = []
         self._speaker_model = self._init_speaker_model(speaker_model)
@@ -349,6 +350,15 @@ class ClusteringDiarizer:
             num_speakers = -1
         sc = LongFormSpeakerClustering(shard_chunks=self.shard_windows, chunk_streams=chunk_streams)
         sc.speaker_clustering.keep_affinity = self.keep_affinity
+        if self.shard_windows:
+            # a recording that takes the full-matrix path (<= embeddings_per_chunk windows): affinity, graph and the
+            # eigensolver's products row-sharded over the ranks (rowshard.py); the long-form path deals its chunks instead
+            from . import rowshard, sharding
+
+            if sharding.is_distributed() and os.environ.get("B200D_NO_ROW_SHARDING") != "1":
+                if self._row_comm is None:
+                    self._row_comm = rowshard.DistComm()
+                sc.speaker_clustering.row_comm = self._row_comm
         labels = sc.forward_infer(
             embeddings_in_scales=e["embeddings"],
             timestamps_in_scales=e["timestamps"],
