@@ -6,8 +6,11 @@ One "step" is one pass of the hot path over one recording per GPU: waveform -> m
 log-mel + TitaNet-L embeddings -> multi-scale affinity -> NME-SC -> spectral clustering -> labels on the host.
 N = 1 runs BASELINE config #3 (1-hour 8-speaker meeting, diar_infer_meeting.yaml), the configuration the headline
 target is quoted on; N > 1 gives every rank its own recording of the same shape (multi-file batches shard by
-recording, no data-path collective: weak scaling) and adds a `strong_4h` object: BASELINE config #5, ONE 4-hour
-recording whose windows, long-form chunks and spectral products are sharded over the N GPUs (NCCL all-gathers).
+recording, no data-path collective: weak scaling) and adds two objects for BASELINE config #5, ONE 4-hour recording over
+the N GPUs: `strong_4h` at the shipped knobs (embedding launch groups dealt to the ranks + NCCL all-gather, long-form
+chunks dealt to the ranks) and `strong_4h_fullmatrix` with embeddings_per_chunk raised above the recording's length, i.e.
+the N x N affinity, its graph and the eigensolver's products ROW-SHARDED (whisper_nemo_b200/rowshard.py: peer stores over
+NVLink from the GEMM epilogue, device-side barriers).
 `--shard` makes that single-recording sharding the main measurement of any workload (scaling "strong").
 Audio is synthetic (tools/workload.py) and the TitaNet-L weights are the fixed-seed random init
 (whisper_nemo_b200.checkpoint.seeded); speech regions come from the ground-truth RTTM (oracle VAD) -- VAD, WAV decoding
@@ -51,6 +54,15 @@ BATCH_WORKLOAD = "general_10min_batch"
 METRIC = "diarized audio-hours/sec (embed+NME-SC, device-timed)"
 UNIT = "audio-hours/s"
 SEED = 100  # recording seed of rank 0 (rank r: SEED + r); the reference arm diarizes rank 0's recording
+
+
+_T0 = time.perf_counter()
+
+
+def _progress(msg):
+    """Timestamped phase marker on stderr (the JSON line on stdout stays the only stdout output)."""
+    sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:6.1f}s] {msg}\n")
+    sys.stderr.flush()
 
 
 def _peaks():
@@ -167,7 +179,7 @@ def _shared_session(workload, seed, rank, barrier):
 
     domain, seconds, speakers, _ = WORKLOADS[workload]
     shared = os.path.join(tempfile.gettempdir(), f"b200d_bench_shared_{workload}_s{seed}")
-    if rank == 0:
+    if rank == 0 and not os.path.exists(os.path.join(shared, "input_manifest.json")):
         wl.make_session_cfg(shared, domain, seconds, speakers, seed)
     barrier()
     cfg = wl.load_domain_config(domain)
@@ -221,6 +233,7 @@ def run_b200(args):
     from whisper_nemo_b200 import ClusteringDiarizer, _cabi, checkpoint
 
     weights = checkpoint.seeded()
+    _progress("weights ready")
     # the bounded CPU sample runs BEFORE the process group exists: the other ranks block in the rendezvous (no NCCL barrier
     # spinning on the host cores next to it, as round 1 had) and torchrun's OMP_NUM_THREADS=1 is overridden explicitly
     cpu = None
@@ -230,9 +243,16 @@ def run_b200(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+        # waits that can last seconds (another rank synthesising audio, rank 0 running a recording alone) go through a gloo
+        # group: its barrier sleeps on a socket, while an NCCL barrier spins on a host core -- and on a box whose ranks share
+        # one CPU allowance the spinning ranks starved the working one (round 1's wrong N > 1 cpu_baseline; a 4-hour synthesis
+        # that took 30 s alone took > 4 min next to one spinning rank)
+        host_group = dist.new_group(backend="gloo")
+        _progress("process group up")
 
     def barrier():
         if world > 1:
+            dist.barrier(group=host_group)
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -257,6 +277,7 @@ def run_b200(args):
     prep_s = time.perf_counter() - t0
     wav_dev = diar._wav_host.to(dev)
     flops, frames, windows = titanet_flops(diar)
+    _progress(f"recording prepared ({windows} windows)")
 
     for _ in range(args.warmup):
         diar.run_device(wav_dev=wav_dev, timers=False)
@@ -270,6 +291,7 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     dev_ms, e2e_ms = all_max([dev_ms, e2e_ms])
     labels_main = {u: r["labels"].copy() for u, r in diar.results.items()}
+    _progress(f"timed steps done: {dev_ms / args.steps:.1f} ms per step")
     # ---- wall clock of the reference-facing call itself (prepare + device path + output files), same recording
     call_s = []
     for _ in range(0 if args.profiling else 3):
@@ -280,9 +302,11 @@ def run_b200(args):
     call_ms = all_max([1e3 * sum(call_s) / max(len(call_s), 1)])[0]
     host_split = dict(getattr(diar, "host_seconds", {}))
     # ---- N > 1: BASELINE config #5, one 4-hour recording sharded over all ranks (strong scaling), next to the weak-scaling line
-    strong = None
+    _progress("diarize() calls done")
+    strong = strong_full = None
     if world > 1 and not shard and not batch_mode and not args.no_strong and not args.profiling:
         strong = strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch)
+        strong_full = strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch, fullmatrix=True)
     # ---- untimed extras on rank 0: per-stage times, per-kernel roofline
     if args.profiling:
         if rank == 0:
@@ -350,19 +374,27 @@ def run_b200(args):
         }
         if strong is not None:
             line["strong_4h"] = strong
+        if strong_full is not None:
+            line["strong_4h_fullmatrix"] = strong_full
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
 
 
-def strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch, workload="telephonic_4h", steps=3, warmup=2):
-    """BASELINE config #5 on the N GPUs of this run: ONE 4-hour 12-speaker recording (telephonic YAML), windows of every scale,
-    long-form chunks and the rows of the spectral products sharded over the ranks, NCCL all-gathers in the data path; rank 0
-    also diarizes it alone, and the labels must be bit-identical."""
+def strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch, workload="telephonic_4h", steps=3, warmup=2, fullmatrix=False):
+    """BASELINE config #5 on the N GPUs of this run: ONE 4-hour 12-speaker recording (telephonic YAML).  The embedding launch
+    groups of every scale are dealt to the ranks (NCCL all-gather of the embeddings); the clustering is sharded either by
+    long-form chunk (shipped knobs: 6 chunks of 10 000 windows) or -- fullmatrix: embeddings_per_chunk raised above the
+    recording's length -- by ROWS of the 51 360^2 affinity / graph / eigensolver products (peer stores over NVLink).  Rank 0
+    also diarizes the recording alone; the labels must be bit-identical."""
     from whisper_nemo_b200 import ClusteringDiarizer
 
+    _progress(f"strong_4h{'_fullmatrix' if fullmatrix else ''}: synthesising / waiting for the shared recording")
     cfg, seconds = _shared_session(workload, 7, rank, barrier)
+    _progress("shared recording ready")
+    if fullmatrix:
+        cfg.diarizer.clustering.parameters.embeddings_per_chunk = 10 ** 7
     diar = ClusteringDiarizer(cfg=cfg, speaker_model=weights, shard_windows=True).to("cuda")
     diar._prepare()
     wav_dev = diar._wav_host.to(dev)
@@ -373,6 +405,7 @@ def strong_single_recording(args, weights, rank, world, dev, barrier, all_max, t
     diar.run_device(wav_dev=wav_dev, timers=True)
     stage_ms = dict(diar.stage_ms)
     sharded = next(iter(diar.results.values()))
+    _progress(f"sharded runs done: {dev_ms / steps:.1f} ms per step; rank 0 now runs it alone")
     out = None
     if rank == 0:
         solo = ClusteringDiarizer(cfg=cfg, speaker_model=weights, shard_windows=False).to("cuda")
@@ -386,16 +419,23 @@ def strong_single_recording(args, weights, rank, world, dev, barrier, all_max, t
         torch.cuda.synchronize()
         solo_ms = e0.elapsed_time(e1)
         alone = next(iter(solo.results.values()))
+        solo.run_device(wav_dev=wav_dev, timers=True)
+        solo_stage = dict(solo.stage_ms)
         hours = seconds / 3600.0
+        how = ("embeddings_per_chunk raised: full-matrix path, affinity / graph / eigensolver products row-sharded" if fullmatrix else
+               "shipped knobs: long-form path, chunks dealt to the ranks")
         out = {"workload": f"{workload} (BASELINE.json configs[4]): ONE {seconds:.0f} s synthetic 12-speaker recording, diar_infer_telephonic.yaml, "
-                           f"sharded over {world} GPUs", "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
+                           f"sharded over {world} GPUs ({how})", "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
                "value": round(hours * steps / (dev_ms * 1e-3), 4), "unit": UNIT, "ms_per_step": round(dev_ms / steps, 3),
                "e2e": {"value": round(hours * steps / (e2e_ms * 1e-3), 4), "ms_per_step": round(e2e_ms / steps, 3)},
                "one_gpu_ms_per_step": round(solo_ms, 3), "speedup_vs_one_gpu": round(solo_ms / (dev_ms / steps), 3),
                "labels_identical_to_one_gpu": bool(len(alone["labels"]) == len(sharded["labels"]) and (alone["labels"] == sharded["labels"]).all()),
                "base_scale_windows": int(len(sharded["labels"])), "speakers_found": int(sharded["debug"]["n_clusters"]),
-               "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}}
+               "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}, "one_gpu_stage_ms": {k: round(v, 3) for k, v in solo_stage.items()}}
+    del diar
+    torch.cuda.empty_cache()
     barrier()
+    _progress("strong measurement done")
     return out
 
 
@@ -506,6 +546,10 @@ def run_reference(args):
 
 
 def main():
+    import faulthandler
+
+    # a run that is still going after this many seconds dumps every thread's stack to stderr (and keeps going)
+    faulthandler.dump_traceback_later(int(os.environ.get("B200D_BENCH_WATCHDOG_S", "900")), repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

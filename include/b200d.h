@@ -227,6 +227,9 @@ typedef struct b200d_titanet_desc {
 int b200d_titanet_pack_weights(int32_t n_tensors, const char* const* names, const float* const* data_host, const int64_t* numel,
                                b200d_titanet_desc* desc, void* packed_host, size_t packed_bytes);
 size_t b200d_titanet_workspace_bytes(const b200d_titanet_desc* desc, int32_t max_frames, int32_t max_segs);
+/* Windows of `fixed_len` samples that b200d_titanet_forward processes per launch group with a workspace of ws_bytes (a caller that
+ * splits one batch of windows over several GPUs at multiples of this count reproduces the single-GPU launches exactly). */
+int32_t b200d_titanet_group_windows(const b200d_titanet_desc* desc, size_t ws_bytes, int32_t fixed_len, int32_t variant);
 int b200d_titanet_forward(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav, const float* logmel,
                           const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_on_stream, int32_t n_seg,
                           int32_t fixed_len, int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes,

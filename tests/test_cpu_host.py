@@ -276,6 +276,39 @@ def _gloo_worker(rank, world, port, tmp):
         mine = torch.from_numpy(sub_idx[(sub_idx >= lo) & (sub_idx < hi)] - lo)
         sub = comm.all_gather_rows(mat[lo:hi].index_select(0, mine)[:, ::ratio].contiguous(), cnt)
         assert torch.equal(sub, mat[::ratio, ::ratio])
+        # launch-group sharding of the embedding extraction (ClusteringDiarizer._extract_embeddings): every window computed once,
+        # by a launch group of the single-GPU run, and returned in manifest order on every rank
+        from whisper_nemo_b200.diarizer import ClusteringDiarizer
+
+        class _StubModel:
+            max_frames = 1000
+            calls = []
+
+            def group_windows(self, fixed_len):
+                return 7
+
+            def embed_segments(self, wav, st, ln, fl, logmel=None, seg_row0=None, n_on_stream=None):
+                self.calls.append((int(fl), int(n_on_stream), st.tolist()))
+                return (st.float()[:, None] * 1000 + float(fl)).expand(-1, 192).contiguous()
+
+        rng = np.random.default_rng(3)
+        n_win = 61
+        plan = {"n": n_win, "fixed": rng.choice([8000, 24000], n_win), "start": np.arange(n_win) * 10, "len": np.full(n_win, 8000),
+                "row0": np.where(rng.random(n_win) < 0.7, np.arange(n_win), -1)}
+        diar = object.__new__(ClusteringDiarizer)
+        diar.device, diar.shard_windows, diar._speaker_model, diar._shard_loads = torch.device("cpu"), True, _StubModel(), []
+        got = diar._extract_embeddings(plan, torch.zeros(1), logmel=torch.zeros(1))
+        want = torch.from_numpy(plan["start"] * 1000.0 + plan["fixed"]).float()[:, None].expand(-1, 192)
+        assert torch.equal(got, want)
+        seen = [None] * world
+        dist.all_gather_object(seen, _StubModel.calls)
+        starts = sorted(s for calls in seen for _, _, sts in calls for s in sts)
+        assert starts == plan["start"].tolist()                      # every window exactly once over the ranks
+        assert all(len(sts) <= 7 for calls in seen for _, _, sts in calls)
+        for calls in seen:                                           # on-stream windows lead every launch group
+            for fl, n_fast, sts in calls:
+                on = [plan["row0"][s // 10] >= 0 for s in sts]
+                assert on == sorted(on, reverse=True) and sum(on) == n_fast
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

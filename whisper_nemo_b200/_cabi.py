@@ -101,6 +101,7 @@ _SIGNATURES = {
                                  POINTER(GemmEpilogue), c_void_p]),
     "b200d_titanet_pack_weights": (c_int32, [c_int32, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), POINTER(TitaNetDesc), c_void_p, c_size_t]),
     "b200d_titanet_workspace_bytes": (c_size_t, [POINTER(TitaNetDesc), c_int32, c_int32]),
+    "b200d_titanet_group_windows": (c_int32, [POINTER(TitaNetDesc), c_size_t, c_int32, c_int32]),
     "b200d_titanet_forward": (c_int32, [POINTER(TitaNetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                         c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
     "b200d_titanet_mel_stream": (c_int32, [POINTER(TitaNetDesc), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),

@@ -489,6 +489,22 @@ extern "C" size_t b200d_titanet_workspace_bytes(const b200d_titanet_desc* desc, 
   return carve(*desc, nullptr, static_cast<size_t>(max_frames), static_cast<size_t>(max_segs), nullptr);
 }
 
+// windows per launch group: the largest count (<= n_seg) whose activations fit ws_bytes
+static long long group_windows(const b200d_titanet_desc& desc, size_t ws_bytes, int T, long long n_seg) {
+  long long lo = 0, hi = n_seg;
+  while (lo < hi) {
+    const long long mid = (lo + hi + 1) / 2;
+    if (carve(desc, nullptr, static_cast<size_t>(mid) * T, static_cast<size_t>(mid), nullptr) <= ws_bytes) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+extern "C" int32_t b200d_titanet_group_windows(const b200d_titanet_desc* desc, size_t ws_bytes, int32_t fixed_len, int32_t variant) {
+  if (!desc || fixed_len <= 0) return 0;
+  const int T = fixed_len / 160 + ((variant & B200D_FEAT_NO_PLUS_ONE) ? 0 : 1);
+  return static_cast<int32_t>(group_windows(*desc, ws_bytes, T, 1 << 24));
+}
+
 extern "C" int b200d_titanet_forward(const b200d_titanet_desc* desc, const void* packed_dev, const float* wav, int64_t n_wav, const float* logmel,
                                      const int32_t* seg_start, const int32_t* seg_len, const int32_t* seg_row0, int32_t n_on_stream, int32_t n_seg,
                                      int32_t fixed_len, int32_t variant, int32_t flags, float* emb_out, int32_t ld_emb, void* ws, size_t ws_bytes,
@@ -498,12 +514,7 @@ extern "C" int b200d_titanet_forward(const b200d_titanet_desc* desc, const void*
   B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(packed_dev) & 255) == 0 && (reinterpret_cast<uintptr_t>(ws) & 255) == 0);
   const int T = fixed_len / 160 + ((variant & B200D_FEAT_NO_PLUS_ONE) ? 0 : 1);
   B200D_CHECK_ARG(T >= 2);
-  // windows per launch group: the largest count whose activations fit the workspace
-  long long lo = 0, hi = n_seg;
-  while (lo < hi) {
-    const long long mid = (lo + hi + 1) / 2;
-    if (carve(*desc, nullptr, static_cast<size_t>(mid) * T, static_cast<size_t>(mid), nullptr) <= ws_bytes) lo = mid; else hi = mid - 1;
-  }
+  const long long lo = group_windows(*desc, ws_bytes, T, n_seg);
   if (lo < 1) return set_error(B200D_EWORKSPACE, "%s: workspace too small for one window (b200d_titanet_workspace_bytes)%s", "b200d_titanet_forward");
   const int group = static_cast<int>(lo);
   Buffers b;

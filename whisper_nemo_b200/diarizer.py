@@ -28,7 +28,7 @@ import torch
 from . import _cabi
 from . import speaker_utils as su
 from .config import as_config
-from .titanet import TitaNetB200
+from .titanet import TitaNetB200, frames_of
 
 
 def _get(cfg, dotted, default=None):
@@ -105,6 +105,7 @@ class ClusteringDiarizer:
         self._cluster_params = _get(self.cfg, "diarizer.clustering.parameters")
         self.shard_windows = bool(shard_windows)
         self._row_comm = None
+        self._shard_loads: List[int] = []
         self._embed_streams: List[torch.cuda.Stream] = []
         self._cluster_streams: List[torch.cuda.Stream] = []
         self._speaker_model = self._init_speaker_model(speaker_model)
@@ -251,45 +252,83 @@ class ClusteringDiarizer:
             pl["row0"] = row0[pos : pos + pl["n"]]
             pos += pl["n"]
         self._streams = (stream_start, stream_off)
+        self._shard_loads = []
 
     # ------------------------------------------------------------------ device work
     def _extract_embeddings(self, plan: dict, wav_dev: torch.Tensor, logmel: torch.Tensor = None) -> torch.Tensor:
         """All windows of one scale -> float32 [n, 192] on device (manifest order).  `logmel`: the stream frames of
-        `_mel_streams` (interior frames of every window are gathered from it instead of recomputed)."""
+        `_mel_streams` (interior frames of every window are gathered from it instead of recomputed).
+
+        shard_windows: the unit dealt to the ranks is the LAUNCH GROUP of the single-GPU run (the windows of one tiled-up
+        length, in its order, cut at multiples of b200d_titanet_group_windows), so every window is computed by exactly the
+        launches -- same neighbours, same position -- that compute it on one GPU and the all-gathered embeddings are bit for bit
+        the single-GPU ones (a window's position in its launch decides the summation order of the SqueezeExcite column sums)."""
         n = plan["n"]
         out = torch.empty(n, 192, dtype=torch.float32, device=self.device)
         if n == 0:
             return out
         fixed = plan["fixed"]
-        lo, hi = 0, n
+        rank, world = 0, 1
         if self.shard_windows:
             from . import sharding
 
             rank, world = sharding.rank_world()
-            lo, hi = sharding.shard_range(n, rank, world)
-            out = torch.empty(hi - lo, 192, dtype=torch.float32, device=self.device)
-        # per tiled-up length: the windows of this rank's slice, those on a log-mel stream first (the featurizer handles the
-        # two kinds with different kernels); index / descriptor arrays are uploaded once per plan and slice
-        groups = plan.setdefault("_groups", {}).get((lo, hi, str(self.device)))
+        # per tiled-up length: the windows, those on a log-mel stream first (the featurizer handles the two kinds with different
+        # kernels), cut into launch groups; index / descriptor arrays are uploaded once per plan
+        key = (rank, world, str(self.device), self._speaker_model.max_frames)
+        groups = plan.setdefault("_groups", {}).get(key)
         if groups is None:
-            groups = []
-            i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.int32))).to(self.device)
-            for fl in np.unique(fixed[lo:hi]):
-                idx = lo + np.nonzero(fixed[lo:hi] == fl)[0]
+            units = []  # (frames, fixed_len, windows on a stream, window indices)
+            for fl in np.unique(fixed):
+                idx = np.nonzero(fixed == fl)[0]
                 on_stream = plan["row0"][idx] >= 0
                 idx = np.concatenate([idx[on_stream], idx[~on_stream]])
-                groups.append((int(fl), int(on_stream.sum()), torch.from_numpy(idx - lo).to(self.device), i32(plan["start"][idx]), i32(plan["len"][idx]),
-                               i32(plan["row0"][idx])))
-            plan["_groups"][(lo, hi, str(self.device))] = groups
-        for fl, n_fast, pos, st, ln, r0 in groups:
+                n_fast = int(on_stream.sum())
+                step = len(idx) if world == 1 else max(1, self._speaker_model.group_windows(int(fl)))
+                for c0 in range(0, len(idx), step):
+                    part = idx[c0 : c0 + step]
+                    units.append((len(part) * frames_of(int(fl)), int(fl), max(0, min(n_fast - c0, len(part))), part))
+            owner = self._deal_launch_groups([u[0] for u in units], world)
+            i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.int32))).to(self.device)
+            mine, offs, pos = [], [0] * world, [None] * len(units)
+            for j, (_, fl, n_fast, idx) in enumerate(units):
+                r = owner[j]
+                pos[j] = (r, offs[r])  # rows [offs, offs + len) of rank r's block
+                offs[r] += len(idx)
+                if r == rank:
+                    mine.append((fl, n_fast, pos[j][1], len(idx), i32(plan["start"][idx]), i32(plan["len"][idx]), i32(plan["row0"][idx])))
+            pad = max(offs)
+            # where every window's embedding lies in the all-gathered [world * pad, 192] block
+            where = np.empty(n, dtype=np.int64)
+            for (r, o), (_, _, _, idx) in zip(pos, units):
+                where[idx] = r * pad + o + np.arange(len(idx))
+            groups = plan["_groups"][key] = (mine, offs[rank], pad, torch.from_numpy(where).to(self.device))
+        mine, n_mine, pad, where = groups
+        local = out if world == 1 else torch.zeros(pad, 192, dtype=torch.float32, device=self.device)
+        for fl, n_fast, o, cnt, st, ln, r0 in mine:
             emb = self._speaker_model.embed_segments(wav_dev, st, ln, fl, logmel=logmel, seg_row0=r0 if logmel is not None else None,
                                                      n_on_stream=n_fast)
-            out.index_copy_(0, pos, emb)
-        if self.shard_windows:
-            from . import sharding
+            local[o : o + cnt] = emb
+        if world == 1:
+            return out.index_select(0, where)
+        gathered = torch.empty(world * pad, 192, dtype=torch.float32, device=self.device)
+        torch.distributed.all_gather_into_tensor(gathered, local)
+        return gathered.index_select(0, where)
 
-            return sharding.all_gather_rows(out, n)
-        return out
+    def _deal_launch_groups(self, frames: List[int], world: int) -> List[int]:
+        """Owner rank of every launch group of one scale: largest first onto the least-loaded rank, the loads carried over the
+        scales of the recording (self._shard_loads; every rank computes the same assignment)."""
+        owner = [0] * len(frames)
+        if world == 1:
+            return owner
+        loads = self._shard_loads
+        if len(loads) != world:
+            loads[:] = [0] * world
+        for j in sorted(range(len(frames)), key=lambda i: (-frames[i], i)):
+            r = min(range(world), key=lambda q: (loads[q], q))
+            owner[j] = r
+            loads[r] += frames[j]
+        return owner
 
     def _mel_streams(self, wav_dev: torch.Tensor):
         """The recording's log-mel frames, each computed once (b200d_mel_stream); None when no window lies on a stream."""

@@ -456,6 +456,12 @@ class TitaNetB200:
             ws = self._ws[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return ws
 
+    def group_windows(self, fixed_len: int) -> int:
+        """Windows of `fixed_len` samples per launch group of embed_segments (b200d_titanet_group_windows)."""
+        import ctypes
+
+        return int(_cabi.load().b200d_titanet_group_windows(ctypes.byref(self.desc), self._workspace().numel(), int(fixed_len), FEATURIZER_VARIANT))
+
     def mel_stream(self, wav: torch.Tensor, stream_start: torch.Tensor, stream_off: torch.Tensor, total_rows: int) -> torch.Tensor:
         """log-mel rows float32 [total_rows, 80] of the planned streams (plan_mel_streams), each frame computed once."""
         import ctypes
