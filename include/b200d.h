@@ -157,6 +157,12 @@ typedef struct b200d_gemm_epilogue {
                              column sums of the fp16-rounded output over each group of 32 rows -- [g][0] the rows of the window
                              (rows_per_seg >= 32 rows each) that row 32 g belongs to, [g][1] the rows of the next window; reduced
                              to per-window means by b200d_se_mean_from_colsum (SqueezeExcite's pool without re-reading the output) */
+  /* CHEB: split-K form of the product.  splitk_ws != NULL (b200d_gemm_cheb_splitk_bytes(M, N, K) bytes, 16-byte aligned): the
+   * launch is cut into (128-row tile, segment of 24 x 64 columns of K) units that fill the chip whatever M is; their raw fp32
+   * accumulators go to the workspace and a second kernel sums them in ascending K order and applies the epilogue.  The
+   * summation order of an output row then depends on K only -- the same bits for any M, i.e. on any number of GPUs.       */
+  void* splitk_ws;
+  uint64_t splitk_ws_bytes;
 } b200d_gemm_epilogue;
 
 /* Kernel choice is a PER-CALL property (no process-wide state): large GEMMs run on a cluster-launched CTA-pair kernel
@@ -168,6 +174,7 @@ typedef struct b200d_gemm_epilogue {
 
 int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K,
                    void* out, int32_t ldo, const b200d_gemm_epilogue* epi, void* stream);
+size_t b200d_gemm_cheb_splitk_bytes(int32_t M, int32_t N, int32_t K);
 /* SqueezeExcite = b200d_time_stats(with_std=0) -> b200d_gemm_f16(fc.0, BIAS_RELU with zero bias)
  * -> b200d_gemm_f16(fc.2, SIGMOID_F32) -> gate float32 [n_seg][C].                                 */
 

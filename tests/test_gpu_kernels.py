@@ -202,6 +202,51 @@ def test_cheb_gemm_step(dev, n, b, pair):
     assert (rec - out).abs().max().item() <= 1e-6 * out.abs().max().item()
 
 
+@pytest.mark.parametrize("n,b", [(300, 32), (3000, 64), (10000, 64), (10000, 32), (1537, 32)])
+def test_cheb_gemm_step_split_k(dev, n, b):
+    """The split-K form of the Chebyshev step (what b200d_eig_bottomk uses): (row tile, 24-K-block segment) units + fix-up kernel.
+    Against fp64, and ROW-INVARIANT: a launch on any subset of the rows gives those rows bit for bit (the property the row-sharded
+    multi-GPU solver relies on), with and without a previous-step operand."""
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200 import clustering as cl
+    from whisper_nemo_b200._cabi import ptr
+
+    g = torch.Generator().manual_seed(n + b)
+    lda = (n + 7) // 8 * 8
+    a = (torch.rand(n, n, generator=g) < 0.05).float()
+    a = 0.5 * (a + a.t())
+    a.fill_diagonal_(0)
+    a16 = torch.zeros(n, lda, dtype=torch.bfloat16, device=dev)
+    a16[:, :n] = a.to(dev).bfloat16()
+    deg = a.sum(1).to(dev)
+    x = torch.randn(n, b, generator=g).to(dev)
+    xp = torch.randn(n, b, generator=g).to(dev)
+    nw = cl.cheb_operand_rows(b)
+    vt_in = torch.zeros(nw, lda, dtype=torch.bfloat16, device=dev)
+    _cabi.call("b200d_right_mul", ptr(x), n, b, b, None, None, ptr(vt_in), lda, _cabi._stream())
+    ws = torch.empty(int(_cabi.load().b200d_gemm_cheb_splitk_bytes(n, nw, n)), dtype=torch.uint8, device=dev)
+    ca, cb, cc = 0.37, -1.2, 0.6
+    ad = a.to(dev).double()
+    for prev in (xp, None):
+        out = torch.empty(n, b, dtype=torch.float32, device=dev)
+        vt_out = torch.zeros(nw, lda, dtype=torch.bfloat16, device=dev)
+        cl._gemm_cheb(a16, lda, vt_in, lda, n, nw, out, deg, x, prev, ca, cb, cc, vt_out, splitk=ws)
+        want = ca * (deg.double()[:, None] * x.double() - ad @ x.double()) + cb * x.double() + (cc * xp.double() if prev is not None else 0.0)
+        err = (out.double() - want).abs().max().item()
+        assert err <= 2e-5 * want.abs().max().item()
+        assert (_unsplit(vt_out, b, n) - out).abs().max().item() <= 1e-6 * out.abs().max().item()
+        # rows [lo, hi) alone: operands offset exactly as b200d_eig_bottomk_sharded offsets them
+        lo, hi = (n // 3) // 8 * 8, n - 5
+        part = torch.full((n, b), float("nan"), dtype=torch.float32, device=dev)
+        vt_part = torch.zeros(nw, lda, dtype=torch.bfloat16, device=dev)
+        cl._gemm_cheb(a16[lo:hi], lda, vt_in, lda, hi - lo, nw, part[lo:hi], deg[lo:hi], x[lo:hi], None if prev is None else prev[lo:hi], ca, cb, cc,
+                      vt_part[:, lo:], splitk=ws, k=n)
+        torch.cuda.synchronize()
+        assert torch.equal(part[lo:hi], out[lo:hi])
+        assert torch.equal(vt_part[:, lo:hi], vt_out[:, lo:hi])
+    print(f"split-K cheb step n={n} b={b}: max err {err:.3e}")
+
+
 def _clustered_graph(n, k, p, seed):
     from oracle import offline_clustering as oc
 

@@ -41,6 +41,8 @@ class GemmEpilogue(Structure):
         ("pad_", c_int32),
         ("peer_delta", c_int64 * 8),
         ("colsum", c_void_p),
+        ("splitk_ws", c_void_p),
+        ("splitk_ws_bytes", ctypes.c_uint64),
     ]
 
 
@@ -99,6 +101,7 @@ _SIGNATURES = {
     "b200d_depthwise_conv": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "b200d_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                  POINTER(GemmEpilogue), c_void_p]),
+    "b200d_gemm_cheb_splitk_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "b200d_titanet_pack_weights": (c_int32, [c_int32, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_int64), POINTER(TitaNetDesc), c_void_p, c_size_t]),
     "b200d_titanet_workspace_bytes": (c_size_t, [POINTER(TitaNetDesc), c_int32, c_int32]),
     "b200d_titanet_group_windows": (c_int32, [POINTER(TitaNetDesc), c_size_t, c_int32, c_int32]),
@@ -215,7 +218,7 @@ def check(rc, name):
 
 
 # kernels launched per C-ABI call (bench.py's gpu_launches claim is the sum over the timed region)
-KERNELS_PER_CALL = {
+KERNELS_PER_CALL = {  # (a split-K CHEB b200d_gemm_f16 call launches 2; the solver's products are counted by the library)
     "b200d_featurize_windows": 3, "b200d_mel_stream": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_mean_from_colsum": 1, "b200d_se_apply_relu": 1, "b200d_se_apply_relu_stats": 1,
     "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
     "b200d_masked_rowsum": 1, "b200d_gather_segment_mean": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,

@@ -295,7 +295,9 @@ def cheb_operand_rows(b: int) -> int:
     return 192 if b == 64 else 128
 
 
-def _gemm_cheb(A16, lda, vt_in, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vt_out):
+def _gemm_cheb(A16, lda, vt_in, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vt_out, splitk=None, k=None):
+    """One Chebyshev / Laplacian step as a b200d_gemm_f16 call; `splitk`: uint8 workspace of b200d_gemm_cheb_splitk_bytes(n, nw, n)
+    bytes -> the split-K form (what b200d_eig_bottomk always uses).  n: rows of this launch; k: columns of A (default n)."""
     epi = GemmEpilogue()
     epi.mode = _cabi.EPI_CHEB
     epi.deg = deg.data_ptr()
@@ -306,7 +308,9 @@ def _gemm_cheb(A16, lda, vt_in, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vt_
     epi.vt = vt_out.data_ptr() if vt_out is not None else None
     epi.ldvt = ldvt
     epi.flags = _cabi.gemm_flags()
-    _cabi.call("b200d_gemm_f16", ptr(A16), lda, ptr(vt_in), ldvt, n, nw, n, ptr(out), out.stride(0), ctypes.byref(epi), _s())
+    if splitk is not None:
+        epi.splitk_ws, epi.splitk_ws_bytes = splitk.data_ptr(), splitk.numel()
+    _cabi.call("b200d_gemm_f16", ptr(A16), lda, ptr(vt_in), ldvt, n, nw, n if k is None else k, ptr(out), out.stride(0), ctypes.byref(epi), _s())
 
 
 def _spmm_cheb(csr, n, b, out, deg, x, xprev, ca, cb, cc):
@@ -418,9 +422,10 @@ def bottom_eigvecs_stepwise(a16: torch.Tensor, deg: torch.Tensor, k: int, tol: f
             _spmm_cheb(csr, n, b, out, deg, x, xprev, ca, cb, cc)
     else:
         vt = [torch.zeros(nw, ldvt, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        splitk = torch.empty(int(_cabi.load().b200d_gemm_cheb_splitk_bytes(n, nw, n)), dtype=torch.uint8, device=dev)
 
         def step(vin, out, x, xprev, ca, cb, cc, vout):
-            _gemm_cheb(a16, lda, vin, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vout)
+            _gemm_cheb(a16, lda, vin, ldvt, n, nw, out, deg, x, xprev, ca, cb, cc, vout, splitk)
     G, Q, theta, resid = f32(b, b), f32(b, b), f32(b), f32(b)
     gws_bytes = _cabi.load().b200d_gram_workspace_bytes(n, b)
     gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev)

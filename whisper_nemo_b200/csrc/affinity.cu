@@ -42,61 +42,91 @@ __global__ void minmax_decode_kernel(unsigned* mm) {
   f[1] = mx;
 }
 
-constexpr int CT = 64;  // tile edge
-constexpr int CK = 16;  // k slab
+constexpr int CT = 128;  // tile edge
+constexpr int CK = 16;   // k slab
 
+// 128 x 128 tile per CTA, 8 x 8 outputs per thread (64 FMAs per 16 shared-memory floats; the first version's 64 x 64 / 4 x 4
+// tiling ran at 8.7 TFLOP/s, a quarter of what the fp32 pipe gives).  Every output is ONE fused multiply-add chain over k in
+// ascending order, whatever the tiling: cos[i][j] and cos[j][i] are the same chain (the symmetry sym_combine_rows relies on),
+// and the row-sharded launches give the bits of the full one.
 // row_lo / row_hi: the rows this launch computes (the whole matrix: 0 / n); cosm holds those rows only, row i at (i - row_lo).
-// Row tiles start at row_lo, which does not change any value: an entry is one fused multiply-add chain over k in ascending order.
 __global__ void __launch_bounds__(256) cos_affinity_kernel(const float* __restrict__ xn, int n, int d, float* __restrict__ cosm,
                                                            unsigned* __restrict__ mm, int row_lo, int row_hi) {
-  __shared__ float sa[CK][CT + 4];
-  __shared__ float sb[CK][CT + 4];
+  __shared__ __align__(16) float sa[CK][CT + 4];
+  __shared__ __align__(16) float sb[CK][CT + 4];
   __shared__ float s_min[8], s_max[8];
   const int bi = row_lo + blockIdx.y * CT, bj = blockIdx.x * CT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  const bool vec = (d & 3) == 0;
   for (int k0 = 0; k0 < d; k0 += CK) {
-    // 64 rows x 16 k per operand, 256 threads -> 4 elements each
+    // 128 rows x 16 k per operand: thread -> (row r, 4 consecutive k), two passes of 64 rows
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = threadIdx.x + 256 * q;
-      const int r = e >> 4, k = e & 15;
-      const int gi = bi + r, gj = bj + r, gk = k0 + k;
-      sa[k][r] = (gi < row_hi && gk < d) ? xn[static_cast<size_t>(gi) * d + gk] : 0.f;
-      sb[k][r] = (gj < n && gk < d) ? xn[static_cast<size_t>(gj) * d + gk] : 0.f;
+    for (int q = 0; q < 2; ++q) {
+      const int r = (threadIdx.x >> 2) + 64 * q, k4 = (threadIdx.x & 3) * 4;
+      const int gi = bi + r, gj = bj + r, gk = k0 + k4;
+      float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec && gk + 3 < d) {
+        if (gi < row_hi) *reinterpret_cast<float4*>(va) = *reinterpret_cast<const float4*>(xn + static_cast<size_t>(gi) * d + gk);
+        if (gj < n) *reinterpret_cast<float4*>(vb) = *reinterpret_cast<const float4*>(xn + static_cast<size_t>(gj) * d + gk);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (gi < row_hi && gk + t < d) va[t] = xn[static_cast<size_t>(gi) * d + gk + t];
+          if (gj < n && gk + t < d) vb[t] = xn[static_cast<size_t>(gj) * d + gk + t];
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        sa[k4 + t][r] = va[t];
+        sb[k4 + t][r] = vb[t];
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < CK; ++k) {
-      float av[4], bv[4];
+      float av[8], bv[8];
+      // rows ty*4 + {0..3} and 64 + ty*4 + {0..3}; columns tx*4 + {0..3} and 64 + tx*4 + {0..3}: conflict-free float4 reads
+      *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(&sa[k][ty * 4]);
+      *reinterpret_cast<float4*>(av + 4) = *reinterpret_cast<const float4*>(&sa[k][64 + ty * 4]);
+      *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(&sb[k][tx * 4]);
+      *reinterpret_cast<float4*>(bv + 4) = *reinterpret_cast<const float4*>(&sb[k][64 + tx * 4]);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = sa[k][ty * 4 + a];
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = sb[k][tx * 4 + b];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
   float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int i = bi + ty * 4 + a;
+  for (int a = 0; a < 8; ++a) {
+    const int i = bi + (a >> 2) * 64 + ty * 4 + (a & 3);
     if (i >= row_hi) continue;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int j = bj + tx * 4 + b;
-      if (j >= n) continue;
-      const float v = (i == j) ? 1.f : acc[a][b];
-      cosm[static_cast<size_t>(i - row_lo) * n + j] = v;
-      mn = fminf(mn, v);
-      mx = fmaxf(mx, v);
+    for (int h = 0; h < 2; ++h) {
+      const int j0 = bj + h * 64 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        v[b] = (i == j0 + b) ? 1.f : acc[a][h * 4 + b];
+        if (j0 + b < n) {
+          mn = fminf(mn, v[b]);
+          mx = fmaxf(mx, v[b]);
+        }
+      }
+      float* o = cosm + static_cast<size_t>(i - row_lo) * n + j0;
+      if (j0 + 3 < n && (n & 3) == 0) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (j0 + b < n) o[b] = v[b];
+      }
     }
   }
   mn = warp_min(mn);

@@ -37,6 +37,11 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
   } while (0)
 
 constexpr int kNumSMs = 148;
+constexpr int kMaxDevices = 16;  // per-device one-time setup flags (function attributes, occupancy queries)
+inline int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

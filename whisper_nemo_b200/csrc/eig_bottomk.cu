@@ -34,6 +34,8 @@ struct EigWs {
   int32_t* rowptr;
   uint32_t* colw;
   long long capacity;
+  void* splitk;          // partial accumulators of the split-K products (dense path)
+  size_t splitk_bytes;
 };
 
 static size_t carve_eig(uint8_t* base, int n, int b, bool sparse, int p, EigWs* out) {
@@ -60,6 +62,8 @@ static size_t carve_eig(uint8_t* base, int n, int b, bool sparse, int p, EigWs* 
     w.colw = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(w.capacity) * 4));
   } else {
     for (int i = 0; i < 2; ++i) w.vt[i] = take(static_cast<size_t>(operand_rows(b)) * ldvt * 2);
+    w.splitk_bytes = b200d_gemm_cheb_splitk_bytes(n, operand_rows(b), n);
+    w.splitk = take(w.splitk_bytes);
   }
   if (out) *out = w;
   return pos;
@@ -135,12 +139,14 @@ static int eig_impl(const void* a_bf16, int32_t lda, const float* deg, int32_t n
     e.ldx = b;
     e.ldvt = ldvt;
     e.flags = flags;
+    e.splitk_ws = w.splitk;  // always the split-K form: an output row's bits then do not depend on how many rows the launch has
+    e.splitk_ws_bytes = w.splitk_bytes;
     if (grp == nullptr) {
       e.deg = deg;
       e.x32 = xx;
       e.xprev32 = xprev;
       e.vt = vout;
-      ProfScope ps(gemm_uses_pair_kernel(n, nw, B200D_EPI_CHEB, flags) ? "gemm[cheb|2cta]" : "gemm[cheb]", 2.0 * n * nw * static_cast<double>(n), st);
+      ProfScope ps("gemm[cheb|splitk]", 2.0 * n * nw * static_cast<double>(n), st, 2);
       return b200d_gemm_f16(a_bf16, lda, vin, ldvt, n, nw, n, out, b, &e, st);
     }
     const int m_rows = row_hi - row_lo;
@@ -154,8 +160,7 @@ static int eig_impl(const void* a_bf16, int32_t lda, const float* deg, int32_t n
       for (int r = 0; r < grp->world; ++r)
         e.peer_delta[r] = reinterpret_cast<const char*>(grp->base[r]) - reinterpret_cast<const char*>(grp->base[grp->rank]);
       if (everywhere) e.flags |= B200D_GEMM_PEER_OUT32;
-      ProfScope ps(gemm_uses_pair_kernel(m_rows, nw, B200D_EPI_CHEB, flags) ? "gemm[cheb|2cta|rows]" : "gemm[cheb|rows]",
-                   2.0 * m_rows * nw * static_cast<double>(n), st);
+      ProfScope ps("gemm[cheb|splitk|rows]", 2.0 * m_rows * nw * static_cast<double>(n), st, 2);
       RC(b200d_gemm_f16(a_bf16, lda, vin, ldvt, m_rows, nw, n, out + off, b, &e, st));
     }
     ProfScope ps("peer_barrier", 0, st);

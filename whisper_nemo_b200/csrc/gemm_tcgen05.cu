@@ -114,8 +114,12 @@ struct GemmParams {
   int M, N, K;
   void* out;
   int ldo;
+  int kseg;  // EPI_PARTIAL: K blocks per segment (a tile of the launch is one (row tile, K segment)); else 0
   b200d_gemm_epilogue epi;
 };
+
+// Internal epilogue of the split-K Chebyshev product: raw fp32 accumulators of one K segment, out32[seg][M][N].
+constexpr int EPI_PARTIAL = 100;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
@@ -196,7 +200,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
   }
   if constexpr (!STORE) {
     return;
-  } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32) {
+  } else if constexpr (MODE == B200D_EPI_BIAS_F32 || MODE == B200D_EPI_SIGMOID_F32 || MODE == EPI_PARTIAL) {
     float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + n0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -333,17 +337,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // that a 10 000-row graph gives 158 tiles instead of 79 on the 148 SMs; the second read of the A rows comes from L2
   constexpr bool SPLIT = BLOCK_N == 96;
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int num_n = SPLIT ? 2 : p.N / BLOCK_N;
-  const int total = num_m * num_n;
   const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  // EPI_PARTIAL: one column tile (N == BLOCK_N); the second tile coordinate is the K segment
+  const int kseg = (MODE == EPI_PARTIAL) ? p.kseg : kblocks;
+  const int num_n = (MODE == EPI_PARTIAL) ? (kblocks + kseg - 1) / kseg : SPLIT ? 2 : p.N / BLOCK_N;
+  const int total = num_m * num_n;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int m_blk = tile / num_n, n_blk = (MODE == EPI_PARTIAL) ? 0 : tile % num_n;
+        const int kb0 = (MODE == EPI_PARTIAL) ? (tile % num_n) * kseg : 0;
+        const int kb1 = (MODE == EPI_PARTIAL) ? (kb0 + kseg < kblocks ? kb0 + kseg : kblocks) : kblocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], A_BYTES + Cfg::B_BYTES);
           tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], kb * BLOCK_K, m_blk * BLOCK_M);
@@ -373,14 +381,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb0 = (MODE == EPI_PARTIAL) ? (tile % num_n) * kseg : 0;
+        const int kb1 = (MODE == EPI_PARTIAL) ? (kb0 + kseg < kblocks ? kb0 + kseg : kblocks) : kblocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t a_desc = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
           const uint64_t b_desc = make_sw128_desc(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -399,7 +409,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const int row = m_blk * BLOCK_M + wq * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      if constexpr (MODE == B200D_EPI_CHEB && SPLIT) {
+      if constexpr (MODE == EPI_PARTIAL) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float acc_f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc_f[j] = __uint_as_float(r[j]);
+            // segment n_blk of the partial buffer: rows [n_blk * M, (n_blk + 1) * M)
+            epilogue_chunk<MODE>(p, n_blk * p.M + row, c * 32, acc_f);
+          }
+        }
+      } else if constexpr (MODE == B200D_EPI_CHEB && SPLIT) {
         cheb_epilogue_cols<32, 64>(p, row, t_row, 0, n_blk * 32);
       } else if constexpr (MODE == B200D_EPI_CHEB) {
         constexpr int B = (BLOCK_N == 192) ? 64 : 32;  // one block of vectors per launch (N == BLOCK_N)
@@ -766,16 +790,86 @@ static int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t rows,
   return B200D_OK;
 }
 
+
+// ------------------------------------------------------------------------------------ split-K Chebyshev product, second half
+// The products of the spectral solver are skinny (M = K = 10 000 .. 57 600 graph rows, N = 128 / 192): one 128-row tile per CTA
+// leaves the chip idle or quantised (79 tiles on 148 SMs: 2 rounds for 10 of them) and re-reads the whole W operand per tile.
+// With a workspace (epi.splitk_ws) the launch is cut into (row tile, K segment) units of kSplitKBlocks K blocks -- a fixed
+// length, so that the summation order of an output row depends on nothing but K: the same bits on any number of GPUs / rows --
+// each unit's raw accumulators go to partial[seg][M][N] (EPI_PARTIAL), and this kernel sums the segments in ascending order and
+// applies the Chebyshev epilogue: y = ca (deg x - (hi + mid + lo)) + cb x + cc xprev, the fp32 rows and the 3-way bf16 split
+// of y^T for the next product, locally or into every peer (b200d_gemm_epilogue.n_peers).
+constexpr int kSplitKBlocks = 24;
+
+template <int B>
+__global__ void __launch_bounds__(256) cheb_fixup_kernel(const float* __restrict__ partial, int nseg, int M, const b200d_gemm_epilogue e,
+                                                         float* __restrict__ out, int ldo) {
+  constexpr int NW = (B == 64) ? 192 : 128;
+  constexpr int ROWS = 32;
+  __shared__ float ys[ROWS][B + 1];
+  const int row0 = blockIdx.x * ROWS;
+  const int j = threadIdx.x % B;
+  constexpr int RSTEP = 256 / B;
+  const size_t seg_stride = static_cast<size_t>(M) * NW;
+  const bool out_everywhere = e.n_peers > 0 && (e.flags & B200D_GEMM_PEER_OUT32) != 0;
+  for (int r = threadIdx.x / B; r < ROWS; r += RSTEP) {
+    const int row = row0 + r;
+    float y = 0.f;
+    if (row < M) {
+      const float* p0 = partial + static_cast<size_t>(row) * NW + j;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int s = 0; s < nseg; ++s) {
+        a0 += p0[s * seg_stride];
+        a1 += p0[s * seg_stride + B];
+        a2 += p0[s * seg_stride + 2 * B];
+      }
+      const float av = (a0 + a1) + a2;
+      const float xv = e.x32[static_cast<size_t>(row) * e.ldx + j];
+      y = e.ca * (__ldg(e.deg + row) * xv - av) + e.cb * xv;
+      if (e.xprev32) y += e.cc * e.xprev32[static_cast<size_t>(row) * e.ldx + j];
+      float* o = out + static_cast<size_t>(row) * ldo + j;
+      if (e.n_peers <= 0) {
+        *o = y;
+      } else {
+        for (int q = 0; q < e.n_peers; ++q)
+          if (out_everywhere || e.peer_delta[q] == 0) *reinterpret_cast<float*>(reinterpret_cast<char*>(o) + e.peer_delta[q]) = y;
+      }
+    }
+    ys[r][j] = y;
+  }
+  if (e.vt == nullptr) return;
+  __syncthreads();
+  // transposed bf16 split: lane = row (32 consecutive rows = 64 contiguous bytes per part and vector), warps over the vectors
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = row0 + lane;
+  if (row >= M) return;
+  __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(e.vt);
+  const int n_peers = e.n_peers > 0 ? e.n_peers : 1;
+  for (int q = 0; q < n_peers; ++q) {
+    __nv_bfloat16* vr = e.n_peers > 0 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(vh) + e.peer_delta[q]) : vh;
+    for (int c = warp; c < B; c += 8) {
+      __nv_bfloat16 h, m, l;
+      split3_bf16(ys[lane][c], h, m, l);
+      vr[static_cast<size_t>(c) * e.ldvt + row] = h;
+      vr[static_cast<size_t>(c + B) * e.ldvt + row] = m;
+      vr[static_cast<size_t>(c + 2 * B) * e.ldvt + row] = l;
+    }
+  }
+}
+
 template <int BLOCK_N, int MODE, bool BF16>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // the attribute is per device: a process may drive more than one GPU
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
     B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
   }
-  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (BLOCK_N == 96 ? 2 : p.N / BLOCK_N);
+  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) *
+                    (MODE == EPI_PARTIAL ? (kblocks + p.kseg - 1) / p.kseg : BLOCK_N == 96 ? 2 : p.N / BLOCK_N);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   B200D_CHECK_LAUNCH();
@@ -785,10 +879,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 template <int MODE, bool BF16 = false>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   auto kern = gemm_tcgen05_2cta_kernel<MODE, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
     B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_set = true;
+    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
   }
   constexpr int BN = (MODE == B200D_EPI_CHEB) ? 192 : 256;
   const int tiles = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (p.N / BN);
@@ -858,6 +953,13 @@ bool gemm_uses_pair_kernel(int M, int N, int mode, int flags) {
 
 using namespace b200d;
 
+extern "C" size_t b200d_gemm_cheb_splitk_bytes(int32_t M, int32_t N, int32_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int nseg = (kblocks + kSplitKBlocks - 1) / kSplitKBlocks;
+  return static_cast<size_t>(nseg) * M * N * sizeof(float);
+}
+
 extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t ldw, int32_t M, int32_t N, int32_t K, void* out,
                               int32_t ldo, const b200d_gemm_epilogue* epi, void* stream) {
   B200D_CHECK_ARG(A && W && out && epi);
@@ -893,7 +995,30 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
   rc = make_map(&tb, W, bf16, N, K, ldw, cheb_split ? 32 : use_2cta ? (mode == B200D_EPI_CHEB ? 96 : 128) : block_n);
   if (rc) return rc;
   GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.epi = *epi;
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldo = ldo; p.kseg = 0; p.epi = *epi;
+  if (mode == B200D_EPI_CHEB && epi->splitk_ws != nullptr) {
+    // split-K: (row tile, K segment) units -> partial[seg][M][N], then the fix-up kernel (see cheb_fixup_kernel)
+    const size_t need = b200d_gemm_cheb_splitk_bytes(M, N, K);
+    if (need > epi->splitk_ws_bytes)
+      return set_error(B200D_EWORKSPACE, "%s: epi.splitk_ws too small (b200d_gemm_cheb_splitk_bytes)%s", "b200d_gemm_f16");
+    B200D_CHECK_ARG((reinterpret_cast<uintptr_t>(epi->splitk_ws) & 15) == 0);
+    rc = make_map(&tb, W, true, N, K, ldw, N);
+    if (rc) return rc;
+    p.out = epi->splitk_ws;
+    p.ldo = N;
+    p.kseg = kSplitKBlocks;
+    rc = (N == 192) ? launch<192, EPI_PARTIAL, true>(ta, tb, p, as_stream(stream)) : launch<128, EPI_PARTIAL, true>(ta, tb, p, as_stream(stream));
+    if (rc) return rc;
+    const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int nseg = (kblocks + kSplitKBlocks - 1) / kSplitKBlocks;
+    const int blocks = (M + 31) / 32;
+    if (N == 192)
+      cheb_fixup_kernel<64><<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(epi->splitk_ws), nseg, M, *epi, reinterpret_cast<float*>(out), ldo);
+    else
+      cheb_fixup_kernel<32><<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(epi->splitk_ws), nseg, M, *epi, reinterpret_cast<float*>(out), ldo);
+    B200D_CHECK_LAUNCH();
+    return B200D_OK;
+  }
   if (use_2cta) return dispatch_mode_2cta(ta, tb, p, as_stream(stream));
   if (mode == B200D_EPI_CHEB) {
     if (cheb_split) return launch<96, B200D_EPI_CHEB, true>(ta, tb, p, as_stream(stream));
