@@ -223,6 +223,16 @@ def _time_steps(diar, wav_dev, steps, barrier, torch):
 
 
 def run_b200(args):
+    # stdout carries ONE JSON line: anything a library prints there (NCCL's version banner under NCCL_DEBUG=VERSION, ...) goes to
+    # stderr instead; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     import torch
 
     rank = int(os.environ.get("RANK", 0))
@@ -310,7 +320,7 @@ def run_b200(args):
     # ---- untimed extras on rank 0: per-stage times, per-kernel roofline
     if args.profiling:
         if rank == 0:
-            print(json.dumps({"profiling_run": True, "ms_per_step": dev_ms / args.steps, "note": "not a bench value"}))
+            emit({"profiling_run": True, "ms_per_step": dev_ms / args.steps, "note": "not a bench value"})
     elif rank == 0 or shard:
         # (under --shard every rank has to take part in the collectives of these two extra passes)
         diar.run_device(wav_dev=wav_dev, timers=True)
@@ -376,7 +386,7 @@ def run_b200(args):
             line["strong_4h"] = strong
         if strong_full is not None:
             line["strong_4h_fullmatrix"] = strong_full
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier(group=host_group)
         dist.destroy_process_group()
