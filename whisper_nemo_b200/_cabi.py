@@ -171,14 +171,18 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    try:  # a library older than its sources would be called with the wrong signatures: rebuild when the stamp differs
-        from . import build as _build
+    # a library older than its sources would be called with the wrong signatures: rebuild when the stamp differs, and refuse
+    # to load a stale one when that rebuild fails
+    from . import build as _build
 
-        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+    if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+        try:
             _build.build_library()
-    except Exception as exc:  # noqa: BLE001 -- fall through to the existence check below
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"building {LIB_PATH} failed: {exc}") from exc
+        except Exception as exc:  # noqa: BLE001
+            raise RuntimeError(f"building {LIB_PATH} failed and the existing library (if any) does not match the sources: {exc}") from exc
+    elif os.path.exists(LIB_PATH) and not _build.library_is_current():
+        raise RuntimeError(f"{LIB_PATH} was built from other sources than the ones next to it and there is no nvcc to rebuild it "
+                           "(python -m whisper_nemo_b200.build on a machine with the CUDA toolkit)")
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} not found: build it with `python -m whisper_nemo_b200.build` "

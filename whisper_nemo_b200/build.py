@@ -26,10 +26,15 @@ def _digest():
     h = hashlib.sha256()
     for p in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(_HERE, "..", "include", "b200d.h")]:
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())  # (not the absolute path: the stamp must stay valid when the tree is copied)
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def library_is_current() -> bool:
+    """The in-tree library exists and was built from the sources next to it (digest stamp)."""
+    return os.path.exists(LIB_PATH) and os.path.exists(_STAMP) and open(_STAMP).read().strip() == _digest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

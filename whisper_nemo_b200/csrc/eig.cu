@@ -269,7 +269,7 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
                                      void* stream) {
   B200D_CHECK_ARG(a && evals && ws);
   B200D_CHECK_ARG(batch > 0 && batch <= kNumSMs && n >= 2 && n <= kMaxEigN && n_low >= 1 && n_low <= n);
-  static int blocks_per_sm = 0;
+  static int blocks_per_sm = 0;  // occupancy of tridiag_kernel: a property of the kernel and sm_100, the same on every device
   if (ws_bytes < b200d_eigvals_workspace_bytes(batch, n))
     return b200d::set_error(B200D_EWORKSPACE, "%s: workspace too small%s", "b200d_eigvals_batched");
   cudaStream_t s = as_stream(stream);
@@ -280,11 +280,13 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
   B200D_CHECK_CUDA(cudaMemsetAsync(bar, 0, static_cast<size_t>(batch) * sizeof(unsigned), s));
   int n_arg = n;
   const size_t smem = static_cast<size_t>(4) * n * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set_dev[kMaxDevices] = {};  // kernel attributes are per device
+  const int attr_dev = current_device();
+  const bool attr_known = attr_dev >= 0 && attr_dev < kMaxDevices;
+  if (!attr_known || !attr_set_dev[attr_dev]) {
     B200D_CHECK_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kMaxEigN * sizeof(float)));
     B200D_CHECK_CUDA(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxEigN * sizeof(double)));
-    attr_set = true;
+    if (attr_known) attr_set_dev[attr_dev] = true;
   }
   if (blocks_per_sm == 0) {
     int occ = 1;

@@ -333,11 +333,13 @@ extern "C" int b200d_kmeans(const float* x, int32_t n, int32_t dim, int32_t n_cl
   p.centers = w; w += kd;
   p.counts = reinterpret_cast<int*>(w);
   const size_t smem = (2 * kd + static_cast<size_t>(kKmMaxTrials) * dim + static_cast<size_t>(kKmSub) * kKmMaxTrials) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set_dev[kMaxDevices] = {};  // kernel attributes are per device
+  const int attr_dev = current_device();
+  const bool attr_known = attr_dev >= 0 && attr_dev < kMaxDevices;
+  if (!attr_known || !attr_set_dev[attr_dev]) {
     B200D_CHECK_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (2 * kKmMaxK * kKmMaxDim + kKmMaxTrials * kKmMaxDim + kKmSub * kKmMaxTrials) * sizeof(float)));
-    attr_set = true;
+    if (attr_known) attr_set_dev[attr_dev] = true;
   }
   void* args[] = {const_cast<KmeansParams*>(&p)};
   B200D_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kmeans_kernel), dim3(G), dim3(kKmThreads), args, smem, as_stream(stream)));

@@ -369,14 +369,16 @@ extern "C" int b200d_gram(const float* x, const float* y, int32_t n, int32_t b, 
 
 extern "C" int b200d_small_eig(const float* g, int32_t b, float* evals, float* evecs, int32_t mode, void* stream) {
   B200D_CHECK_ARG(g && evecs && b >= 2 && b <= kMaxJacobi && b % 2 == 0 && (mode == 0 || mode == 1) && (mode == 1 || evals));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set_dev[kMaxDevices] = {};  // kernel attributes are per device
+  const int attr_dev = current_device();
+  const bool attr_known = attr_dev >= 0 && attr_dev < kMaxDevices;
+  if (!attr_known || !attr_set_dev[attr_dev]) {
     const int big = 2 * 96 * 97 * sizeof(double);
     B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     B200D_CHECK_CUDA(cudaFuncSetAttribute(small_eig_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           kMaxJacobi * (kMaxJacobi + 1) * (sizeof(double) + sizeof(float))));
-    attr_set = true;
+    if (attr_known) attr_set_dev[attr_dev] = true;
   }
   cudaStream_t st = as_stream(stream);
   const size_t smem64 = static_cast<size_t>(2) * b * (b + 1) * sizeof(double);

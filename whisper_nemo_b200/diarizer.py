@@ -255,14 +255,16 @@ class ClusteringDiarizer:
         self._shard_loads = []
 
     # ------------------------------------------------------------------ device work
-    def _extract_embeddings(self, plan: dict, wav_dev: torch.Tensor, logmel: torch.Tensor = None) -> torch.Tensor:
+    def _extract_embeddings(self, plan: dict, wav_dev: torch.Tensor, logmel: torch.Tensor = None, gather: bool = True):
         """All windows of one scale -> float32 [n, 192] on device (manifest order).  `logmel`: the stream frames of
         `_mel_streams` (interior frames of every window are gathered from it instead of recomputed).
 
         shard_windows: the unit dealt to the ranks is the LAUNCH GROUP of the single-GPU run (the windows of one tiled-up
         length, in its order, cut at multiples of b200d_titanet_group_windows), so every window is computed by exactly the
         launches -- same neighbours, same position -- that compute it on one GPU and the all-gathered embeddings are bit for bit
-        the single-GPU ones (a window's position in its launch decides the summation order of the SqueezeExcite column sums)."""
+        the single-GPU ones (a window's position in its launch decides the summation order of the SqueezeExcite column sums).
+        gather=False returns this rank's block and a closure that all-gathers it: the caller embeds every scale first and
+        gathers afterwards, so that only the TOTAL load of a rank has to balance, not its load within each scale."""
         n = plan["n"]
         out = torch.empty(n, 192, dtype=torch.float32, device=self.device)
         if n == 0:
@@ -311,9 +313,13 @@ class ClusteringDiarizer:
             local[o : o + cnt] = emb
         if world == 1:
             return out.index_select(0, where)
-        gathered = torch.empty(world * pad, 192, dtype=torch.float32, device=self.device)
-        torch.distributed.all_gather_into_tensor(gathered, local)
-        return gathered.index_select(0, where)
+
+        def finish():
+            gathered = torch.empty(world * pad, 192, dtype=torch.float32, device=self.device)
+            torch.distributed.all_gather_into_tensor(gathered, local)
+            return gathered.index_select(0, where)
+
+        return finish() if gather else finish
 
     def _deal_launch_groups(self, frames: List[int], world: int) -> List[int]:
         """Owner rank of every launch group of one scale: largest first onto the least-loaded rank, the loads carried over the
@@ -346,7 +352,10 @@ class ClusteringDiarizer:
         _cabi.single_cta_gemms), which costs more than the overlap wins."""
         n_streams = min(len(self._scales), max(1, int(os.environ.get("B200D_EMBED_STREAMS", "1"))))
         logmel = self._mel_streams(wav_dev)
-        if n_streams <= 1 or self.shard_windows:
+        if self.shard_windows:
+            pending = {k: self._extract_embeddings(plan, wav_dev, logmel, gather=False) for k, plan in self._scales.items()}
+            return {k: (v() if callable(v) else v) for k, v in pending.items()}
+        if n_streams <= 1:
             return {k: self._extract_embeddings(plan, wav_dev, logmel) for k, plan in self._scales.items()}
         from concurrent.futures import ThreadPoolExecutor
 
