@@ -244,6 +244,13 @@ def test_cheb_gemm_step_split_k(dev, n, b):
         torch.cuda.synchronize()
         assert torch.equal(part[lo:hi], out[lo:hi])
         assert torch.equal(vt_part[:, lo:hi], vt_out[:, lo:hi])
+        # a short launch (takes the 128-row units where the full one takes the 256-row units): still the same bits
+        hi2 = min(n, lo + 300)
+        part2 = torch.full((n, b), float("nan"), dtype=torch.float32, device=dev)
+        cl._gemm_cheb(a16[lo:hi2], lda, vt_in, lda, hi2 - lo, nw, part2[lo:hi2], deg[lo:hi2], x[lo:hi2], None if prev is None else prev[lo:hi2], ca, cb,
+                      cc, None, splitk=ws, k=n)
+        torch.cuda.synchronize()
+        assert torch.equal(part2[lo:hi2], out[lo:hi2])
     print(f"split-K cheb step n={n} b={b}: max err {err:.3e}")
 
 

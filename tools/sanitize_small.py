@@ -6,7 +6,8 @@ plain run, so every shape is tiny):
 
 Covers: both tcgen05 GEMM kernels (1-CTA, CTA-pair with the SE column-sum epilogue), the split Chebyshev GEMM, featurizer
 (stream + window kernels), depthwise / statistics / pooling kernels through b200d_titanet_forward, k-means, top-p
-binarisation, the batched eigenvalue kernels and b200d_eig_bottomk."""
+binarisation, the batched eigenvalue kernels, b200d_eig_bottomk (split-K products + fix-up kernel) and the row-sharded path on
+two LocalComm ranks (row kernels, peer stores of the fix-up kernel, device-side barriers)."""
 import os
 import sys
 
@@ -48,6 +49,33 @@ def main():
     lab = cl.kmeans_torch(vec, k)
     torch.cuda.synchronize()
     print("clustering", k, p, tuple(vec.shape), tuple(vec2.shape), int(lab.max()))
+    # row-sharded forms on two ranks (host threads, one stream and one peer buffer each)
+    import threading
+
+    from whisper_nemo_b200 import rowshard
+
+    n = mat.shape[0]
+    comms = rowshard.LocalComm.make(2)
+    shards = rowshard.row_shards(n, 2)
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    out = [None, None]
+
+    def work(r):
+        torch.cuda.set_device(0)
+        with torch.cuda.stream(streams[r]), torch.no_grad():
+            lo, hi = shards[r]
+            rows = rowshard.fused_affinity_rows(comms[r], [1.0], [x.to(dev)], [np.arange(n, dtype=np.int32)], lo, hi)
+            a_rows, deg = rowshard.graph_rows(comms[r], rows, p, lo, hi, shards)
+            out[r] = rowshard.bottom_eigvecs_sharded(comms[r], a_rows, deg, k, lo, hi)
+            streams[r].synchronize()
+
+    torch.cuda.synchronize()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    print("row-sharded", tuple(out[0].shape), bool(torch.equal(out[0], out[1])))
 
 
 if __name__ == "__main__":
