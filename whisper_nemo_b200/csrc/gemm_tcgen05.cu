@@ -458,165 +458,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------------------------ split-K units of 256 rows
-// The (row tile, K segment) unit of the split-K Chebyshev product with TWO 128-row MMA tiles sharing one W stage: per 64-wide K
-// block the CTA pulls 32 KB of A + 24 KB of W for 256 x 192 outputs instead of 16 + 24 KB for 128 x 192 -- the product is bound
-// by the L2 -> SM path (the W operand is re-read by every row tile), and this takes 503 MB per 10 000 x 10 000 x 192 product down
-// to 352 MB.  Same MMA shape and K order as gemm_tcgen05_kernel<.., EPI_PARTIAL>: bit-identical partial accumulators.
-// warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue (lane quarter x row half).  One accumulator
-// pair (2 x BLOCK_N TMEM columns), so a unit's MMAs wait for the previous unit's epilogue; the smem ring keeps prefetching.
-template <int BLOCK_N>
-struct Split256Cfg {
-  static constexpr int STAGES = (BLOCK_N == 192) ? 3 : 4;
-  static constexpr int A2_BYTES = 2 * A_BYTES;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int TMEM_COLS = (BLOCK_N == 192) ? 512 : 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * (A2_BYTES + B_BYTES) + 256;
-};
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(384, 1)
-gemm_splitk256_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = Split256Cfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * Cfg::A2_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
-  uint64_t* tempty = tfull + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int kseg = p.kseg;
-  const int nseg = (kblocks + kseg - 1) / kseg;
-  const int total = num_m * nseg;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
-        const int m_blk = unit / nseg, seg = unit % nseg;
-        const int kb0 = seg * kseg, kb1 = kb0 + kseg < kblocks ? kb0 + kseg : kblocks;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::A2_BYTES + Cfg::B_BYTES);
-          tma_load_2d(sA + stage * Cfg::A2_BYTES, &tmA, &full[stage], kb * BLOCK_K, m_blk * 2 * BLOCK_M);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BLOCK_K, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
-                                 (static_cast<uint32_t>(BLOCK_M >> 4) << 24);  // D fp32, A / B bf16 K-major, N, M = 128
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
-        const int seg = unit % nseg;
-        const int kb0 = seg * kseg, kb1 = kb0 + kseg < kblocks ? kb0 + kseg : kblocks;
-        mbar_wait(tempty, acc_phase ^ 1);
-        tc_fence_after();
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t a_lo = make_sw128_desc(smem_u32(sA + stage * Cfg::A2_BYTES));
-          const uint64_t a_hi = make_sw128_desc(smem_u32(sA + stage * Cfg::A2_BYTES + A_BYTES));
-          const uint64_t b_desc = make_sw128_desc(smem_u32(sB + stage * Cfg::B_BYTES));
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint32_t accumulate = (kb != kb0 || k != 0) ? 1u : 0u;
-            umma_f16(tmem_base, a_lo + 2 * k, b_desc + 2 * k, idesc, accumulate);
-            umma_f16(tmem_base + BLOCK_N, a_hi + 2 * k, b_desc + 2 * k, idesc, accumulate);
-          }
-          umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(tfull);
-        acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    const int wq = warp & 3;          // TMEM lane quarter
-    const int half = (warp - 4) >> 2; // rows [0, 128) or [128, 256) of the unit
-    uint32_t acc_phase = 0;
-    float* partial = reinterpret_cast<float*>(p.out);
-    for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
-      const int m_blk = unit / nseg, seg = unit % nseg;
-      mbar_wait(tfull, acc_phase);
-      tc_fence_after();
-      const int row = m_blk * 2 * BLOCK_M + half * BLOCK_M + wq * 32 + lane;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + half * BLOCK_N;
-      float* o = partial + (static_cast<size_t>(seg) * p.M + row) * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
-        tmem_ld_wait();
-        if (row < p.M) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + c * 32 + j) =
-                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-      acc_phase ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-template <int BLOCK_N>
-static int launch_splitk256(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = Split256Cfg<BLOCK_N>;
-  auto kern = gemm_splitk256_kernel<BLOCK_N>;
-  static bool attr_set[kMaxDevices] = {};
-  const int dev = current_device();
-  if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
-    B200D_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
-  }
-  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int units = ((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((kblocks + p.kseg - 1) / p.kseg);
-  const int grid = units < kNumSMs ? units : kNumSMs;
-  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
-  B200D_CHECK_LAUNCH();
-  return B200D_OK;
-}
-
 // ------------------------------------------------------------------------------------ 2-CTA kernel
 // CTA-pair variant (cta_group::2) for the large pointwise convs.  The 1-CTA kernel above moves 48 KB from L2 per
 // 128x256x64 MMA block and saturates the L2 -> SM path (~6.3 KB/clk chip-wide) at about half of the tensor peak.
@@ -1166,17 +1007,10 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
     p.out = epi->splitk_ws;
     p.ldo = N;
     p.kseg = kSplitKBlocks;
-    // 256-row units (two MMA tiles per W stage) once there are enough rows to fill the chip with them; same bits either way
-    static const bool env_128 = getenv("B200D_SPLITK_128") != nullptr;
-    const int kb_all = (K + BLOCK_K - 1) / BLOCK_K;
-    const long long units256 = static_cast<long long>((M + 255) / 256) * ((kb_all + kSplitKBlocks - 1) / kSplitKBlocks);
-    if (!env_128 && units256 >= kNumSMs) {
-      rc = make_map(&ta, A, true, M, K, lda, 2 * BLOCK_M);
-      if (rc) return rc;
-      rc = (N == 192) ? launch_splitk256<192>(ta, tb, p, as_stream(stream)) : launch_splitk256<128>(ta, tb, p, as_stream(stream));
-    } else {
-      rc = (N == 192) ? launch<192, EPI_PARTIAL, true>(ta, tb, p, as_stream(stream)) : launch<128, EPI_PARTIAL, true>(ta, tb, p, as_stream(stream));
-    }
+    // (measured and dropped in round 2: 256-row units -- two MMA tiles per W stage, 352 instead of 503 MB through L2 per
+    // 10 000^2 x 192 product -- gave the same bits and no speed-up, 56.0 against 52.8 ms per step: the product is bound by the
+    // MMA's shared-memory operand reads at N = 192 per 128 rows, which only the CTA-pair form halves)
+    rc = (N == 192) ? launch<192, EPI_PARTIAL, true>(ta, tb, p, as_stream(stream)) : launch<128, EPI_PARTIAL, true>(ta, tb, p, as_stream(stream));
     if (rc) return rc;
     const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
     const int nseg = (kblocks + kSplitKBlocks - 1) / kSplitKBlocks;
