@@ -554,6 +554,34 @@ def test_in_memory_waveform_api_matches_file_path(dev, weights, tmp_path):
         assert mem_ts == file_ts
 
 
+def test_diarize_async_next_to_other_gpu_work(dev, weights, tmp_path):
+    """SURVEY.md 8f row 4 (the reference's diarize_parallel.py:117-120 / :191-196 subprocess): `diarize_async()` runs the stage on
+    its own thread and stream while the caller keeps the GPU busy (a matmul loop standing in for the Whisper transcription);
+    `.result()` joins it.  Same RTTM as the synchronous call on a decisive recording."""
+    from whisper_nemo_b200 import ClusteringDiarizer
+
+    cfg_a, _, _ = make_session_cfg(tmp_path / "sync", "telephonic", 120.0, 2, seed=11)
+    sync = ClusteringDiarizer(cfg=cfg_a, speaker_model=weights).to("cuda")
+    sync.diarize()
+    cfg_b, _, _ = make_session_cfg(tmp_path / "async", "telephonic", 120.0, 2, seed=11)
+    diar = ClusteringDiarizer(cfg=cfg_b, speaker_model=weights).to("cuda")
+    fut = diar.diarize_async()
+    a = torch.randn(4096, 4096, device=dev, dtype=torch.float16)
+    n_iter = 0
+    while not fut.done() and n_iter < 20000:  # "transcription" on the caller's stream
+        a = (a @ a).clamp_(-1, 1)
+        n_iter += 1
+    assert fut.result(timeout=120) is None
+    torch.cuda.synchronize()
+    assert n_iter > 0
+    cos = torch.nn.functional.cosine_similarity(sync.embs_and_timestamps["mono_file"]["embeddings"], diar.embs_and_timestamps["mono_file"]["embeddings"], dim=1)
+    assert (1 - cos).max().item() <= 1e-5
+    assert diar.results["mono_file"]["debug"]["n_clusters"] == sync.results["mono_file"]["debug"]["n_clusters"]
+    assert best_permutation_agreement(diar.results["mono_file"]["labels"], sync.results["mono_file"]["labels"]) == 1.0
+    assert rttm_der_between(str(tmp_path / "sync" / "pred_rttms" / "mono_file.rttm"), str(tmp_path / "async" / "pred_rttms" / "mono_file.rttm")) == 0.0
+    print(f"diarize_async: {n_iter} caller-side matmuls overlapped; max(1-cos) vs synchronous call {(1 - cos).max().item():.1e}")
+
+
 def test_neural_diarizer_wrapper_and_msdd_handoff_files(dev, oracle_model, weights, tmp_path):
     """The reference's literal call -- NeuralDiarizer(cfg=create_config(dir)).to(device).diarize() (diarize.py:200-201) --
     through the B200 wrapper, and the files NeMo's MSDD stage reads afterwards against the oracle's: the per-scale

@@ -3,6 +3,7 @@ plain run, so every shape is tiny):
 
     compute-sanitizer --tool memcheck  python tools/sanitize_small.py > profiles/r02_sanitizer_memcheck.log 2>&1
     compute-sanitizer --tool racecheck python tools/sanitize_small.py > profiles/r02_sanitizer_racecheck.log 2>&1
+    compute-sanitizer --tool memcheck  python tools/sanitize_small.py --rowshard   (adds the row-sharded path on two ranks)
 
 Covers: both tcgen05 GEMM kernels (1-CTA, CTA-pair with the SE column-sum epilogue), the split Chebyshev GEMM, featurizer
 (stream + window kernels), depthwise / statistics / pooling kernels through b200d_titanet_forward, k-means, top-p
@@ -49,7 +50,10 @@ def main():
     lab = cl.kmeans_torch(vec, k)
     torch.cuda.synchronize()
     print("clustering", k, p, tuple(vec.shape), tuple(vec2.shape), int(lab.max()))
-    # row-sharded forms on two ranks (host threads, one stream and one peer buffer each)
+    if "--rowshard" not in sys.argv:
+        return
+    # row-sharded forms on two ranks (host threads, one stream and one peer buffer each).  A separate invocation: the device-side
+    # barriers need both ranks' kernels in flight at once, which a sanitizer that serialises kernels turns into a barrier time-out
     import threading
 
     from whisper_nemo_b200 import rowshard

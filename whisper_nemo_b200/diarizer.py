@@ -528,6 +528,40 @@ class ClusteringDiarizer:
         self.host_seconds = {"prepare": t1 - t0, "device_path": t2 - t1, "write": time.perf_counter() - t2}
         return None
 
+    def diarize_async(self, paths2audio_files: List[str] = None, batch_size: int = 0):
+        """`diarize()` on a worker thread and a CUDA stream of its own; returns a concurrent.futures.Future.
+
+        In-process counterpart of the reference's parallel mode: diarize_parallel.py:117-120
+        starts `python nemo_process.py` as a SUBPROCESS next to the Whisper transcription and joins it at :191-196
+        (`nemo_process.wait()`), paying a second CUDA context, a second copy of the models and the interpreter start-up for
+        a stage that takes a fraction of a second here.  The caller keeps transcribing on its own stream(s) and calls
+        `.result()` where the reference calls `.wait()`.  The other streams of the process are busy while this runs, so the
+        worker's GEMMs carry B200D_GEMM_NO_PAIR (include/b200d.h: the cluster-launched kernel never shares the device with
+        another stream's kernels); the embeddings then differ from a plain `diarize()` in the last bits (SqueezeExcite means by
+        a separate pass instead of the pair kernel's epilogue sums), within the same tolerances."""
+        import threading
+        from concurrent.futures import Future
+
+        fut: Future = Future()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if getattr(self, "_async_stream", None) is None:
+            self._async_stream = torch.cuda.Stream(device=dev_index)
+        stream = self._async_stream
+        stream.wait_stream(torch.cuda.current_stream(dev_index))
+
+        def work():
+            try:
+                torch.cuda.set_device(dev_index)
+                with torch.cuda.stream(stream), torch.no_grad(), _cabi.single_cta_gemms():
+                    res = self.diarize(paths2audio_files=paths2audio_files, batch_size=batch_size)
+                    stream.synchronize()
+                fut.set_result(res)
+            except BaseException as exc:  # noqa: BLE001 -- delivered through the future
+                fut.set_exception(exc)
+
+        threading.Thread(target=work, name="b200d-diarize", daemon=True).start()
+        return fut
+
     # ------------------------------------------------------------------ in-memory fast path (SURVEY.md section 8f, rows 2-3)
     def diarize_waveform(self, waveform, speech_regions, uniq_id: str = "mono_file", write_rttm_dir: Optional[str] = None):
         """Diarize one recording that is already in memory -- no WAV / manifest / RTTM round trip through the disk.
