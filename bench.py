@@ -311,6 +311,29 @@ def run_b200(args):
         call_s.append(time.perf_counter() - t0)
     call_ms = all_max([1e3 * sum(call_s) / max(len(call_s), 1)])[0]
     host_split = dict(getattr(diar, "host_seconds", {}))
+    # ---- N = 1: the same recording on the FULL-MATRIX path ("final solve 14 399^2 or long-form ... run and
+    # report both"): embeddings_per_chunk raised above the recording's length, i.e. one N x N affinity instead of long-form chunks
+    fullmatrix = None
+    if world == 1 and not batch_mode and not args.profiling and seconds >= 3000:
+        import copy
+
+        cfg_f = copy.deepcopy(cfg)
+        cfg_f.diarizer.clustering.parameters.embeddings_per_chunk = 10 ** 7
+        diar_f = ClusteringDiarizer(cfg=cfg_f, speaker_model=weights).to("cuda")
+        diar_f._prepare()
+        for _ in range(2):
+            diar_f.run_device(wav_dev=wav_dev, timers=False)
+        f_dev_ms, f_e2e_ms = _time_steps(diar_f, wav_dev, 3, barrier, torch)
+        diar_f.run_device(wav_dev=wav_dev, timers=True)
+        res_f = next(iter(diar_f.results.values()))
+        fullmatrix = {"what": "the same recording with embeddings_per_chunk raised above its length: one N x N affinity / graph / eigensolve instead of "
+                              "long-form chunks (3 steps)", "ms_per_step": round(f_dev_ms / 3, 3), "value": round(seconds / 3600.0 * 3 / (f_dev_ms * 1e-3), 4),
+                      "e2e_ms_per_step": round(f_e2e_ms / 3, 3), "unit": UNIT, "base_scale_windows": int(len(res_f["labels"])),
+                      "speakers_found": int(res_f["debug"]["n_clusters"]), "p_hat": int(res_f["debug"]["p_hat"]),
+                      "stage_ms": {k: round(v, 3) for k, v in diar_f.stage_ms.items()}}
+        del diar_f
+        torch.cuda.empty_cache()
+        _progress(f"full-matrix variant done: {f_dev_ms / 3:.1f} ms per step")
     # ---- N > 1: BASELINE config #5, one 4-hour recording sharded over all ranks (strong scaling), next to the weak-scaling line
     _progress("diarize() calls done")
     strong = strong_full = None
@@ -382,6 +405,8 @@ def run_b200(args):
             "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()}, "kernels_ms_per_step": kernels, "host_prepare_s": round(prep_s, 3),
             "spectral_solver": spectral,
         }
+        if fullmatrix is not None:
+            line["fullmatrix_path"] = fullmatrix
         if strong is not None:
             line["strong_4h"] = strong
         if strong_full is not None:

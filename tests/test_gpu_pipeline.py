@@ -650,6 +650,8 @@ def test_fullsize_meeting_one_hour_matches_oracle(dev, oracle_model, weights, tm
         labels, DER between the two RTTMs <= 1e-3.  Otherwise the numbers are printed: over-clustering 10 000 windows of
         8 speakers into 50 is chaotic under ANY perturbation of the embeddings, and no implementation (NeMo on another
         BLAS included) reproduces the labels of an ill-posed instance.
+      * FULL-MATRIX PATH end to end (embeddings_per_chunk raised on both sides, each on its own embeddings): the well-posed
+        form of the same recording -- same speaker count (the 8 true ones), labels identical on >= 99.9 % of the windows, asserted.
     Set B200D_SKIP_FULLSIZE_1H=1 to skip (development runs)."""
     if os.environ.get("B200D_SKIP_FULLSIZE_1H") == "1":
         pytest.skip("B200D_SKIP_FULLSIZE_1H=1")
@@ -729,6 +731,28 @@ def test_fullsize_meeting_one_hour_matches_oracle(dev, oracle_model, weights, tm
           f"true speakers oracle {purity_o:.4f} B200 {purity_g:.4f}; oracle under two perturbations of its own embeddings of the device error's size ({rel:.1e}): speakers {probe_k}, labels "
           f"differing {probe_diff} -> {'decisive' if decisive else 'NEAR-TIE: the oracle does not reproduce its own labels, end-to-end labels not asserted'} "
           f"({time.perf_counter() - t0:.0f} s)")
+    # ---- the same recording on the FULL-MATRIX path ("final solve 14 399^2 or long-form ... run and report
+    # both"): embeddings_per_chunk raised above the recording's length on both sides, each side on its OWN embeddings.  Without the
+    # over-cluster / merge heuristic the problem is well posed, so here the end-to-end outcome is asserted: same speaker count and
+    # p-hat, identical labels, and that they are the 8 true speakers.
+    t0 = time.perf_counter()
+    kw_full = dict(kw, embeddings_per_chunk=10 ** 7)
+    state = torch.get_rng_state()
+    full_o = OracleLF().forward_infer(eo_all["embeddings"], eo_all["timestamps"], eo_all["multiscale_segment_counts"], eo_all["multiscale_weights"],
+                                      **kw_full).numpy()
+    torch.set_rng_state(state)
+    full_lf = LongFormSpeakerClustering()
+    full_g = full_lf.forward_infer(eg_all["embeddings"].to(dev), eg_all["timestamps"], eg_all["multiscale_segment_counts"],
+                                   eg_all["multiscale_weights"], **kw_full).cpu().numpy()
+    kf_o, kf_g = len(set(full_o.tolist())), len(set(full_g.tolist()))
+    full_diff = len(_differing(full_g, full_o)) if kf_o == kf_g else n
+    pur_fo = best_permutation_agreement(full_o[truth >= 0], truth[truth >= 0])
+    pur_fg = best_permutation_agreement(full_g[truth >= 0], truth[truth >= 0])
+    print(f"   full-matrix path ({n} x {n} affinity, no long-form), end to end: speakers oracle {kf_o} B200 {kf_g} (p-hat {full_lf.speaker_clustering.debug['p_hat']}); "
+          f"{full_diff} of {n} labels differ; purity vs the 8 true speakers oracle {pur_fo:.4f} B200 {pur_fg:.4f} ({time.perf_counter() - t0:.0f} s)")
+    assert kf_g == kf_o == 8
+    assert full_diff <= tol  # (1e-3 of the windows: a window straddling a speaker change may fall either way under the 4e-5 embedding difference)
+    assert pur_fg >= 0.99
     dump = os.environ.get("B200D_DUMP_DIR")
     if dump:
         os.makedirs(dump, exist_ok=True)
