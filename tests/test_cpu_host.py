@@ -396,3 +396,24 @@ def test_row_shards_cover_every_row_once():
         assert all(hi > lo for lo, hi in sh)
         if n >= 16 * world * rowshard.ROW_ALIGN:
             assert all(lo % rowshard.ROW_ALIGN == 0 for lo, _ in sh)
+
+
+def test_later_subsegment_rule_matches_the_oracle_switch(monkeypatch):
+    """B200D_SUBSEGMENT_RULE=v2 (the get_subsegments of later NeMo 2.x releases) in the PRODUCT path: per region and through the
+    vectorised planner, equal to the oracle under oracle.switches.SUBSEGMENT_RULE = "v2"."""
+    from oracle import speaker_utils as osu
+    from oracle import switches
+
+    monkeypatch.setattr(switches, "SUBSEGMENT_RULE", "v2")
+    monkeypatch.setattr(su, "SUBSEGMENT_RULE", "v2")
+    rng = np.random.default_rng(11)
+    offs = np.round(rng.uniform(0, 500, 200), 5)
+    durs = np.round(np.concatenate([rng.uniform(0.005, 0.6, 60), rng.uniform(0.5, 30, 140)]), 5)
+    for w, s in SCALES:
+        want = []
+        for r, (o, d) in enumerate(zip(offs.tolist(), durs.tolist())):
+            segs = osu.get_subsegments(o, w, s, d)
+            assert segs == su.get_subsegments(o, w, s, d)
+            want += [(r, st, du) for st, du in segs if du > su.MIN_SUBSEGMENT_DURATION]
+        region, start, dur = su.subsegment_arrays(offs, durs, w, s)
+        assert region.tolist() == [x[0] for x in want] and start.tolist() == [x[1] for x in want] and dur.tolist() == [x[2] for x in want]

@@ -64,9 +64,36 @@ def parse_scale_configs(window_lengths_in_sec, shift_lengths_in_sec, multiscale_
             "multiscale_weights": list(multiscale_weights)}
 
 
+# Which release of upstream's `get_subsegments` the window grid follows.  "classic" (NeMo 1.x / early 2.x): float64 python
+# arithmetic, n = ceil((dur - w) / shift) + 1.  "v2" (later 2.x; the reference pins only nemo >= 2.dev): start times from
+# torch.arange (float32), durations rounded to 2 decimals, a region shorter than the shift kept as one window.  The two differ in
+# the last digits of window times and occasionally in the window count of a region; set B200D_SUBSEGMENT_RULE=v2 to follow a
+# NeMo that has the later one (the oracle's oracle/switches.py SUBSEGMENT_RULE is the same switch on the CPU side).
+SUBSEGMENT_RULE = os.environ.get("B200D_SUBSEGMENT_RULE", "classic")
+
+
+def get_subsegments_v2(offset: float, window: float, shift: float, duration: float, min_subsegment_duration: float = 0.01,
+                       decimals: int = 2) -> List[List[float]]:
+    """The later form of upstream's get_subsegments (see SUBSEGMENT_RULE)."""
+    slice_end = offset + duration
+    slices = 1 if min_subsegment_duration <= duration <= shift else int(np.ceil(1 + (duration - window) / shift))
+    if slices == 1:
+        return [[offset, min(duration, window)]] if min(duration, window) >= min_subsegment_duration else []
+    if slices <= 0:
+        return []
+    starts = torch.arange(offset, slice_end, shift)[:slices]
+    durs = window * torch.ones(slices)
+    durs[-1] = min(slice_end - starts[-1], window)
+    durs = torch.round(durs, decimals=decimals)
+    keep = durs >= min_subsegment_duration
+    return torch.stack([starts[keep], durs[keep]], dim=1).tolist()
+
+
 def get_subsegments(offset: float, window: float, shift: float, duration: float) -> List[List[float]]:
     """Sliding windows over one speech region: start_k = offset + k * shift, the last window is cut at
     the region's end.  n = ceil((duration - window) / shift) + 1 (1 if the region is shorter than a window)."""
+    if SUBSEGMENT_RULE == "v2":
+        return get_subsegments_v2(offset, window, shift, duration)
     base = math.ceil((duration - window) / shift)
     count = 1 if base < 0 else base + 1
     region_end = offset + duration
@@ -156,6 +183,11 @@ def subsegment_arrays(offsets: np.ndarray, durations: np.ndarray, window: float,
     order as the per-region Python loop, so every start / duration is bit-identical to it).
     Returns (region index int64 [n], start float64 [n], duration float64 [n]) with windows <= min_subsegment_duration dropped."""
     offsets, durations = np.asarray(offsets, dtype=np.float64), np.asarray(durations, dtype=np.float64)
+    if SUBSEGMENT_RULE == "v2":  # the later rule goes through torch.arange per region (float32 starts): no vectorised twin
+        rows = [(r, st, du) for r, (o, d) in enumerate(zip(offsets.tolist(), durations.tolist()))
+                for st, du in get_subsegments_v2(o, window, shift, d) if du > min_subsegment_duration]
+        return (np.array([x[0] for x in rows], dtype=np.int64), np.array([x[1] for x in rows], dtype=np.float64),
+                np.array([x[2] for x in rows], dtype=np.float64))
     base = np.ceil((durations - window) / shift)
     count = np.where(base < 0, 1, base + 1).astype(np.int64)
     region = np.repeat(np.arange(offsets.shape[0], dtype=np.int64), count)
