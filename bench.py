@@ -345,7 +345,8 @@ def run_b200(args):
         if rank == 0:
             emit({"profiling_run": True, "ms_per_step": dev_ms / args.steps, "note": "not a bench value"})
     elif rank == 0 or shard:
-        # (under --shard every rank has to take part in the collectives of these two extra passes)
+        # (under --shard every rank has to take part in the collectives of these extra passes)
+        diar.run_device(wav_dev=wav_dev, timers=False)  # the side measurements above released the allocator's cache: re-warm it
         diar.run_device(wav_dev=wav_dev, timers=True)
         stage_ms = dict(diar.stage_ms)
         from whisper_nemo_b200 import clustering as _cl
