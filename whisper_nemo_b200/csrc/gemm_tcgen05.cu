@@ -801,18 +801,21 @@ static int make_map(CUtensorMap* map, const void* base, bool bf16, int64_t rows,
 // of y^T for the next product, locally or into every peer (b200d_gemm_epilogue.n_peers).
 constexpr int kSplitKBlocks = 24;
 
+// 1024 threads per 32-row block: the kernel is a pure stream (56 MB of partials per 10 000-row product), and with 256 threads a
+// block the ~2 resident blocks per SM had too few requests in flight (ncu r02: 25 us, 2.4 TB/s).
+constexpr int kFixupThreads = 1024;
+
 template <int B>
-__global__ void __launch_bounds__(256) cheb_fixup_kernel(const float* __restrict__ partial, int nseg, int M, const b200d_gemm_epilogue e,
+__global__ void __launch_bounds__(kFixupThreads) cheb_fixup_kernel(const float* __restrict__ partial, int nseg, int M, const b200d_gemm_epilogue e,
                                                          float* __restrict__ out, int ldo) {
   constexpr int NW = (B == 64) ? 192 : 128;
   constexpr int ROWS = 32;
   __shared__ float ys[ROWS][B + 1];
   const int row0 = blockIdx.x * ROWS;
   const int j = threadIdx.x % B;
-  constexpr int RSTEP = 256 / B;
+  constexpr int RSTEP = kFixupThreads / B;
   const size_t seg_stride = static_cast<size_t>(M) * NW;
   const bool out_everywhere = e.n_peers > 0 && (e.flags & B200D_GEMM_PEER_OUT32) != 0;
-#pragma unroll 2
   for (int r = threadIdx.x / B; r < ROWS; r += RSTEP) {
     const int row = row0 + r;
     float y = 0.f;
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(256) cheb_fixup_kernel(const float* __restrict
   const int n_peers = e.n_peers > 0 ? e.n_peers : 1;
   for (int q = 0; q < n_peers; ++q) {
     __nv_bfloat16* vr = e.n_peers > 0 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(vh) + e.peer_delta[q]) : vh;
-    for (int c = warp; c < B; c += 8) {
+    for (int c = warp; c < B; c += kFixupThreads / 32) {
       __nv_bfloat16 h, m, l;
       split3_bf16(ys[lane][c], h, m, l);
       vr[static_cast<size_t>(c) * e.ldvt + row] = h;
@@ -1036,9 +1039,9 @@ extern "C" int b200d_gemm_f16(const void* A, int32_t lda, const void* W, int32_t
     const int nseg = (kblocks + kSplitKBlocks - 1) / kSplitKBlocks;
     const int blocks = (M + 31) / 32;
     if (N == 192)
-      cheb_fixup_kernel<64><<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(epi->splitk_ws), nseg, M, *epi, reinterpret_cast<float*>(out), ldo);
+      cheb_fixup_kernel<64><<<blocks, kFixupThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(epi->splitk_ws), nseg, M, *epi, reinterpret_cast<float*>(out), ldo);
     else
-      cheb_fixup_kernel<32><<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(epi->splitk_ws), nseg, M, *epi, reinterpret_cast<float*>(out), ldo);
+      cheb_fixup_kernel<32><<<blocks, kFixupThreads, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(epi->splitk_ws), nseg, M, *epi, reinterpret_cast<float*>(out), ldo);
     B200D_CHECK_LAUNCH();
     return B200D_OK;
   }
