@@ -356,7 +356,8 @@ class single_cta_gemms:
     def __enter__(self):
         self.prev = gemm_flags()
         # B200D_PAIR_IN_STREAMS=1 (development): keep the pair kernel inside multi-stream regions -- the round-1 deadlock
-        # did not reproduce in round 2 (profiles/r02_concurrency_*.log); the conservative default stays off
+        # did not reproduce in round 2's runs of tools/concurrency_check.py (their logs were lost with a replaced build machine); the
+        # conservative default stays off
         _tls.gemm_flags = self.prev if os.environ.get("B200D_PAIR_IN_STREAMS") == "1" else self.prev | GEMM_NO_PAIR
         return self
 

@@ -16,7 +16,9 @@ Every rank holds all embeddings (all-gathered by the diarizer) and rows [lo, hi)
                          the result straight into every peer's buffer over NVLink; device-side flag barrier per product
   k-means                replicated (N x k floats)
 
-All of it is bit-for-bit the single-GPU arithmetic (see include/b200d.h), so the labels equal the single-GPU labels.
+All of it is bit-for-bit the single-GPU arithmetic (see include/b200d.h), so the labels equal the single-GPU labels -- with one
+caveat: the sharded solver always takes dense tcgen05 products, while one GPU switches to fp32 CSR gathers for very sparse graphs
+(at most 32 neighbours or 1/64 of a row; clustering._use_csr_products), where the two agree to fp32 rounding instead of bit for bit.
 The small collectives go through a `comm` object: DistComm (torch.distributed, NCCL on the GPUs) or LocalComm (several
 "ranks" as host threads with a stream each on ONE GPU -- how the single-GPU test suite exercises this path).
 """
