@@ -15,7 +15,12 @@
  *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
  *    its name ends in _host; the caller (PyTorch) owns all memory;
  *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
- *    hidden synchronisation, no allocation, no retained pointers;
+ *    allocation, no retained pointers, no process-wide mutable state (kernel
+ *    choice is a per-call flag; one-time kernel attributes are per device).
+ *    Exceptions, each stated at its declaration: b200d_eig_bottomk(_sharded)
+ *    synchronise `stream` once per outer iteration (host decisions on 2 b
+ *    floats); b200d_peer_alloc / b200d_peer_free own the one buffer the
+ *    library allocates (the peer buffer of the multi-GPU solver);
  *  - return 0 on success, a negative B200D_E* code on failure;
  *    b200d_last_error() returns a thread-local message;
  *  - sm_100a only; there is no CPU path.
