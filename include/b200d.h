@@ -327,6 +327,11 @@ int b200d_graph_reach_rank(const void* rank_u16, const void* rankT_u16, int32_t 
 size_t b200d_eigvals_workspace_bytes(int32_t batch, int32_t n);
 int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t n_low, float* evals, void* ws, size_t ws_bytes,
                           void* stream);
+/* The same for a SUBSET of a larger batch: layout_batch >= batch is the size of the batch whose per-matrix work split (and with it
+ * the fp32 reduction order) is used, so the subset's eigenvalues are bit for bit those the full batch gives -- the p values of the
+ * NME sweep dealt to the ranks of a row-sharded recording ("NME sweep").                                   */
+int b200d_eigvals_batched_layout(float* a, int32_t batch, int32_t layout_batch, int32_t n, int32_t n_low, float* evals, void* ws,
+                                 size_t ws_bytes, void* stream);
 
 /* Top-p binarisation of the full matrix (getAffinityGraphMat on the N x N fused affinity):
  * a[i][j] = 0.5*([j in top_p(row i)] + [i in top_p(row j)]), diagonal zeroed, as __nv_bfloat16 [n][lda]

@@ -113,6 +113,33 @@ def test_sharded_eigensolver_equals_single_gpu(dev, world, k, monkeypatch):
         assert torch.equal(x, want)
 
 
+def test_eigenvalues_of_a_subset_with_the_full_batch_layout(dev):
+    """b200d_eigvals_batched_layout: every third Laplacian of a 30-matrix sweep diagonalised alone gives bit for bit the eigenvalues
+    the full batch gives (the property that lets the ranks of a row-sharded recording share the NME sweep)."""
+    from whisper_nemo_b200 import _cabi
+    from whisper_nemo_b200._cabi import ptr
+
+    g = torch.Generator().manual_seed(4)
+    n, batch, n_low = 515, 30, 9
+    a = torch.rand(batch, n, n, generator=g)
+    a = (a + a.transpose(1, 2)).to(dev).contiguous()
+    lib = _cabi.load()
+
+    def run(mats, layout):
+        m = mats.clone()
+        ws = torch.empty(int(lib.b200d_eigvals_workspace_bytes(m.shape[0], n)), dtype=torch.uint8, device=dev)
+        out = torch.empty(m.shape[0], n_low + 1, dtype=torch.float32, device=dev)
+        _cabi.call("b200d_eigvals_batched_layout", ptr(m), m.shape[0], layout, n, n_low, ptr(out), ptr(ws), ws.numel(), _cabi._stream())
+        torch.cuda.synchronize()
+        return out
+
+    full = run(a, batch)
+    for r in range(3):
+        assert torch.equal(run(a[r::3].contiguous(), batch), full[r::3])
+    ref = torch.linalg.eigvalsh(a[:2].double().cpu())
+    assert (full[:2, :n_low].double().cpu() - ref[:, :n_low]).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_row_sharded_clustering_gives_single_gpu_labels(dev, world):
     """forward_infer with everything quadratic row-sharded: same speaker count, p-hat and labels as SpeakerClustering.forward_infer

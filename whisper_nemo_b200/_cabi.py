@@ -145,6 +145,7 @@ _SIGNATURES = {
     "b200d_graph_reach_rank": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200d_eigvals_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "b200d_eigvals_batched": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200d_eigvals_batched_layout": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200d_topp_binarize": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200d_gram_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "b200d_gram": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -226,7 +227,7 @@ KERNELS_PER_CALL = {  # (a split-K CHEB b200d_gemm_f16 call launches 2; the solv
     "b200d_featurize_windows": 3, "b200d_mel_stream": 1, "b200d_depthwise_conv": 1, "b200d_gemm_f16": 1, "b200d_time_stats": 1, "b200d_se_mean_from_colsum": 1, "b200d_se_apply_relu": 1, "b200d_se_apply_relu_stats": 1,
     "b200d_attn_pool": 1, "b200d_l2_normalize": 1, "b200d_cos_affinity": 3, "b200d_fuse_scales": 1, "b200d_interp_scales": 1,
     "b200d_masked_rowsum": 1, "b200d_gather_segment_mean": 1, "b200d_row_rank": 1, "b200d_laplacian_from_rank": 1, "b200d_graph_reach_rank": 1,
-    "b200d_eigvals_batched": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
+    "b200d_eigvals_batched": 2, "b200d_eigvals_batched_layout": 2, "b200d_topp_binarize": 3, "b200d_gram": 2, "b200d_small_eig": 1, "b200d_right_mul": 1,
     "b200d_resid_norms": 2, "b200d_kmeans": 1, "b200d_csr_from_dense": 3, "b200d_spmm_cheb": 1,
     "b200d_cos_affinity_rows": 3, "b200d_fuse_scales_rows": 1, "b200d_topp_select_rows": 1, "b200d_sym_combine_rows": 1, "b200d_peer_barrier": 1,
     "b200d_peer_alloc": 0, "b200d_peer_open": 0, "b200d_peer_close": 0, "b200d_peer_free": 0, "b200d_peer_status": 0,

@@ -181,10 +181,14 @@ class NMESC:
 
     def __init__(self, mat: torch.Tensor, max_num_speakers: int = 10, max_rp_threshold: float = 0.15, sparse_search: bool = True,
                  sparse_search_volume: int = 30, nme_mat_size: int = 512, use_subsampling_for_nme: bool = True,
-                 fixed_thres: float = -1.0, maj_vote_spk_count: bool = False, presampled_ratio: Optional[int] = None):
+                 fixed_thres: float = -1.0, maj_vote_spk_count: bool = False, presampled_ratio: Optional[int] = None, comm=None):
         """presampled_ratio: `mat` already IS the strided subsample mat_full[::r, ::r] with r = presampled_ratio (the
-        row-sharded path gathers only those rows from the ranks); p-hat is still reported on the full matrix's scale."""
+        row-sharded path gathers only those rows from the ranks); p-hat is still reported on the full matrix's scale.
+        comm (rowshard.DistComm / LocalComm): the p values of the sweep are dealt to the communicator's ranks -- every rank
+        builds and diagonalises the Laplacians of its own p values with the single-GPU reduction layout
+        (b200d_eigvals_batched_layout) and the eigenvalues are all-gathered: bit for bit the replicated sweep."""
         self.presampled_ratio = presampled_ratio
+        self.comm = comm
         self.max_num_speakers = int(max_num_speakers)
         self.max_rp_threshold = max_rp_threshold
         self.use_subsampling_for_nme = use_subsampling_for_nme
@@ -230,14 +234,24 @@ class NMESC:
         m = min(self.max_num_speakers, n - 1)  # gaps[:max_num_speakers] needs lambda_0 .. lambda_m
         n_low = m + 1
         evals_all = []
+        world = self.comm.world if self.comm is not None else 1
         for b0 in range(0, np_, 64):
-            pl = p_list[b0 : b0 + 64]
-            lap = torch.empty(len(pl), n, n, dtype=torch.float32, device=dev)
-            _cabi.call("b200d_laplacian_from_rank", ptr(rank), ptr(rankT), n, _i32_array(pl), len(pl), ptr(lap), _s())
-            ws_bytes = _cabi.load().b200d_eigvals_workspace_bytes(len(pl), n)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            pl_all = p_list[b0 : b0 + 64]
+            mine = list(range(len(pl_all)))[self.comm.rank :: world] if world > 1 else list(range(len(pl_all)))
+            pl = [pl_all[i] for i in mine]
             evals = torch.empty(len(pl), n_low + 1, dtype=torch.float32, device=dev)
-            _cabi.call("b200d_eigvals_batched", ptr(lap), len(pl), n, n_low, ptr(evals), ptr(ws), ws_bytes, _s())
+            if pl:
+                lap = torch.empty(len(pl), n, n, dtype=torch.float32, device=dev)
+                _cabi.call("b200d_laplacian_from_rank", ptr(rank), ptr(rankT), n, _i32_array(pl), len(pl), ptr(lap), _s())
+                ws_bytes = _cabi.load().b200d_eigvals_workspace_bytes(len(pl), n)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _cabi.call("b200d_eigvals_batched_layout", ptr(lap), len(pl), len(pl_all), n, n_low, ptr(evals), ptr(ws), ws_bytes, _s())
+            if world > 1:  # rank r holds the p values r, r + world, ...: gather in rank order, then back to sweep order
+                counts = [len(range(r, len(pl_all), world)) for r in range(world)]
+                gathered = self.comm.all_gather_rows(evals, counts)
+                order = [i for r in range(world) for i in range(r, len(pl_all), world)]
+                evals = torch.empty_like(gathered)
+                evals[torch.tensor(order, device=dev)] = gathered
             evals_all.append(evals)
         evals = torch.cat(evals_all).cpu()  # [np, n_low + 1]  (the sweep's only device->host read)
         est_num_of_spk_list, eig_ratio_list = nme_ratios(evals, self.p_value_list, n, self.max_num_speakers, self.eps)

@@ -267,8 +267,16 @@ extern "C" size_t b200d_eigvals_workspace_bytes(int32_t batch, int32_t n) {
 
 extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t n_low, float* evals, void* ws, size_t ws_bytes,
                                      void* stream) {
+  return b200d_eigvals_batched_layout(a, batch, batch, n, n_low, evals, ws, ws_bytes, stream);
+}
+
+// layout_batch >= batch: every matrix is tridiagonalised by as many CTAs -- i.e. with the reduction order -- as in a launch of
+// layout_batch matrices, so a SUBSET of a batch computed alone (the p values of the NME sweep dealt to the ranks of a
+// row-sharded recording) gives bit for bit the eigenvalues the full batch gives.
+extern "C" int b200d_eigvals_batched_layout(float* a, int32_t batch, int32_t layout_batch, int32_t n, int32_t n_low, float* evals, void* ws,
+                                            size_t ws_bytes, void* stream) {
   B200D_CHECK_ARG(a && evals && ws);
-  B200D_CHECK_ARG(batch > 0 && batch <= kNumSMs && n >= 2 && n <= kMaxEigN && n_low >= 1 && n_low <= n);
+  B200D_CHECK_ARG(batch > 0 && layout_batch >= batch && layout_batch <= kNumSMs && n >= 2 && n <= kMaxEigN && n_low >= 1 && n_low <= n);
   static int blocks_per_sm = 0;  // occupancy of tridiag_kernel: a property of the kernel and sm_100, the same on every device
   if (ws_bytes < b200d_eigvals_workspace_bytes(batch, n))
     return b200d::set_error(B200D_EWORKSPACE, "%s: workspace too small%s", "b200d_eigvals_batched");
@@ -293,7 +301,7 @@ extern "C" int b200d_eigvals_batched(float* a, int32_t batch, int32_t n, int32_t
     B200D_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tridiag_kernel, kTriThreads, 4 * kMaxEigN * sizeof(float)));
     blocks_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);
   }
-  int cpm = tridiag_cpm(batch, blocks_per_sm);
+  int cpm = tridiag_cpm(layout_batch, blocks_per_sm);
   void* args[] = {&a, &n_arg, &cpm, &d, &e, &pbuf, &bar};
   B200D_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tridiag_kernel), dim3(batch * cpm), dim3(kTriThreads), args, smem, s));
   const int wanted = n_low + 1;

@@ -8,7 +8,9 @@ Every rank holds all embeddings (all-gathered by the diarizer) and rows [lo, hi)
 
   per-scale cosine rows  b200d_cos_affinity_rows      + all-reduce of the per-scale (min, max)            [2 S floats]
   fused affinity rows    b200d_fuse_scales_rows
-  NME sweep              the strided subsample's rows gathered from their owners (<= 1024^2 floats), sweep replicated
+  NME sweep              the strided subsample's rows gathered from their owners (<= 1024^2 floats); the p values of the sweep
+                         dealt to the ranks (b200d_eigvals_batched_layout: the single-GPU reduction order) + all-gather of
+                         the eigenvalues [~10 floats per p]
   top-p binarisation     b200d_topp_select_rows       + all-gather of each row's threshold / tie cut-off   [8 B per row]
                          b200d_sym_combine_rows (transposed term from the symmetric entry, no all-to-all)
                          + all-gather of the degrees                                                       [4 B per row]
@@ -310,7 +312,7 @@ def forward_infer_rows(sc, comm, embeddings_in_scales: List[torch.Tensor], times
     sub = comm.all_gather_rows(sub_rows, counts).contiguous()
     nmesc = cl.NMESC(sub, max_num_speakers=max_num_speakers if oracle_num_speakers <= 0 else oracle_num_speakers, max_rp_threshold=max_rp_threshold,
                      sparse_search=sc.sparse_search, sparse_search_volume=sparse_search_volume, fixed_thres=fixed_thres,
-                     nme_mat_size=sc.nme_mat_size, maj_vote_spk_count=sc.maj_vote_spk_count, presampled_ratio=ratio)
+                     nme_mat_size=sc.nme_mat_size, maj_vote_spk_count=sc.maj_vote_spk_count, presampled_ratio=ratio, comm=comm)
     est_num_of_spk, p_hat_value = nmesc.forward()
     n_clusters = int(oracle_num_speakers) if oracle_num_speakers > 0 else int(est_num_of_spk)
     sc.debug = {"est_num_of_spk": int(est_num_of_spk), "p_hat": int(p_hat_value), "n_clusters": n_clusters,
