@@ -417,3 +417,17 @@ def test_later_subsegment_rule_matches_the_oracle_switch(monkeypatch):
             want += [(r, st, du) for st, du in segs if du > su.MIN_SUBSEGMENT_DURATION]
         region, start, dur = su.subsegment_arrays(offs, durs, w, s)
         assert region.tolist() == [x[0] for x in want] and start.tolist() == [x[1] for x in want] and dur.tolist() == [x[2] for x in want]
+
+
+def test_round_robin_gather_order_restores_the_sweep():
+    """The NME sweep's p values are dealt round-robin to the ranks and their eigenvalues gathered in rank order: the inverse
+    permutation puts every row back where the replicated sweep has it (uneven counts and empty ranks included)."""
+    for n_items, world in [(30, 8), (30, 2), (5, 8), (1, 4), (64, 3)]:
+        counts, order = sharding.round_robin_counts_and_order(n_items, world)
+        assert sum(counts) == n_items and sorted(order) == list(range(n_items))
+        per_rank = [list(range(n_items))[r::world] for r in range(world)]
+        assert counts == [len(x) for x in per_rank]
+        gathered = torch.tensor([i for part in per_rank for i in part], dtype=torch.float32)
+        out = torch.empty_like(gathered)
+        out[torch.tensor(order)] = gathered
+        assert out.tolist() == [float(i) for i in range(n_items)]

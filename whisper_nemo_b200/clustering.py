@@ -247,9 +247,10 @@ class NMESC:
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 _cabi.call("b200d_eigvals_batched_layout", ptr(lap), len(pl), len(pl_all), n, n_low, ptr(evals), ptr(ws), ws_bytes, _s())
             if world > 1:  # rank r holds the p values r, r + world, ...: gather in rank order, then back to sweep order
-                counts = [len(range(r, len(pl_all), world)) for r in range(world)]
+                from .sharding import round_robin_counts_and_order
+
+                counts, order = round_robin_counts_and_order(len(pl_all), world)
                 gathered = self.comm.all_gather_rows(evals, counts)
-                order = [i for r in range(world) for i in range(r, len(pl_all), world)]
                 evals = torch.empty_like(gathered)
                 evals[torch.tensor(order, device=dev)] = gathered
             evals_all.append(evals)

@@ -60,6 +60,14 @@ def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
     return torch.cat(pieces, dim=0)
 
 
+def round_robin_counts_and_order(n_items: int, world: int) -> Tuple[List[int], List[int]]:
+    """Items dealt round-robin (item i to rank i % world) and gathered in rank order: (items per rank, the original index of
+    every gathered row) -- `out[order[g]] = gathered[g]` restores the original order (the NME sweep's p values)."""
+    counts = [len(range(r, n_items, world)) for r in range(world)]
+    order = [i for r in range(world) for i in range(r, n_items, world)]
+    return counts, order
+
+
 def chunks_of_rank(n_chunks: int, rank: int, world: int) -> List[int]:
     """Long-form chunks are dealt round-robin: chunk w belongs to rank w % world."""
     return [w for w in range(n_chunks) if w % world == rank]
