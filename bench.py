@@ -338,8 +338,17 @@ def run_b200(args):
     _progress("diarize() calls done")
     strong = strong_full = None
     if world > 1 and not shard and not batch_mode and not args.no_strong and not args.profiling:
-        strong = strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch)
-        strong_full = strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch, fullmatrix=True)
+        # a failure of one of these side measurements (e.g. CUDA IPC refused on a box) must not take the main line with it: it is
+        # recorded in the object instead (the product itself raises -- this guard is the benchmark's only)
+        def guarded(**kw):
+            try:
+                return strong_single_recording(args, weights, rank, world, dev, barrier, all_max, torch, **kw)
+            except Exception as exc:  # noqa: BLE001
+                _progress(f"strong measurement failed: {exc!r}")
+                return {"error": repr(exc)[:300]} if rank == 0 else None
+
+        strong = guarded()
+        strong_full = guarded(fullmatrix=True)
     # ---- untimed extras on rank 0: per-stage times, per-kernel roofline
     if args.profiling:
         if rank == 0:
