@@ -171,3 +171,34 @@ def test_eig_bottomk_queries():
     sparse = lib.b200d_eig_bottomk_workspace_bytes(10000, 50, 11, None)
     assert dense > 4 * 10000 * 64 * 4 + 2 * 192 * 10000 * 2 and 4 * 10000 * 64 * 4 < sparse < dense  # CSR lists (22 per row) instead of two bf16 operand buffers
     assert lib.b200d_eig_bottomk_workspace_bytes(10000, 60, 0, None) == 0
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """Every structure that crosses the C ABI by pointer: sizeof and the offset of every field as gcc lays them out from
+    include/b200d.h equal the ctypes mirror in _cabi.py (a drifted field would silently shift everything behind it)."""
+    import ctypes
+    import subprocess
+
+    from whisper_nemo_b200 import _cabi
+
+    pairs = {"b200d_gemm_epilogue": _cabi.GemmEpilogue, "b200d_peer_group": _cabi.PeerGroup, "b200d_eig_options": _cabi.EigOptions,
+             "b200d_eig_stats": _cabi.EigStats, "b200d_titanet_desc": _cabi.TitaNetDesc, "b200d_profile_span": _cabi.ProfileSpan}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200d.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    include = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call(["gcc", "-I", include, str(src), "-o", str(exe)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, val = ln.split()
+        got[(cname, field)] = int(val)
+    for cname, cls in pairs.items():
+        assert got[(cname, "sizeof")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
