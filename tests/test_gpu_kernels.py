@@ -475,3 +475,25 @@ def test_titanet_forward_composite_equals_the_stepwise_orchestration(dev, weight
     torch.cuda.synchronize()
     assert "encoder" in taps
     assert torch.equal(got, want)
+
+
+def test_plain_c_host_drives_the_clustering_half(dev, tmp_path):
+    """tools/cabi_host_example.c: a host that is not Python (plain C, include/b200d.h + the CUDA runtime, its own cudaMalloc'ed
+    buffers) runs affinity -> fusion -> top-p graph -> b200d_eig_bottomk -> k-means through the C ABI and recovers planted
+    clusters exactly (the boundary is the C ABI, not the Python wrapper)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this host")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    lib_dir = os.path.join(root, "whisper_nemo_b200")
+    exe = tmp_path / "cabi_host"
+    subprocess.check_call(["gcc", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                           os.path.join(root, "tools", "cabi_host_example.c"), "-o", str(exe), "-L", lib_dir, "-lb200d",
+                           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", f"-Wl,-rpath,{lib_dir}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"])
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    print(run.stdout.strip())
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "labels match the planted clusters on 3000 of 3000 points" in run.stdout
