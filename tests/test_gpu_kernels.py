@@ -481,6 +481,7 @@ def test_plain_c_host_drives_the_clustering_half(dev, tmp_path):
     """tools/cabi_host_example.c: a host that is not Python (plain C, include/b200d.h + the CUDA runtime, its own cudaMalloc'ed
     buffers) runs affinity -> fusion -> top-p graph -> b200d_eig_bottomk -> k-means through the C ABI and recovers planted
     clusters exactly (the boundary is the C ABI, not the Python wrapper)."""
+    import os
     import shutil
     import subprocess
 
